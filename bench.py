@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the RQS-flow hot path (BASELINE.json metric: RQS-flow samples/sec, one forward
++ one inverse pass, each with log-det, d=64, 8 layers, K=8 bins, batch 2^20 per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); the batch is sharded by rows,
+every rank evaluates 2^20 rows (weak scaling), no data-path collective.  Prints ONE JSON line
+on rank 0.  `--impl reference` times the CPU restatement of the reference (oracle/) on the
+host cores (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rqs_flow_samples_per_sec_fwd_inv_logdet"
+UNIT = "samples/s"
+D, SIZE, DIM, LAYERS, KBINS, TAIL = 64, 32, 2, 8, 8, 3.0
+ROW_BYTES_PER_LAYER = 32 * 23 * 4 + 64 * 4 + 64 * 4 + 8      # 3,464 B
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=1 << 20, help="rows per GPU")
+    ap.add_argument("--hidden", type=int, default=128, help="conditioner hidden width")
+    ap.add_argument("--arith", default="hybrid", choices=["hybrid", "exact", "fast"])
+    ap.add_argument("--conditioner", default="auto", choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"cfg2: RQS coupling flow d=64, 8 x NSF_CL(size=32,dim=2,K=8,B=3,H={a.hidden}), batch {a.batch}/GPU"
+
+
+def specs():
+    return [dict(type="NSF_CL", size=SIZE, dim=DIM, K=KBINS, B=TAIL, mask=[i % 2]) for i in range(LAYERS)]
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle (torch-CPU restatement of the reference) on the host cores
+# ------------------------------------------------------------------------------------------
+def make_state_dict(hidden):
+    """Reference-initialised weights (nn.Linear default init under manual_seed(0)), built
+    without touching the GPU so both arms share them."""
+    import torch.nn as nn
+    torch.manual_seed(0)
+    sd = {}
+    for i in range(LAYERS):
+        net = nn.Sequential(nn.Linear(SIZE, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh(),
+                            nn.Linear(hidden, 23 * SIZE))
+        for k, v in net.state_dict().items():
+            sd[f"flows.{i}.psi.network.{k}"] = v.detach().clone()
+    return sd
+
+
+def cpu_pass(sd, rows, repeats=1):
+    from oracle import nf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = torch.randn(rows, D, generator=torch.Generator().manual_seed(1))
+    z = torch.randn(rows, D, generator=torch.Generator().manual_seed(2))
+    sp = specs()
+    best = float("inf")
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.flow_fwd_inv_pass(sp, sd, x, z)
+            best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_baseline(a, sd, budget_s=12.0):
+    rows = a.cpu_rows
+    if rows <= 0:
+        probe_rows = 2048
+        t = cpu_pass(sd, probe_rows)
+        rows = int(max(2048, min(65536, probe_rows * budget_s / max(t, 1e-3))))
+        rows = (rows // 1024) * 1024
+    t = cpu_pass(sd, rows)
+    return {"value": rows / t, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{rows} rows of the same workload (one fwd+inv pass of oracle/nf_oracle.py, torch CPU fp32, "
+                      f"{torch.get_num_threads()} threads), {t:.2f} s"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sd = make_state_dict(a.hidden)
+    rows = a.cpu_rows if a.cpu_rows > 0 else 8192
+    for _ in range(a.warmup):
+        cpu_pass(sd, min(rows, 1024))
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cpu_pass(sd, rows)
+    dt = (time.perf_counter() - t0) / max(1, a.steps)
+    val = rows / dt
+    cores = os.cpu_count() or 1
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "hidden": a.hidden,
+                       "note": "CPU arm: each step is a bounded sample of the workload"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{rows} rows per step, torch CPU fp32, {torch.get_num_threads()} threads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [t.strip() for t in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------
+def run_native(a):
+    import torch.distributed as dist
+    from normalizingflow_b200 import _lib, _ops
+    from normalizingflow_b200.flows import NSF_CL
+    from normalizingflow_b200.models import GaussianPrior, NormalizingFlowModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cond = a.conditioner
+    if cond == "auto":
+        cond = "bf16" if _lib.have("nfk_linear_bf16") else "fp32"
+    sd = make_state_dict(a.hidden)
+    flows = [NSF_CL(SIZE, dim=DIM, K=KBINS, B=TAIL, hidden_dim=a.hidden, mask=[i % 2], arith=a.arith)
+             for i in range(LAYERS)]
+    for f in flows:
+        f.psi.precision = cond
+    model = NormalizingFlowModel(GaussianPrior(D, device=dev), flows, device=dev)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+
+    N = a.batch
+    # each rank owns rows [rank*N, (rank+1)*N) of the global batch: seeded per rank
+    gx = torch.Generator().manual_seed(1 + 1000 * rank)
+    gz = torch.Generator().manual_seed(2 + 1000 * rank)
+    hx = torch.randn(N, D, generator=gx).pin_memory()
+    hz = torch.randn(N, D, generator=gz).pin_memory()
+    x = hx.to(dev)
+    z = hz.to(dev)
+
+    def step():
+        with torch.no_grad():
+            zz, plp, ld = model.forward(x)
+            xx, ldi = model.inverse(z)
+        return zz, plp, ld, xx, ldi
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, a.warmup)):
+        step()
+    barrier()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    timer = _ops.KernelTimer()
+    _ops.KERNEL_TIMER = timer
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    _ops.KERNEL_TIMER = None
+    ksum = timer.summary()
+    clk = clocks.stop() if rank == 0 else None
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / a.steps
+    value = world * N / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers
+    e2e = None
+    if not a.no_e2e:
+        out_lp = torch.empty(N, dtype=torch.float32).pin_memory()
+        out_x = torch.empty(N, D, dtype=torch.float32).pin_memory()
+        out_lpx = torch.empty(N, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            xd = hx.to(dev, non_blocking=True)
+            zd = hz.to(dev, non_blocking=True)
+            lp = model.evaluate(xd)                                    # log p(x): forward + prior
+            with torch.no_grad():
+                xs, ldi = model.inverse(zd)                            # sampling direction
+                lpx = model.prior.log_prob(zd) - ldi
+            out_lp.copy_(lp, non_blocking=True)
+            out_x.copy_(xs, non_blocking=True)
+            out_lpx.copy_(lpx, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(a.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ems = max(e0.elapsed_time(e1), wall)
+        t = torch.tensor([ems], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t.item()) / a.steps
+        e2e = {"value": world * N / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems,
+               "h2d_bytes_per_step": 2 * N * D * 4, "d2h_bytes_per_step": N * D * 4 + 2 * N * 4,
+               "api": "NormalizingFlowModel.evaluate(x) + NormalizingFlowModel.inverse(z) on pinned host buffers"}
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        n_l, k_ms = ksum.get("rqs_coupling", (0, 0.0))
+        avg_ms = k_ms / max(1, n_l)
+        achieved = ROW_BYTES_PER_LAYER * N / (avg_ms * 1e-3) / 1e9 if n_l else None
+        roofline = {"bound": "hbm", "kernel": "rqs_coupling_tiled", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ROW_BYTES_PER_LAYER * N, "avg_launch_ms": avg_ms,
+                    "launches_timed": n_l, "share_of_step": (k_ms / ms) if ms else None}
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                roofline["traffic"] = json.load(open(tp)).get("rqs_coupling_tiled_bytes_per_launch")
+            except Exception:
+                pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": max(3, a.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32" if cond == "fp32" else "f32 transforms / bf16 conditioner GEMMs",
+                "data": "synthetic",
+                "config": {"workload": workload_name(a), "hidden": a.hidden, "arith": a.arith, "conditioner": cond,
+                           "global_batch": world * N, "parallelism": f"batch-sharded x{world}",
+                           "l2": "inputs larger than L2 (x 268 MB, spline params 3.1 GB per layer)"},
+                "roofline": roofline, "clocks": clk, "gpu_launches": launches, "e2e": e2e}
+        if not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(a, sd)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+/* nfk.h — C-ABI of libnfk.so, the B200 (sm_100a) implementation of the normalizing-flow
+ * transform hot path of sherryli59/NormalizingFlow.
+ *
+ * The reference exposes no FFI; its boundary for this path is the Python class protocol
+ *   layer.forward(x) -> (z, log_det),  layer.inverse(z) -> (x, log_det)
+ * (reference nf/models.py:16-18, :25-27).  Each entry point below replaces the ATen op
+ * chain behind one of those methods; the citation on every function names it.
+ *
+ * Conventions (all functions)
+ *   - return 0 on success, non-zero NFK_E* otherwise; never throw/abort across the ABI;
+ *     nfk_last_error() returns a thread-local message for the last failure;
+ *   - every pointer is a DEVICE pointer on the device that owns `stream`, 16-byte aligned
+ *     base, row-major contiguous fp32 unless stated otherwise; the caller allocates and
+ *     owns all buffers, the callee never allocates, frees or synchronises;
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - `mask` arguments are HOST pointers to small int32 arrays;
+ *   - sm_100a only: there is no CPU path and no other-arch path.
+ */
+#ifndef NFK_H_
+#define NFK_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFK_ABI_VERSION 1
+
+enum {
+  NFK_OK = 0,
+  NFK_EINVAL = 1,   /* bad shape / argument (Python wrapper raises ValueError, cf. nf/utils.py:64-71) */
+  NFK_ECUDA = 2,    /* a CUDA runtime call failed */
+  NFK_EUNSUPPORTED = 3
+};
+
+/* arithmetic flavour of the spline kernels */
+enum {
+  NFK_ARITH_EXACT = 0,  /* op-for-op the rounding sequence of the reference's ATen CUDA chain:
+                           bins, outputs and per-element log-dets bit-identical to it */
+  NFK_ARITH_HYBRID = 1, /* searched-side knot chain EXACT (bins bit-identical), the rest
+                           FMA-contracted with MUFU ex2/lg2/rcp (a few ulp) -- the default */
+  NFK_ARITH_FAST = 2    /* all approximations; a bin may differ within a few ulp of a knot */
+};
+
+int nfk_abi_version(void);
+const char* nfk_last_error(void);
+/* number of kernels launched by this library since load (bench.py "gpu_launches") */
+int64_t nfk_launch_count(void);
+/* association order of the EXACT cumsum (torch.cumsum on CUDA, nf/utils.py:75):
+ * 0 sequential, 1 Sklansky, 2 up-sweep/down-sweep (ATen ScanUtils.cuh).  Process-global. */
+int nfk_set_scan_order(int order);
+int nfk_get_scan_order(void);
+/* override the tile geometry of nfk_rqs_coupling (0 = automatic): rows per tile (multiple of
+ * 4), threads per CTA (multiple of 32, <= 640), pipeline stages, CTAs per SM.  For tuning. */
+int nfk_set_tuning(int rows_per_tile, int threads, int stages, int ctas_per_sm);
+/* test hook: knots [M, K+1] of one side from logits [M, K] (layer_norm != 0: apply the
+ * layer's 2B*softmax first).  nf/flows.py:233-234 + nf/utils.py:73-79. */
+int nfk_debug_knots(const float* logits, float* knots, int64_t M, int K, float B, int layer_norm,
+                    int exact, void* stream);
+
+/* ---- RQS coupling: replaces NSF_CL.forward/inverse after `psi`
+ *      (nf/flows.py:232-239, :246-253) + unconstrained_RQS/RQS/searchsorted (nf/utils.py:20-152).
+ * x [N, size*dim]; params [N, F_t, 3K-1] raw conditioner output, F_t = size*(dim-n_mask);
+ * out [N, size*dim] in the reference's column order (conditioning columns first inside each
+ * dim-group); logdet [N] (overwritten, or += when accumulate != 0); bins [N, F_t] int8, may
+ * be NULL (-1 marks the identity tails). */
+int nfk_rqs_coupling(const float* x, const float* params, float* out, float* logdet,
+                     int8_t* bins, int64_t N, int size, int dim, const int32_t* mask,
+                     int n_mask, int K, float B, int inverse, int accumulate, int arith,
+                     void* stream);
+
+/* backward of the above: given grad_out [N, size*dim] and grad_logdet [N] (may be NULL = 0)
+ * writes grad_x [N, size*dim] (w.r.t. ALL input columns, excluding the path through the
+ * conditioner) and grad_params [N, F_t, 3K-1].  Replaces autograd through the same chain. */
+int nfk_rqs_coupling_bwd(const float* x, const float* params, const float* grad_out,
+                         const float* grad_logdet, float* grad_x, float* grad_params,
+                         int64_t N, int size, int dim, const int32_t* mask, int n_mask,
+                         int K, float B, int inverse, void* stream);
+
+/* ---- free-function spline: replaces unconstrained_RQS (nf/utils.py:27-56) on
+ * inputs [M], W,H [M,K], D [M,K-1] (already layer-normalised once) -> out [M], lad [M]. */
+int nfk_unconstrained_rqs(const float* inputs, const float* W, const float* H, const float* D,
+                          float* out, float* lad, int8_t* bins, int64_t M, int K, float B,
+                          int inverse, int arith, void* stream);
+
+/* ---- affine half-coupling: y = t + v*exp(s) (forward) or (v - t)*exp(-s) (inverse),
+ * logdet (+)= +-sum_j s.  Replaces nf/flows.py:56, :59, :61-62 and :69, :72, :74-75.
+ * v is read from x[:, v_off : v_off+h] (row stride ld_x), s,t are [N,h] contiguous, y is
+ * written to out[:, y_off : y_off+h] (row stride ld_out). */
+int nfk_affine_halfcoupling(const float* x, int64_t ld_x, int v_off, const float* s,
+                            const float* t, float* out, int64_t ld_out, int y_off,
+                            float* logdet, int64_t N, int h, int inverse, int accumulate,
+                            void* stream);
+int nfk_affine_halfcoupling_bwd(const float* x, int64_t ld_x, int v_off, const float* s,
+                                const float* t, const float* grad_y, int64_t ld_gy, int gy_off,
+                                const float* grad_logdet, float* grad_v, int64_t ld_gv,
+                                int gv_off, float* grad_s, float* grad_t, int64_t N, int h,
+                                int inverse, void* stream);
+
+/* ---- planar stack: L tanh planar layers applied in sequence in ONE pass over x.
+ * Replaces L calls of Planar.forward (nf/flows_1.py:42-60).  w,u [L,d], b [L];
+ * nfk_planar_prepare computes the parameter-only terms uhat [L,d] (flows_1.py:51-53) and
+ * wuhat [L] = w_l . uhat_l once; nfk_planar_stack then writes out [N,d] and
+ * logdet [N] (+)= sum over layers of log(|1 + (1-tanh^2)(w.uhat)| + 1e-4). */
+int nfk_planar_prepare(const float* w, const float* u, float* uhat, float* wuhat, int d, int L,
+                       void* stream);
+int nfk_planar_stack(const float* x, const float* w, const float* uhat, const float* wuhat,
+                     const float* b, float* out, float* logdet, int64_t N, int d, int L,
+                     int accumulate, void* stream);
+/* backward: recomputes the forward layer by layer; grad_w/grad_uhat [L,d], grad_b/grad_wuhat
+ * [L] are ACCUMULATED with atomics into zero-initialised buffers (the chain from uhat, wuhat to
+ * u, w is parameter-sized and stays in the host wrapper). */
+int nfk_planar_stack_bwd(const float* x, const float* w, const float* uhat, const float* wuhat,
+                         const float* b, const float* grad_out, const float* grad_logdet,
+                         float* grad_x, float* grad_w, float* grad_uhat, float* grad_b,
+                         float* grad_wuhat, int64_t N, int d, int L, void* stream);
+
+/* ---- radial layer (nf/flows_1.py:85-97).
+ * per_sample == 0: reference behaviour, r = ||x - x0||_F over the WHOLE batch; the caller
+ *   provides sumsq (device scalar, sum of squares, already all-reduced across ranks if the
+ *   batch is sharded) computed with nfk_radial_sumsq; logdet gets ONE value (logdet[0]).
+ * per_sample != 0: r is the per-row norm and logdet is [N]. */
+int nfk_radial_sumsq(const float* x, const float* x0, float* sumsq /*zeroed*/, int64_t N, int d,
+                     void* stream);
+int nfk_radial(const float* x, const float* x0, const float* log_alpha, const float* beta,
+               const float* sumsq, float* out, float* logdet, int64_t N, int d, int per_sample,
+               int accumulate, void* stream);
+
+/* ---- log-prob reduction: out[n] = -0.5*sum_j z[n,j]^2/var - 0.5*d*log(2*pi*var) (+ add[n]).
+ * Replaces prior.log_prob + the additions at nf/models.py:19-20, :34, :39. */
+int nfk_gauss_logprob(const float* z, const float* add /*nullable*/, float add_sign, float* out,
+                      int64_t N, int d, float var, void* stream);
+
+/* ---- conditioner MLP layer: Y = act(X W^T + b).  Replaces one nn.Linear (+Tanh) of FCNN
+ * (nf/flows.py:26-35).  X [M, K] with row stride ldx (lets the caller pass a strided column
+ * gather), W [Nout, K] row-major (nn.Linear layout), b [Nout], Y [M, Nout] contiguous.
+ * act: 0 = identity, 1 = tanh.  fp32 CUDA-core kernel (parity mode). */
+int nfk_linear_f32(const float* X, int64_t ldx, const float* W, const float* b, float* Y,
+                   int64_t M, int K, int Nout, int act, void* stream);
+/* generic fp32 GEMM used by the conditioner backward: C[M,N] (+)= op(A) op(B),
+ * ta/tb: 0 = as stored row-major [M,K]/[K,N], 1 = stored transposed ([K,M]/[N,K]). */
+int nfk_gemm_f32(const float* A, int64_t lda, int ta, const float* Bm, int64_t ldb, int tb,
+                 float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate,
+                 void* stream);
+
+/* bf16 tensor-core (tcgen05 + TMEM + TMA) layer: X,W bf16, fp32 accumulate, bias fp32,
+ * Y bf16 (out_f32 == 0) or fp32 (out_f32 != 0).  K % 16 == 0 (pad), rows/cols arbitrary. */
+int nfk_linear_bf16(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* b,
+                    void* Y, int64_t ldy, int64_t M, int K, int Nout, int act, int out_f32,
+                    void* stream);
+
+/* x[:, cols] gather -> dense fp32 or bf16 [N, size*n_cols] (conditioner input, flows.py:230) */
+int nfk_gather_cols(const float* x, void* out, int64_t N, int size, int dim,
+                    const int32_t* cols, int n_cols, int out_bf16, int64_t ld_out,
+                    void* stream);
+int nfk_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
+
+/* ---- leapfrog pieces for flow-preconditioned HMC (hmc.py:34-41 drives
+ * simulation.integration_step; the integrator pattern is applications/src/systems.py:331-336).
+ * kick-drift: p += 0.5*dt*F ; q += dt*inv_mass*p.   kick: p += 0.5*dt*F. */
+int nfk_leapfrog_kick_drift(float* q, float* p, const float* force, int64_t n, float dt,
+                            float inv_mass, void* stream);
+int nfk_leapfrog_kick(float* p, const float* force, int64_t n, float dt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFK_H_ */

@@ -1,0 +1,141 @@
+"""ctypes binding of libnfk.so — the C-ABI declared in include/nfk.h.
+
+There is no CPU path and no other backend: if the library is missing this module raises at
+import, and every op raises if it is handed a tensor that is not a CUDA tensor.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnfk.so")
+
+NFK_OK, NFK_EINVAL, NFK_ECUDA, NFK_EUNSUPPORTED = 0, 1, 2, 3
+ARITH_EXACT, ARITH_HYBRID, ARITH_FAST = 0, 1, 2
+ARITH = {"exact": ARITH_EXACT, "hybrid": ARITH_HYBRID, "fast": ARITH_FAST}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or `make -C normalizingflow_b200/csrc` (needs nvcc; sm_100a only, there is no fallback)")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_P = c_void_p
+# name -> (restype, argtypes); mirrors include/nfk.h one to one
+SIGNATURES = {
+    "nfk_abi_version": (c_int, []),
+    "nfk_last_error": (c_char_p, []),
+    "nfk_launch_count": (c_int64, []),
+    "nfk_set_scan_order": (c_int, [c_int]),
+    "nfk_get_scan_order": (c_int, []),
+    "nfk_set_tuning": (c_int, [c_int, c_int, c_int, c_int]),
+    "nfk_debug_knots": (c_int, [_P, _P, c_int64, c_int, c_float, c_int, c_int, _P]),
+    "nfk_rqs_coupling": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_float,
+                                 c_int, c_int, c_int, _P]),
+    "nfk_unconstrained_rqs": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int, _P]),
+    "nfk_affine_halfcoupling": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int64, c_int, _P, c_int64, c_int,
+                                        c_int, c_int, _P]),
+    "nfk_affine_halfcoupling_bwd": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int64, c_int, _P, _P, c_int64,
+                                            c_int, _P, _P, c_int64, c_int, c_int, _P]),
+    "nfk_planar_prepare": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
+    "nfk_planar_stack": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "nfk_radial_sumsq": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
+    "nfk_radial": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "nfk_gauss_logprob": (c_int, [_P, _P, c_float, _P, c_int64, c_int, c_float, _P]),
+    "nfk_linear_f32": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "nfk_gemm_f32": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int64,
+                             c_int, _P]),
+    "nfk_gather_cols": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int64, _P]),
+    "nfk_cast_f32_bf16": (c_int, [_P, _P, c_int64, _P]),
+    "nfk_leapfrog_kick_drift": (c_int, [_P, _P, _P, c_int64, c_float, c_float, _P]),
+    "nfk_leapfrog_kick": (c_int, [_P, _P, c_int64, c_float, _P]),
+}
+
+
+def _bind():
+    missing = []
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    return missing
+
+
+MISSING = _bind()
+
+
+def have(name: str) -> bool:
+    return name in SIGNATURES and name not in MISSING
+
+
+def last_error() -> str:
+    return (lib.nfk_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    """0 -> None; NFK_EINVAL -> ValueError (as nf/utils.py:64-71 raise); else RuntimeError."""
+    if rc == NFK_OK:
+        return
+    msg = f"{what}: {last_error()}" if what else last_error()
+    if rc == NFK_EINVAL:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def call(name: str, *args) -> None:
+    if name in MISSING:
+        raise RuntimeError(f"libnfk.so does not export {name}; rebuild the library")
+    check(getattr(lib, name)(*args), name)
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "normalizingflow_b200 has no CPU path: tensors must live on a CUDA (sm_100a) device; "
+                f"got a {t.device} tensor")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} and {t.device}")
+    return dev
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32, contiguous, 16-byte aligned view/copy of ``t``."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def ptr(t) -> c_void_p:
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream_ptr(dev: torch.device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def i32_array(values):
+    arr = (c_int32 * len(values))(*[int(v) for v in values])
+    return arr
+
+
+def launch_count() -> int:
+    return int(lib.nfk_launch_count())

@@ -1,0 +1,479 @@
+// RQS coupling transform (K1): the part of NSF_CL.forward/inverse after the conditioner
+// (reference nf/flows.py:232-239, :246-253) fused with unconstrained_RQS / RQS / searchsorted
+// (nf/utils.py:20-152) into one pass over HBM.
+//
+// Data movement (B200): a persistent CTA walks row tiles.  The spline parameters of a tile
+// (R rows x F_t features x (3K-1) fp32, one contiguous block of the [N, F_t, 3K-1] tensor) and
+// the tile's activations arrive in shared memory through 1-D TMA bulk copies
+// (cp.async.bulk, SASS UBLKCP) into a multi-stage mbarrier ring, so HBM reads are full-line
+// and asynchronous; each thread then reads the 3K-1 words of ITS element at word stride 3K-1
+// (odd => bank-conflict free), does bin search + spline + log-det entirely in registers, the
+// per-row log-det is a warp-shuffle reduction, and the output tile (reference column order,
+// quirk Q5) leaves through a TMA bulk store.
+//
+// Algorithmic HBM bytes per row: F_t*(3K-1)*4 + 2*d*4 + 4 (+4 when accumulating log-det).
+#include "rqs_math.cuh"
+
+namespace nfk {
+
+constexpr int MAXDIM = 16;
+constexpr int MAX_THREADS = 640;
+
+struct CouplingArgs {
+  const float* x;
+  const float* params;
+  float* out;
+  float* logdet;
+  int8_t* bins;
+  long long n_tiles;   // tiled kernel: number of full tiles
+  long long row0;      // rows kernel: first row
+  int size, dim, n_mask, n_unm, d, F_t, P, R, stages, accumulate;
+  int mask[MAXDIM];
+  int unm[MAXDIM];
+  RqsConsts c;
+};
+
+struct SmemPtr {
+  const float* p;
+  __device__ __forceinline__ float operator()(int i) const { return p[i]; }
+};
+
+template <int MODE, int KT, bool INVERSE, bool FT32>
+__global__ void __launch_bounds__(MAX_THREADS)
+rqs_coupling_tiled(const __grid_constant__ CouplingArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int s_mask[MAXDIM], s_unm[MAXDIM];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  const int P = a.P, R = a.R, d = a.d, F_t = a.F_t, S = a.stages;
+  const int dim = a.dim, n_mask = a.n_mask, n_unm = a.n_unm;
+  const int n_el = R * F_t;
+  const int ptile = n_el * P;      // floats; R % 4 == 0 keeps every tile 16-byte aligned
+  const int xtile = R * d;
+
+  float* ps = reinterpret_cast<float*>(smem_raw);
+  float* xs = ps + (size_t)S * ptile;
+  float* outs = xs + (size_t)S * xtile;
+  float* lads = outs + 2 * xtile;
+  uint64_t* full = reinterpret_cast<uint64_t*>(lads + (FT32 ? 0 : 2 * n_el));
+
+  if (tid < MAXDIM) {
+    s_mask[tid] = a.mask[tid];
+    s_unm[tid] = a.unm[tid];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const long long first = blockIdx.x, stride = gridDim.x;
+  const long long my_tiles = (a.n_tiles > first) ? (a.n_tiles - first + stride - 1) / stride : 0;
+
+  auto issue = [&](long long it) {
+    const long long tile = first + it * stride;
+    const int stage = (int)(it % S);
+    mbar_expect_tx(&full[stage], (uint32_t)(ptile + xtile) * 4u);
+    bulk_g2s(ps + (size_t)stage * ptile, a.params + tile * ptile, (uint32_t)ptile * 4u,
+             &full[stage]);
+    bulk_g2s(xs + (size_t)stage * xtile, a.x + tile * xtile, (uint32_t)xtile * 4u, &full[stage]);
+  };
+  if (tid == 0)
+    for (long long it = 0; it < S && it < my_tiles; ++it) issue(it);
+
+  for (long long it = 0; it < my_tiles; ++it) {
+    const long long tile = first + it * stride;
+    const int stage = (int)(it % S);
+    const int buf = (int)(it & 1);
+    const float* pst = ps + (size_t)stage * ptile;
+    const float* xst = xs + (size_t)stage * xtile;
+    float* ob = outs + buf * xtile;
+    float* lb = lads + buf * n_el;
+    const long long row_base = tile * R;
+
+    mbar_wait(&full[stage], (uint32_t)((it / S) & 1));
+
+    for (int e = tid; e < n_el; e += nthr) {
+      int r, f;
+      if (FT32) {
+        r = e >> 5;
+        f = e & 31;
+      } else {
+        r = e / F_t;
+        f = e - r * F_t;
+      }
+      int s = f, j = 0;
+      if (n_unm > 1) {
+        s = f / n_unm;
+        j = f - s * n_unm;
+      }
+      const float xin = xst[r * d + s * dim + s_unm[j]];
+      const RqsOut o = rqs_element<MODE, KT, INVERSE, true>(SmemPtr{pst + (size_t)e * P}, xin, a.c);
+      ob[r * d + s * dim + n_mask + j] = o.y;
+      if (a.bins) a.bins[(row_base + r) * F_t + f] = (int8_t)o.bin;
+      if (FT32) {
+        const float t = warp_sum(o.lad);                               // flows.py:238
+        if (lane == 0) {
+          float* ldp = a.logdet + row_base + r;
+          *ldp = a.accumulate ? *ldp + t : t;
+        }
+      } else {
+        lb[e] = o.lad;
+      }
+    }
+    // conditioning columns move to the front of each dim-group (flows.py:239, quirk Q5)
+    {
+      const int per_row = a.size * n_mask;
+      for (int i = tid; i < R * per_row; i += nthr) {
+        const int r = i / per_row;
+        const int rem = i - r * per_row;
+        int s = rem, mi = 0;
+        if (n_mask > 1) {
+          s = rem / n_mask;
+          mi = rem - s * n_mask;
+        }
+        ob[r * d + s * dim + mi] = xst[r * d + s * dim + s_mask[mi]];
+      }
+    }
+    fence_proxy_async();
+    if (tid == 0) bulk_wait_read<0>();   // store of tile it-1 has drained outs[buf^1]
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(a.out + tile * xtile, ob, (uint32_t)xtile * 4u);
+      bulk_commit();
+      if (it + S < my_tiles) issue(it + S);
+    }
+    if (!FT32) {
+      for (int r = warp; r < R; r += nwarps) {
+        float t = 0.f;
+        for (int f = lane; f < F_t; f += 32) t += lb[r * F_t + f];
+        t = warp_sum(t);
+        if (lane == 0) {
+          float* ldp = a.logdet + row_base + r;
+          *ldp = a.accumulate ? *ldp + t : t;
+        }
+      }
+    }
+  }
+  if (tid == 0) bulk_wait_all<0>();
+}
+
+struct GmemPtr {
+  const float* p;
+  __device__ __forceinline__ float operator()(int i) const { return __ldg(p + i); }
+};
+
+// One CTA per row, plain global accesses: tail rows (N % R), tiny batches and shapes whose
+// tiles do not fit shared memory.
+template <int MODE, int KT, bool INVERSE>
+__global__ void __launch_bounds__(128) rqs_coupling_rows(const __grid_constant__ CouplingArgs a) {
+  __shared__ int s_mask[MAXDIM], s_unm[MAXDIM];
+  __shared__ float red[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < MAXDIM) {
+    s_mask[tid] = a.mask[tid];
+    s_unm[tid] = a.unm[tid];
+  }
+  __syncthreads();
+  const long long row = a.row0 + blockIdx.x;
+  const float* xr = a.x + row * a.d;
+  float* outr = a.out + row * a.d;
+  float acc = 0.f;
+  for (int f = tid; f < a.F_t; f += 128) {
+    const int s = f / a.n_unm, j = f - s * a.n_unm;
+    const float xin = xr[s * a.dim + s_unm[j]];
+    const RqsOut o = rqs_element<MODE, KT, INVERSE, true>(
+        GmemPtr{a.params + (row * a.F_t + f) * a.P}, xin, a.c);
+    outr[s * a.dim + a.n_mask + j] = o.y;
+    if (a.bins) a.bins[row * a.F_t + f] = (int8_t)o.bin;
+    acc += o.lad;
+  }
+  for (int i = tid; i < a.size * a.n_mask; i += 128) {
+    const int s = i / a.n_mask, mi = i - s * a.n_mask;
+    outr[s * a.dim + mi] = xr[s * a.dim + s_mask[mi]];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    const float t = (red[0] + red[1]) + (red[2] + red[3]);
+    a.logdet[row] = a.accumulate ? a.logdet[row] + t : t;
+  }
+}
+
+struct SplitPtr {
+  const float *w, *h, *dd;
+  int K;
+  __device__ __forceinline__ float operator()(int i) const {
+    return i < K ? __ldg(w + i) : (i < 2 * K ? __ldg(h + (i - K)) : __ldg(dd + (i - 2 * K)));
+  }
+};
+
+template <int MODE, int KT, bool INVERSE>
+__global__ void __launch_bounds__(128)
+unconstrained_rqs_kernel(const float* __restrict__ inputs, const float* __restrict__ W,
+                         const float* __restrict__ H, const float* __restrict__ D,
+                         float* __restrict__ out, float* __restrict__ lad,
+                         int8_t* __restrict__ bins, long long M, RqsConsts c) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M) return;
+  const int K = KT ? KT : c.K;
+  const RqsOut o = rqs_element<MODE, KT, INVERSE, false>(
+      SplitPtr{W + e * K, H + e * K, D + e * (K - 1), K}, inputs[e], c);
+  out[e] = o.y;
+  lad[e] = o.lad;
+  if (bins) bins[e] = (int8_t)o.bin;
+}
+
+template <bool EXACT, int KT, bool LAYER_NORM>
+__global__ void __launch_bounds__(128)
+debug_knots_kernel(const float* __restrict__ logits, float* __restrict__ knots, long long M,
+                   RqsConsts c) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M) return;
+  constexpr int KK = KT ? KT : KMAX;
+  const int K = KT ? KT : c.K;
+  float v[KK + 1];
+#pragma unroll
+  for (int j = 0; j < KK; ++j)
+    if (j < K) v[j] = logits[e * K + j];
+  knot_chain<EXACT, KT, LAYER_NORM>(v, c);
+#pragma unroll
+  for (int j = 0; j <= KK; ++j)
+    if (j <= K) knots[e * (K + 1) + j] = v[j];
+}
+
+// ---- host side -----------------------------------------------------------------------
+static RqsConsts make_consts(int K, float B) {
+  RqsConsts c;
+  c.B = B;
+  c.twoB = (float)(2.0 * (double)B);
+  c.negB = -B;
+  c.Bnudge = B + 1e-6f;
+  c.min_bin = 1e-3f;
+  c.one_m = (float)(1.0 - 1e-3 * (double)K);
+  c.min_d = 1e-3f;
+  c.edge_c = (float)log(exp(1.0 - 1e-3) - 1.0);
+  c.g0 = c.twoB * LOG2E;
+  c.q0 = c.twoB * c.one_m;
+  c.kstep = c.twoB * 1e-3f;
+  c.K = K;
+  c.scan_order = scan_order();
+  return c;
+}
+
+static int g_tune_R = 0, g_tune_threads = 0, g_tune_stages = 0, g_tune_ctas = 0;
+
+template <int MODE, int KT, bool INVERSE>
+static int launch_coupling(CouplingArgs& a, long long N, cudaStream_t st) {
+  // ---- tile geometry
+  const int F_t = a.F_t;
+  const size_t row_floats = (size_t)F_t * a.P + a.d;
+  int R = g_tune_R;
+  if (R <= 0) {
+    R = 4;
+    while (R * F_t < 256 && R < 64) R *= 2;
+  }
+  R = (R + 3) & ~3;
+  const int n_el = R * F_t;
+  int threads = g_tune_threads;
+  if (threads <= 0) {
+    const int iters = (n_el + MAX_THREADS - 1) / MAX_THREADS;
+    threads = ((n_el + iters - 1) / iters + 31) & ~31;
+  }
+  threads = max(32, min(MAX_THREADS, (threads + 31) & ~31));
+  const bool ft32 = (F_t == 32);
+  const size_t stage_bytes = (size_t)R * row_floats * 4;
+  const size_t fixed = (size_t)2 * R * a.d * 4 + (ft32 ? 0 : (size_t)2 * n_el * 4) + 8 * 8 + 128;
+  int stages = g_tune_stages;
+  size_t budget = 110 * 1024;
+  if (stages <= 0) {
+    stages = (int)((budget - fixed) / stage_bytes);
+    if (stages < 3) {
+      budget = 220 * 1024;
+      stages = (int)((budget > fixed ? budget - fixed : 0) / stage_bytes);
+    }
+    stages = min(stages, 4);
+  }
+  const size_t smem = fixed + (size_t)stages * stage_bytes;
+  const bool tiled_ok = stages >= 2 && smem <= 226 * 1024 &&
+                        ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.params) |
+                          reinterpret_cast<uintptr_t>(a.out)) & 15) == 0;
+  long long n_tiles = tiled_ok ? N / R : 0;
+  if (n_tiles > 0) {
+    a.R = R;
+    a.stages = stages;
+    a.n_tiles = n_tiles;
+    auto kern = ft32 ? rqs_coupling_tiled<MODE, KT, INVERSE, true>
+                     : rqs_coupling_tiled<MODE, KT, INVERSE, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("rqs_coupling: cannot set %zu B dynamic shared memory: %s", smem,
+                cudaGetErrorString(e));
+      return NFK_ECUDA;
+    }
+    int ctas_per_sm = g_tune_ctas > 0 ? g_tune_ctas : max(1, (int)((227 * 1024) / (smem + 1024)));
+    ctas_per_sm = min(ctas_per_sm, max(1, 2048 / threads));
+    const long long cap = (long long)sm_count() * ctas_per_sm;
+    const long long grid = n_tiles < cap ? n_tiles : cap;
+    kern<<<(unsigned)grid, threads, smem, st>>>(a);
+    count_launch();
+    if (int rc = check_launch("rqs_coupling_tiled")) return rc;
+  }
+  const long long done = n_tiles * R;
+  if (done < N) {
+    a.row0 = done;
+    rqs_coupling_rows<MODE, KT, INVERSE><<<(unsigned)(N - done), 128, 0, st>>>(a);
+    count_launch();
+    if (int rc = check_launch("rqs_coupling_rows")) return rc;
+  }
+  return NFK_OK;
+}
+
+#define NFK_DISPATCH_MODE_K_INV(FN, mode, K, inverse, ...)                                   \
+  do {                                                                                        \
+    const int m_ = (mode);                                                                    \
+    const bool k8_ = ((K) == 8);                                                              \
+    const bool inv_ = (inverse) != 0;                                                         \
+    if (m_ == NFK_ARITH_EXACT) {                                                              \
+      if (k8_) return inv_ ? FN<NFK_ARITH_EXACT, 8, true>(__VA_ARGS__)                        \
+                           : FN<NFK_ARITH_EXACT, 8, false>(__VA_ARGS__);                      \
+      return inv_ ? FN<NFK_ARITH_EXACT, 0, true>(__VA_ARGS__)                                 \
+                  : FN<NFK_ARITH_EXACT, 0, false>(__VA_ARGS__);                               \
+    } else if (m_ == NFK_ARITH_HYBRID) {                                                      \
+      if (k8_) return inv_ ? FN<NFK_ARITH_HYBRID, 8, true>(__VA_ARGS__)                       \
+                           : FN<NFK_ARITH_HYBRID, 8, false>(__VA_ARGS__);                     \
+      return inv_ ? FN<NFK_ARITH_HYBRID, 0, true>(__VA_ARGS__)                                \
+                  : FN<NFK_ARITH_HYBRID, 0, false>(__VA_ARGS__);                              \
+    } else {                                                                                  \
+      if (k8_) return inv_ ? FN<NFK_ARITH_FAST, 8, true>(__VA_ARGS__)                         \
+                           : FN<NFK_ARITH_FAST, 8, false>(__VA_ARGS__);                       \
+      return inv_ ? FN<NFK_ARITH_FAST, 0, true>(__VA_ARGS__)                                  \
+                  : FN<NFK_ARITH_FAST, 0, false>(__VA_ARGS__);                                \
+    }                                                                                         \
+  } while (0)
+
+template <int MODE, int KT, bool INVERSE>
+static int launch_free(const float* inputs, const float* W, const float* H, const float* D,
+                       float* out, float* lad, int8_t* bins, long long M, RqsConsts c,
+                       cudaStream_t st) {
+  const long long grid = (M + 127) / 128;
+  unconstrained_rqs_kernel<MODE, KT, INVERSE><<<(unsigned)grid, 128, 0, st>>>(inputs, W, H, D, out,
+                                                                              lad, bins, M, c);
+  count_launch();
+  return check_launch("unconstrained_rqs");
+}
+
+static int dispatch_coupling(int mode, int K, int inverse, CouplingArgs& a, long long N,
+                             cudaStream_t st) {
+  NFK_DISPATCH_MODE_K_INV(launch_coupling, mode, K, inverse, a, N, st);
+}
+static int dispatch_free(int mode, int K, int inverse, const float* inputs, const float* W,
+                         const float* H, const float* D, float* out, float* lad, int8_t* bins,
+                         long long M, RqsConsts c, cudaStream_t st) {
+  NFK_DISPATCH_MODE_K_INV(launch_free, mode, K, inverse, inputs, W, H, D, out, lad, bins, M, c, st);
+}
+
+int fill_coupling_geometry(CouplingArgs& a, int size, int dim, const int32_t* mask, int n_mask,
+                           int K, float B) {
+  NFK_REQUIRE(size > 0 && dim > 1 && dim <= MAXDIM, "rqs_coupling: need size > 0 and 2 <= dim <= %d",
+              MAXDIM);
+  NFK_REQUIRE(mask != nullptr && n_mask > 0 && n_mask < dim,
+              "rqs_coupling: mask must name between 1 and dim-1 columns");
+  NFK_REQUIRE(K >= 2 && K <= KMAX, "rqs_coupling: 2 <= K <= %d supported (got %d)", KMAX, K);
+  // nf/utils.py:68-71
+  NFK_REQUIRE(1e-3 * K <= 1.0, "Minimal bin width too large for the number of bins");
+  NFK_REQUIRE(B > 0.f, "rqs_coupling: tail bound must be positive");
+  bool used[MAXDIM] = {false};
+  for (int i = 0; i < n_mask; ++i) {
+    NFK_REQUIRE(mask[i] >= 0 && mask[i] < dim, "rqs_coupling: mask column %d outside [0, %d)",
+                mask[i], dim);
+    NFK_REQUIRE(!used[mask[i]], "rqs_coupling: mask column %d repeated", mask[i]);
+    used[mask[i]] = true;
+    a.mask[i] = mask[i];
+  }
+  int nu = 0;
+  for (int cidx = 0; cidx < dim; ++cidx)
+    if (!used[cidx]) a.unm[nu++] = cidx;                               // flows.py:225
+  for (int i = n_mask; i < MAXDIM; ++i) a.mask[i] = 0;
+  for (int i = nu; i < MAXDIM; ++i) a.unm[i] = 0;
+  a.size = size;
+  a.dim = dim;
+  a.n_mask = n_mask;
+  a.n_unm = nu;
+  a.d = size * dim;
+  a.F_t = size * nu;
+  a.P = 3 * K - 1;
+  a.c = make_consts(K, B);
+  return NFK_OK;
+}
+
+}  // namespace nfk
+
+using namespace nfk;
+
+extern "C" {
+
+int nfk_set_tuning(int rows_per_tile, int threads, int stages, int ctas_per_sm) {
+  g_tune_R = rows_per_tile;
+  g_tune_threads = threads;
+  g_tune_stages = stages;
+  g_tune_ctas = ctas_per_sm;
+  return NFK_OK;
+}
+
+int nfk_rqs_coupling(const float* x, const float* params, float* out, float* logdet,
+                     int8_t* bins, int64_t N, int size, int dim, const int32_t* mask,
+                     int n_mask, int K, float B, int inverse, int accumulate, int arith,
+                     void* stream) {
+  NFK_REQUIRE(N >= 0, "rqs_coupling: negative batch");
+  NFK_REQUIRE(arith >= NFK_ARITH_EXACT && arith <= NFK_ARITH_FAST, "rqs_coupling: bad arith %d",
+              arith);
+  CouplingArgs a{};
+  if (int rc = fill_coupling_geometry(a, size, dim, mask, n_mask, K, B)) return rc;
+  if (N == 0) return NFK_OK;
+  NFK_REQUIRE(x && params && out && logdet, "rqs_coupling: null device pointer");
+  NFK_REQUIRE(x != out, "rqs_coupling: out must not alias x");
+  a.x = x;
+  a.params = params;
+  a.out = out;
+  a.logdet = logdet;
+  a.bins = bins;
+  a.accumulate = accumulate;
+  return dispatch_coupling(arith, K, inverse, a, N, (cudaStream_t)stream);
+}
+
+int nfk_unconstrained_rqs(const float* inputs, const float* W, const float* H, const float* D,
+                          float* out, float* lad, int8_t* bins, int64_t M, int K, float B,
+                          int inverse, int arith, void* stream) {
+  NFK_REQUIRE(M >= 0, "unconstrained_rqs: negative size");
+  NFK_REQUIRE(K >= 2 && K <= KMAX, "unconstrained_rqs: 2 <= K <= %d supported (got %d)", KMAX, K);
+  NFK_REQUIRE(1e-3 * K <= 1.0, "Minimal bin width too large for the number of bins");
+  NFK_REQUIRE(arith >= NFK_ARITH_EXACT && arith <= NFK_ARITH_FAST, "unconstrained_rqs: bad arith");
+  if (M == 0) return NFK_OK;
+  NFK_REQUIRE(inputs && W && H && D && out && lad, "unconstrained_rqs: null device pointer");
+  return dispatch_free(arith, K, inverse, inputs, W, H, D, out, lad, bins, M, make_consts(K, B),
+                       (cudaStream_t)stream);
+}
+
+int nfk_debug_knots(const float* logits, float* knots, int64_t M, int K, float B, int layer_norm,
+                    int exact, void* stream) {
+  NFK_REQUIRE(K >= 2 && K <= KMAX, "debug_knots: bad K");
+  if (M == 0) return NFK_OK;
+  const RqsConsts c = make_consts(K, B);
+  const unsigned grid = (unsigned)((M + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+#define NFK_DK(EX, KT, LN) debug_knots_kernel<EX, KT, LN><<<grid, 128, 0, st>>>(logits, knots, M, c)
+  if (K == 8) {
+    if (exact) { if (layer_norm) NFK_DK(true, 8, true); else NFK_DK(true, 8, false); }
+    else       { if (layer_norm) NFK_DK(false, 8, true); else NFK_DK(false, 8, false); }
+  } else {
+    if (exact) { if (layer_norm) NFK_DK(true, 0, true); else NFK_DK(true, 0, false); }
+    else       { if (layer_norm) NFK_DK(false, 0, true); else NFK_DK(false, 0, false); }
+  }
+#undef NFK_DK
+  count_launch();
+  return check_launch("debug_knots");
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""GPU parity tests of the RQS coupling kernel (K1) against the committed golden fixtures
+(outputs of the unmodified reference) and against the oracle on seeded inputs.
+
+Gates (BASELINE.json north_star / SURVEY.md §8(d)): bin indices bit-exact, z and log_det
+within 1e-5 in the measure |a-b| / max(1, |b|), fp32, identical inputs and conditioner outputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import RTOL_FP32, T, golden, parse_masks, rel_err
+
+pytestmark = pytest.mark.gpu
+
+NSF_FIXTURES = ["nsfcl_d64.npz", "nsfcl_d64_stress.npz", "nsfcl_lj38.npz", "nsfcl_k32.npz"]
+
+
+def _ops():
+    from normalizingflow_b200 import _ops
+    return _ops
+
+
+@pytest.mark.parametrize("arith", ["hybrid", "exact", "fast"])
+@pytest.mark.parametrize("name", NSF_FIXTURES)
+def test_transform_matches_reference_fixtures(name, arith):
+    ops = _ops()
+    g = golden(name)
+    size, dim, K, B = int(g["size"]), int(g["dim"]), int(g["K"]), float(g["B"])
+    for mi, mask in enumerate(parse_masks(g)):
+        p = f"m{mi}."
+        for inv, xk, pk, ok, lk, bk in ((False, "x", "params", "z", "ld", "bins"),
+                                        (True, "zin", "params_inv", "x_inv", "ld_inv", "bins_inv")):
+            x = T(g[p + xk]).cuda()
+            params = T(g[p + pk]).cuda()
+            out, ld, bins = ops.rqs_coupling(x, params, size, dim, mask, K, B, inv, arith, want_bins=True)
+            torch.cuda.synchronize()
+            ref_bins = g[p + bk]
+            got_bins = bins.cpu().numpy()
+            if arith == "fast":
+                # documented: FAST may move an input that sits within a few ulp of a knot
+                assert (got_bins != ref_bins).mean() <= 1e-3
+                assert np.abs(got_bins.astype(int) - ref_bins.astype(int)).max() <= 1
+            else:
+                assert np.array_equal(got_bins, ref_bins), (name, mask, inv, int((got_bins != ref_bins).sum()))
+            assert rel_err(out, g[p + ok]) <= RTOL_FP32, (name, mask, inv, rel_err(out, g[p + ok]))
+            assert rel_err(ld, g[p + lk]) <= RTOL_FP32, (name, mask, inv, rel_err(ld, g[p + lk]))
+
+
+@pytest.mark.parametrize("arith", ["hybrid", "exact"])
+def test_unconstrained_rqs_function(arith):
+    ops = _ops()
+    g = golden("rqs_function.npz")
+    for tag in ("k8", "k5", "k32"):
+        B = float(g[f"{tag}.B"])
+        v, W, H, D = (T(g[f"{tag}.{k}"]).cuda() for k in "vWHD")
+        for inv, s in ((False, "fwd"), (True, "inv")):
+            out, lad, bins = ops.unconstrained_rqs(v, W, H, D, inv, B, arith, want_bins=True)
+            assert np.array_equal(bins.cpu().numpy(), g[f"{tag}.{s}.bins"])
+            assert rel_err(out, g[f"{tag}.{s}.out"]) <= RTOL_FP32
+            assert rel_err(lad, g[f"{tag}.{s}.lad"]) <= RTOL_FP32
+
+
+@pytest.mark.parametrize("N", [0, 1, 3, 8, 13, 4099])
+def test_ragged_batches_and_accumulate(N):
+    """empty, sub-tile, tile-aligned and ragged batches; log-det accumulation; the tiled (TMA)
+    path and the per-row tail path must agree with the oracle."""
+    from oracle import nf_oracle as O
+    ops = _ops()
+    gen = torch.Generator().manual_seed(N)
+    x = torch.randn(N, 64, generator=gen) * 1.5
+    params = torch.randn(N, 32, 23, generator=gen)
+    for inv in (False, True):
+        ro, rl, rb = O.nsf_cl_transform(x, params, 32, 2, [1], 8, 3.0, inv) if N else (x, torch.zeros(0), None)
+        out, ld, bins = ops.rqs_coupling(x.cuda(), params.cuda(), 32, 2, [1], 8, 3.0, inv, "hybrid", want_bins=True)
+        assert out.shape == (N, 64) and ld.shape == (N,)
+        if N:
+            assert np.array_equal(bins.cpu().numpy(), rb.numpy().astype(np.int8))
+            assert rel_err(out, ro) <= RTOL_FP32 and rel_err(ld, rl) <= RTOL_FP32
+            acc = torch.full((N,), 2.5, device="cuda")
+            ops.rqs_coupling(x.cuda(), params.cuda(), 32, 2, [1], 8, 3.0, inv, "hybrid", logdet=acc)
+            assert rel_err(acc, rl + 2.5) <= RTOL_FP32
+
+
+def test_tails_nan_and_all_outside():
+    """Q6 / Q7: identity + zero log-det outside [-B, B] and for NaN; a batch with no inside
+    element passes through (the reference would raise on torch.min of an empty tensor)."""
+    ops = _ops()
+    x = torch.full((16, 64), 7.0)
+    x[0, 0] = float("nan")
+    x[1, 3] = -9.0
+    params = torch.randn(16, 32, 23, generator=torch.Generator().manual_seed(5))
+    out, ld, bins = ops.rqs_coupling(x.cuda(), params.cuda(), 32, 2, [0], 8, 3.0, False, "hybrid", want_bins=True)
+    out = out.cpu()
+    assert torch.equal(torch.nan_to_num(out, nan=123.0), torch.nan_to_num(x, nan=123.0))
+    assert float(ld.abs().max()) == 0.0 and int(bins.max()) == -1
+
+
+def test_bad_arguments_raise_valueerror():
+    ops = _ops()
+    x = torch.zeros(4, 64, device="cuda")
+    p = torch.zeros(4, 32, 23, device="cuda")
+    with pytest.raises(ValueError):
+        ops.rqs_coupling(x, p, 32, 2, [2], 8, 3.0, False)          # mask column outside dim
+    with pytest.raises(ValueError):
+        ops.rqs_coupling(x, p[:, :, :20], 32, 2, [1], 8, 3.0, False)
+    with pytest.raises(RuntimeError):
+        ops.rqs_coupling(x.cpu(), p, 32, 2, [1], 8, 3.0, False)     # no CPU path
+
+
+def test_large_batch_vs_oracle_cpu_and_cuda():
+    """65,536 rows (2.1 M splines): bins vs the oracle on the host CPU and vs the same torch
+    op chain executed by ATen on the GPU.  EXACT/HYBRID must equal the ATen-CUDA chain exactly;
+    against the CPU chain a bin may only differ where x is within a few ulp of a knot."""
+    from oracle import nf_oracle as O
+    ops = _ops()
+    gen = torch.Generator().manual_seed(77)
+    N = 65536
+    x = torch.randn(N, 64, generator=gen) * 1.5
+    params = torch.randn(N, 32, 23, generator=gen) * 1.5
+    for inv in (False, True):
+        ro, rl, rb = O.nsf_cl_transform(x, params, 32, 2, [1], 8, 3.0, inv)
+        co, cl, cb = O.nsf_cl_transform(x.cuda(), params.cuda(), 32, 2, [1], 8, 3.0, inv)
+        for arith in ("hybrid", "exact"):
+            out, ld, bins = ops.rqs_coupling(x.cuda(), params.cuda(), 32, 2, [1], 8, 3.0, inv, arith, want_bins=True)
+            b = bins.long()
+            assert int((b != cb).sum()) == 0, (arith, inv, int((b != cb).sum()))
+            n_cpu = int((b.cpu() != rb).sum())
+            assert n_cpu <= 8, (arith, inv, n_cpu)
+            assert rel_err(out, ro) <= RTOL_FP32 and rel_err(ld, rl) <= RTOL_FP32
+            if arith == "exact":
+                # bit-identical outputs to the ATen-on-CUDA chain
+                assert torch.equal(out.view(torch.int32), co.view(torch.int32))
