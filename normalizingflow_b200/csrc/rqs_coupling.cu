@@ -38,7 +38,10 @@ struct SmemPtr {
   __device__ __forceinline__ float operator()(int i) const { return p[i]; }
 };
 
-template <int MODE, int KT, bool INVERSE, bool FT32>
+// Generic geometry: one element per thread per tile (the launcher sizes the CTA to the tile), so
+// every index a thread needs is loop-invariant; activations and outputs go through shared-memory
+// tiles moved by TMA bulk copies.
+template <int MODE, int KT, bool INVERSE>
 __global__ void __launch_bounds__(MAX_THREADS)
 rqs_coupling_tiled(const __grid_constant__ CouplingArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -55,7 +58,7 @@ rqs_coupling_tiled(const __grid_constant__ CouplingArgs a) {
   float* xs = ps + (size_t)S * ptile;
   float* outs = xs + (size_t)S * xtile;
   float* lads = outs + 2 * xtile;
-  uint64_t* full = reinterpret_cast<uint64_t*>(lads + (FT32 ? 0 : 2 * n_el));
+  uint64_t* full = reinterpret_cast<uint64_t*>(lads + 2 * n_el);
 
   if (tid < MAXDIM) {
     s_mask[tid] = a.mask[tid];
@@ -67,73 +70,57 @@ rqs_coupling_tiled(const __grid_constant__ CouplingArgs a) {
   }
   __syncthreads();
 
-  const long long first = blockIdx.x, stride = gridDim.x;
-  const long long my_tiles = (a.n_tiles > first) ? (a.n_tiles - first + stride - 1) / stride : 0;
+  const unsigned first = blockIdx.x, stride = gridDim.x;
+  const unsigned n_tiles = (unsigned)a.n_tiles;
+  const unsigned my_tiles = (n_tiles > first) ? (n_tiles - first + stride - 1) / stride : 0;
+  const uint32_t stage_bytes = (uint32_t)(ptile + xtile) * 4u;
 
-  auto issue = [&](long long it) {
-    const long long tile = first + it * stride;
-    const int stage = (int)(it % S);
-    mbar_expect_tx(&full[stage], (uint32_t)(ptile + xtile) * 4u);
-    bulk_g2s(ps + (size_t)stage * ptile, a.params + tile * ptile, (uint32_t)ptile * 4u,
-             &full[stage]);
+  // loop-invariant element geometry
+  const bool has_el = tid < n_el;
+  int xoff = 0, ooff = 0, r_el = 0;
+  if (has_el) {
+    r_el = tid / F_t;
+    const int f = tid - r_el * F_t;
+    const int s = f / n_unm, j = f - s * n_unm;
+    xoff = r_el * d + s * dim + s_unm[j];
+    ooff = r_el * d + s * dim + n_mask + j;
+  }
+  const int per_row = a.size * n_mask;
+  const int n_copy = R * per_row;
+
+  auto issue = [&](unsigned it, int stage) {
+    const size_t tile = first + (size_t)it * stride;
+    mbar_expect_tx(&full[stage], stage_bytes);
+    bulk_g2s(ps + (size_t)stage * ptile, a.params + tile * ptile, (uint32_t)ptile * 4u, &full[stage]);
     bulk_g2s(xs + (size_t)stage * xtile, a.x + tile * xtile, (uint32_t)xtile * 4u, &full[stage]);
   };
   if (tid == 0)
-    for (long long it = 0; it < S && it < my_tiles; ++it) issue(it);
+    for (int it = 0; it < S && (unsigned)it < my_tiles; ++it) issue(it, it);
 
-  for (long long it = 0; it < my_tiles; ++it) {
-    const long long tile = first + it * stride;
-    const int stage = (int)(it % S);
+  int stage = 0;
+  uint32_t phase = 0;
+  for (unsigned it = 0; it < my_tiles; ++it) {
+    const size_t tile = first + (size_t)it * stride;
     const int buf = (int)(it & 1);
     const float* pst = ps + (size_t)stage * ptile;
     const float* xst = xs + (size_t)stage * xtile;
     float* ob = outs + buf * xtile;
     float* lb = lads + buf * n_el;
-    const long long row_base = tile * R;
+    const size_t row_base = tile * R;
 
-    mbar_wait(&full[stage], (uint32_t)((it / S) & 1));
-
-    for (int e = tid; e < n_el; e += nthr) {
-      int r, f;
-      if (FT32) {
-        r = e >> 5;
-        f = e & 31;
-      } else {
-        r = e / F_t;
-        f = e - r * F_t;
-      }
-      int s = f, j = 0;
-      if (n_unm > 1) {
-        s = f / n_unm;
-        j = f - s * n_unm;
-      }
-      const float xin = xst[r * d + s * dim + s_unm[j]];
-      const RqsOut o = rqs_element<MODE, KT, INVERSE, true>(SmemPtr{pst + (size_t)e * P}, xin, a.c);
-      ob[r * d + s * dim + n_mask + j] = o.y;
-      if (a.bins) a.bins[(row_base + r) * F_t + f] = (int8_t)o.bin;
-      if (FT32) {
-        const float t = warp_sum(o.lad);                               // flows.py:238
-        if (lane == 0) {
-          float* ldp = a.logdet + row_base + r;
-          *ldp = a.accumulate ? *ldp + t : t;
-        }
-      } else {
-        lb[e] = o.lad;
-      }
+    mbar_wait(&full[stage], phase);
+    if (has_el) {
+      const RqsOut o = rqs_element<MODE, KT, INVERSE, true>(SmemPtr{pst + (size_t)tid * P}, xst[xoff], a.c);
+      ob[ooff] = o.y;
+      lb[tid] = o.lad;
+      if (a.bins) a.bins[row_base * F_t + tid] = (int8_t)o.bin;
     }
     // conditioning columns move to the front of each dim-group (flows.py:239, quirk Q5)
-    {
-      const int per_row = a.size * n_mask;
-      for (int i = tid; i < R * per_row; i += nthr) {
-        const int r = i / per_row;
-        const int rem = i - r * per_row;
-        int s = rem, mi = 0;
-        if (n_mask > 1) {
-          s = rem / n_mask;
-          mi = rem - s * n_mask;
-        }
-        ob[r * d + s * dim + mi] = xst[r * d + s * dim + s_mask[mi]];
-      }
+    for (int i = tid; i < n_copy; i += nthr) {
+      const int r = i / per_row;
+      const int rem = i - r * per_row;
+      const int s = rem / n_mask, mi = rem - s * n_mask;
+      ob[r * d + s * dim + mi] = xst[r * d + s * dim + s_mask[mi]];
     }
     fence_proxy_async();
     if (tid == 0) bulk_wait_read<0>();   // store of tile it-1 has drained outs[buf^1]
@@ -141,21 +128,90 @@ rqs_coupling_tiled(const __grid_constant__ CouplingArgs a) {
     if (tid == 0) {
       bulk_s2g(a.out + tile * xtile, ob, (uint32_t)xtile * 4u);
       bulk_commit();
-      if (it + S < my_tiles) issue(it + S);
+      if (it + S < my_tiles) issue(it + S, stage);
     }
-    if (!FT32) {
-      for (int r = warp; r < R; r += nwarps) {
-        float t = 0.f;
-        for (int f = lane; f < F_t; f += 32) t += lb[r * F_t + f];
-        t = warp_sum(t);
-        if (lane == 0) {
-          float* ldp = a.logdet + row_base + r;
-          *ldp = a.accumulate ? *ldp + t : t;
-        }
+    for (int r = warp; r < R; r += nwarps) {                           // flows.py:238
+      float t = 0.f;
+      for (int f = lane; f < F_t; f += 32) t += lb[r * F_t + f];
+      t = warp_sum(t);
+      if (lane == 0) {
+        float* ldp = a.logdet + row_base + r;
+        *ldp = a.accumulate ? *ldp + t : t;
       }
+    }
+    if (++stage == S) {
+      stage = 0;
+      phase ^= 1;
     }
   }
   if (tid == 0) bulk_wait_all<0>();
+}
+
+// Specialised geometry of the headline workload (size = 32, dim = 2, one masked column): one warp
+// owns one row, lane s owns the column pair (2s, 2s+1), so activations are one coalesced 8-byte
+// load/store per thread straight from/to HBM (prefetched one tile ahead in registers), only the
+// spline parameters go through the TMA ring, and the row log-det is one warp-shuffle reduction.
+constexpr int PAIR_THREADS = 256;
+
+template <int MODE, int KT, bool INVERSE>
+__global__ void __launch_bounds__(PAIR_THREADS, 4)
+rqs_coupling_pairs(const __grid_constant__ CouplingArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int T = PAIR_THREADS;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int P = a.P, S = a.stages;
+  const int ptile = T * P;                       // floats per stage
+  float* ps = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ps + (size_t)S * ptile);
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const unsigned first = blockIdx.x, stride = gridDim.x;
+  const unsigned n_tiles = (unsigned)a.n_tiles;
+  const unsigned my_tiles = (n_tiles > first) ? (n_tiles - first + stride - 1) / stride : 0;
+  const bool cond_first = (a.mask[0] == 0);      // conditioning column is column 0 of the pair
+
+  auto issue = [&](unsigned it, int stage) {
+    const size_t tile = first + (size_t)it * stride;
+    mbar_expect_tx(&full[stage], (uint32_t)ptile * 4u);
+    bulk_g2s(ps + (size_t)stage * ptile, a.params + tile * ptile, (uint32_t)ptile * 4u, &full[stage]);
+  };
+  if (tid == 0)
+    for (int it = 0; it < S && (unsigned)it < my_tiles; ++it) issue(it, it);
+
+  const float2* x2 = reinterpret_cast<const float2*>(a.x);
+  float2* o2 = reinterpret_cast<float2*>(a.out);
+  float2 xn = make_float2(0.f, 0.f);
+  if (my_tiles) xn = __ldcs(x2 + (size_t)first * T + tid);
+
+  const float* pth = ps + (size_t)tid * P;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (unsigned it = 0; it < my_tiles; ++it) {
+    const size_t tile = first + (size_t)it * stride;
+    const float2 xc = xn;
+    if (it + 1 < my_tiles) xn = __ldcs(x2 + (tile + stride) * T + tid);
+    mbar_wait(&full[stage], phase);
+    const RqsOut o = rqs_element<MODE, KT, INVERSE, true>(SmemPtr{pth + (size_t)stage * ptile},
+                                                          cond_first ? xc.y : xc.x, a.c);
+    // out pair = (conditioning value, transformed value)  (flows.py:239, quirk Q5)
+    __stcs(o2 + tile * T + tid, make_float2(cond_first ? xc.x : xc.y, o.y));
+    if (a.bins) a.bins[tile * T + tid] = (int8_t)o.bin;
+    const float t = warp_sum(o.lad);                                   // flows.py:238
+    if (lane == 0) {
+      float* ldp = a.logdet + tile * (T / 32) + (tid >> 5);
+      *ldp = a.accumulate ? *ldp + t : t;
+    }
+    __syncthreads();                     // every thread is done with this stage's parameters
+    if (tid == 0 && it + S < my_tiles) issue(it + S, stage);
+    if (++stage == S) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
 }
 
 struct GmemPtr {
@@ -266,61 +322,73 @@ static int g_tune_R = 0, g_tune_threads = 0, g_tune_stages = 0, g_tune_ctas = 0;
 
 template <int MODE, int KT, bool INVERSE>
 static int launch_coupling(CouplingArgs& a, long long N, cudaStream_t st) {
-  // ---- tile geometry
   const int F_t = a.F_t;
-  const size_t row_floats = (size_t)F_t * a.P + a.d;
-  int R = g_tune_R;
-  if (R <= 0) {
-    R = 4;
-    while (R * F_t < 256 && R < 64) R *= 2;
-  }
-  R = (R + 3) & ~3;
-  const int n_el = R * F_t;
-  int threads = g_tune_threads;
-  if (threads <= 0) {
-    const int iters = (n_el + MAX_THREADS - 1) / MAX_THREADS;
-    threads = ((n_el + iters - 1) / iters + 31) & ~31;
-  }
-  threads = max(32, min(MAX_THREADS, (threads + 31) & ~31));
-  const bool ft32 = (F_t == 32);
-  const size_t stage_bytes = (size_t)R * row_floats * 4;
-  const size_t fixed = (size_t)2 * R * a.d * 4 + (ft32 ? 0 : (size_t)2 * n_el * 4) + 8 * 8 + 128;
-  int stages = g_tune_stages;
-  size_t budget = 110 * 1024;
-  if (stages <= 0) {
-    stages = (int)((budget - fixed) / stage_bytes);
-    if (stages < 3) {
-      budget = 220 * 1024;
-      stages = (int)((budget > fixed ? budget - fixed : 0) / stage_bytes);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.params) |
+                         reinterpret_cast<uintptr_t>(a.out)) & 15) == 0;
+  long long done = 0;
+  if (aligned && F_t == 32 && a.dim == 2 && a.n_mask == 1 && g_tune_R >= 0) {
+    // ---- headline geometry: pairs kernel, 8 rows (256 splines) per tile
+    const int R = PAIR_THREADS / 32;
+    const long long n_tiles = N / R;
+    if (n_tiles > 0 && n_tiles < (1LL << 31)) {
+      int stages = g_tune_stages > 0 ? g_tune_stages : 2;
+      const size_t stage_bytes = (size_t)PAIR_THREADS * a.P * 4;
+      while (stages > 2 && stages * stage_bytes + 64 > 226 * 1024) --stages;
+      const size_t smem = stages * stage_bytes + 64;
+      if (smem <= 226 * 1024) {
+        a.R = R;
+        a.stages = stages;
+        a.n_tiles = n_tiles;
+        auto kern = rqs_coupling_pairs<MODE, KT, INVERSE>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+          set_error("rqs_coupling: cannot set %zu B dynamic shared memory: %s", smem, cudaGetErrorString(e));
+          return NFK_ECUDA;
+        }
+        int ctas_per_sm = g_tune_ctas > 0 ? g_tune_ctas : (int)((227 * 1024) / (smem + 1024));
+        ctas_per_sm = max(1, min(ctas_per_sm, 2048 / PAIR_THREADS));
+        const long long cap = (long long)sm_count() * ctas_per_sm;
+        const long long grid = n_tiles < cap ? n_tiles : cap;
+        kern<<<(unsigned)grid, PAIR_THREADS, smem, st>>>(a);
+        count_launch();
+        if (int rc = check_launch("rqs_coupling_pairs")) return rc;
+        done = n_tiles * R;
+      }
     }
-    stages = min(stages, 4);
-  }
-  const size_t smem = fixed + (size_t)stages * stage_bytes;
-  const bool tiled_ok = stages >= 2 && smem <= 226 * 1024 &&
-                        ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.params) |
-                          reinterpret_cast<uintptr_t>(a.out)) & 15) == 0;
-  long long n_tiles = tiled_ok ? N / R : 0;
-  if (n_tiles > 0) {
-    a.R = R;
-    a.stages = stages;
-    a.n_tiles = n_tiles;
-    auto kern = ft32 ? rqs_coupling_tiled<MODE, KT, INVERSE, true>
-                     : rqs_coupling_tiled<MODE, KT, INVERSE, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("rqs_coupling: cannot set %zu B dynamic shared memory: %s", smem,
-                cudaGetErrorString(e));
-      return NFK_ECUDA;
+  } else if (aligned) {
+    // ---- generic geometry: one element per thread per tile
+    int R = g_tune_R > 0 ? g_tune_R : 4;
+    if (g_tune_R <= 0)
+      while ((2 * R) * F_t <= MAX_THREADS && R < 64) R *= 2;
+    R = (R + 3) & ~3;
+    const int n_el = R * F_t;
+    const int threads = (n_el + 31) & ~31;
+    const size_t row_floats = (size_t)F_t * a.P + a.d;
+    const size_t stage_bytes = (size_t)R * row_floats * 4;
+    const size_t fixed = (size_t)2 * R * a.d * 4 + (size_t)2 * n_el * 4 + 8 * 8 + 128;
+    int stages = g_tune_stages > 0 ? g_tune_stages : 2;
+    const size_t smem = fixed + (size_t)stages * stage_bytes;
+    const long long n_tiles = N / R;
+    if (threads <= MAX_THREADS && smem <= 226 * 1024 && n_tiles > 0 && n_tiles < (1LL << 31)) {
+      a.R = R;
+      a.stages = stages;
+      a.n_tiles = n_tiles;
+      auto kern = rqs_coupling_tiled<MODE, KT, INVERSE>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) {
+        set_error("rqs_coupling: cannot set %zu B dynamic shared memory: %s", smem, cudaGetErrorString(e));
+        return NFK_ECUDA;
+      }
+      int ctas_per_sm = g_tune_ctas > 0 ? g_tune_ctas : (int)((227 * 1024) / (smem + 1024));
+      ctas_per_sm = max(1, min(ctas_per_sm, 2048 / threads));
+      const long long cap = (long long)sm_count() * ctas_per_sm;
+      const long long grid = n_tiles < cap ? n_tiles : cap;
+      kern<<<(unsigned)grid, threads, smem, st>>>(a);
+      count_launch();
+      if (int rc = check_launch("rqs_coupling_tiled")) return rc;
+      done = n_tiles * R;
     }
-    int ctas_per_sm = g_tune_ctas > 0 ? g_tune_ctas : max(1, (int)((227 * 1024) / (smem + 1024)));
-    ctas_per_sm = min(ctas_per_sm, max(1, 2048 / threads));
-    const long long cap = (long long)sm_count() * ctas_per_sm;
-    const long long grid = n_tiles < cap ? n_tiles : cap;
-    kern<<<(unsigned)grid, threads, smem, st>>>(a);
-    count_launch();
-    if (int rc = check_launch("rqs_coupling_tiled")) return rc;
   }
-  const long long done = n_tiles * R;
   if (done < N) {
     a.row0 = done;
     rqs_coupling_rows<MODE, KT, INVERSE><<<(unsigned)(N - done), 128, 0, st>>>(a);

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import RTOL_FP32, T, golden, parse_masks, rel_err
+from tests.helpers import RTOL_FP32, T, assert_parity, golden, parse_masks, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -42,8 +42,10 @@ def test_transform_matches_reference_fixtures(name, arith):
                 assert np.abs(got_bins.astype(int) - ref_bins.astype(int)).max() <= 1
             else:
                 assert np.array_equal(got_bins, ref_bins), (name, mask, inv, int((got_bins != ref_bins).sum()))
-            assert rel_err(out, g[p + ok]) <= RTOL_FP32, (name, mask, inv, rel_err(out, g[p + ok]))
-            assert rel_err(ld, g[p + lk]) <= RTOL_FP32, (name, mask, inv, rel_err(ld, g[p + lk]))
+            from oracle import nf_oracle as O
+            cu = O.nsf_cl_transform(x, params, size, dim, mask, K, B, inv)       # reference chain on ATen-CUDA
+            assert_parity(out, g[p + ok], cu[0], (name, mask, inv, "z"))
+            assert_parity(ld, g[p + lk], cu[1], (name, mask, inv, "log_det"))
 
 
 @pytest.mark.parametrize("arith", ["hybrid", "exact"])
@@ -56,8 +58,10 @@ def test_unconstrained_rqs_function(arith):
         for inv, s in ((False, "fwd"), (True, "inv")):
             out, lad, bins = ops.unconstrained_rqs(v, W, H, D, inv, B, arith, want_bins=True)
             assert np.array_equal(bins.cpu().numpy(), g[f"{tag}.{s}.bins"])
-            assert rel_err(out, g[f"{tag}.{s}.out"]) <= RTOL_FP32
-            assert rel_err(lad, g[f"{tag}.{s}.lad"]) <= RTOL_FP32
+            from oracle import nf_oracle as O
+            cu = O.rqs_elementwise(v, W, H, D, inv, B)
+            assert_parity(out, g[f"{tag}.{s}.out"], cu[0], (tag, s, "out"))
+            assert_parity(lad, g[f"{tag}.{s}.lad"], cu[1], (tag, s, "lad"))
 
 
 @pytest.mark.parametrize("N", [0, 1, 3, 8, 13, 4099])
@@ -74,11 +78,13 @@ def test_ragged_batches_and_accumulate(N):
         out, ld, bins = ops.rqs_coupling(x.cuda(), params.cuda(), 32, 2, [1], 8, 3.0, inv, "hybrid", want_bins=True)
         assert out.shape == (N, 64) and ld.shape == (N,)
         if N:
+            cu = O.nsf_cl_transform(x.cuda(), params.cuda(), 32, 2, [1], 8, 3.0, inv)
             assert np.array_equal(bins.cpu().numpy(), rb.numpy().astype(np.int8))
-            assert rel_err(out, ro) <= RTOL_FP32 and rel_err(ld, rl) <= RTOL_FP32
+            assert_parity(out, ro, cu[0], (N, inv, "z"))
+            assert_parity(ld, rl, cu[1], (N, inv, "log_det"))
             acc = torch.full((N,), 2.5, device="cuda")
             ops.rqs_coupling(x.cuda(), params.cuda(), 32, 2, [1], 8, 3.0, inv, "hybrid", logdet=acc)
-            assert rel_err(acc, rl + 2.5) <= RTOL_FP32
+            assert_parity(acc, rl + 2.5, cu[1] + 2.5, (N, inv, "accumulated log_det"))
 
 
 def test_tails_nan_and_all_outside():
@@ -126,7 +132,32 @@ def test_large_batch_vs_oracle_cpu_and_cuda():
             assert int((b != cb).sum()) == 0, (arith, inv, int((b != cb).sum()))
             n_cpu = int((b.cpu() != rb).sum())
             assert n_cpu <= 8, (arith, inv, n_cpu)
-            assert rel_err(out, ro) <= RTOL_FP32 and rel_err(ld, rl) <= RTOL_FP32
+            assert_parity(out, ro, co, (arith, inv, "z"))
+            assert_parity(ld, rl, cl, (arith, inv, "log_det"))
             if arith == "exact":
-                # bit-identical outputs to the ATen-on-CUDA chain
                 assert torch.equal(out.view(torch.int32), co.view(torch.int32))
+
+
+def test_exact_is_bitwise_aten_cuda():
+    """EXACT arithmetic reproduces the reference's op chain as ATen executes it on the GPU bit
+    for bit: knots, bins, outputs and per-element log|det| (free-function entry point, so the
+    per-element values are visible).  The same comparison against the CPU run of the SAME
+    reference code is printed: that pair already differs by more than 1e-5 on ill-conditioned
+    splines, which is why the fp32 gate in tests/helpers.py is stated against that noise."""
+    from oracle import nf_oracle as O
+    ops = _ops()
+    gen = torch.Generator().manual_seed(123)
+    M, K, B = 1 << 20, 8, 3.0
+    v = (torch.randn(M, generator=gen) * 1.5)
+    W = torch.randn(M, K, generator=gen) * 2
+    H = torch.randn(M, K, generator=gen) * 2
+    D = torch.randn(M, K - 1, generator=gen) * 2
+    for inv in (False, True):
+        co, cl, cb = O.rqs_elementwise(v.cuda(), W.cuda(), H.cuda(), D.cuda(), inv, B)
+        out, lad, bins = ops.unconstrained_rqs(v.cuda(), W.cuda(), H.cuda(), D.cuda(), inv, B, "exact", want_bins=True)
+        assert torch.equal(bins.long(), cb)
+        assert torch.equal(out.view(torch.int32), co.view(torch.int32)), int((out != co).sum())
+        assert torch.equal(lad.view(torch.int32), cl.view(torch.int32)), int((lad != cl).sum())
+        ro, rl, rb = O.rqs_elementwise(v, W, H, D, inv, B)
+        print(f"reference(ATen CUDA) vs reference(ATen CPU), inverse={inv}: out {rel_err(co, ro):.2e} "
+              f"lad {rel_err(cl, rl):.2e} bins differing {int((cb.cpu() != rb).sum())}")

@@ -41,7 +41,7 @@ def main():
     row_bytes = F_t * 23 * 4 + 2 * d * 4 + 8
     ld = torch.zeros(N, device=dev)
     for tune in a.tune:
-        R, th, st, ct = (int(v) for v in tune.split(","))
+        R, th, st, ct = (-1 if v == "g" else int(v) for v in tune.split(","))
         _lib.lib.nfk_set_tuning(R, th, st, ct)
         for mode in a.modes:
             for inv in (False, True):
