@@ -48,6 +48,7 @@ SIGNATURES = {
     "nfk_radial": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "nfk_gauss_logprob": (c_int, [_P, _P, c_float, _P, c_int64, c_int, c_float, _P]),
     "nfk_linear_f32": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "nfk_linear_bf16": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P]),
     "nfk_gemm_f32": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int64,
                              c_int, _P]),
     "nfk_gather_cols": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int64, _P]),

@@ -114,6 +114,10 @@ class NSF_CL(nn.Module):
     def _lower(self, x):
         if x.requires_grad and torch.is_grad_enabled():
             return x.reshape(-1, self.size, self.dim)[:, :, self._mask].flatten(start_dim=1)
+        if getattr(self.psi, "precision", None) == "bf16":
+            # gather straight into the padded bf16 operand of the first tensor-core GEMM
+            w = self.size * len(self._mask)
+            return _ops.gather_cols(x, self.size, self.dim, self._mask, bf16=True, ld_out=(w + 7) // 8 * 8)
         return _ops.gather_cols(x, self.size, self.dim, self._mask)
 
     def _transform(self, x, inverse, logdet=None):

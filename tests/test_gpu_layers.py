@@ -1,0 +1,165 @@
+"""GPU parity tests of the conditioner GEMMs, RealNVP, Planar, Radial and the model-level
+interface against the golden fixtures produced by the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import RTOL_BF16, RTOL_FP32, T, golden, parse_masks, rel_err, sub_sd
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from normalizingflow_b200 import _bf16, _ops, flows, models
+    return _ops, _bf16, flows, models
+
+
+@pytest.mark.parametrize("M,K,N,act", [(1, 1, 1, 0), (7, 32, 24, 1), (300, 33, 130, 1), (1000, 128, 736, 0),
+                                       (257, 800, 100, 1)])
+def test_linear_f32_matches_torch(M, K, N, act):
+    ops, _, _, _ = _mods()
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    if act:
+        ref = torch.tanh(ref)
+    y = ops.linear_f32(x.cuda(), w.cuda(), b.cuda(), act)
+    assert rel_err(y, ref) <= RTOL_FP32
+
+
+@pytest.mark.parametrize("M,K,N,act,f32", [(128, 64, 128, 1, False), (1, 8, 16, 0, True), (300, 32, 128, 1, False),
+                                           (1000, 128, 736, 0, True), (513, 800, 800, 1, False),
+                                           (129, 104, 100, 1, False), (4096, 128, 128, 1, False)])
+def test_linear_bf16_tcgen05_matches_torch(M, K, N, act, f32):
+    """tcgen05 GEMM vs an fp64 matmul of the SAME bf16-rounded operands: only accumulation
+    order, MUFU.TANH and the bf16 output rounding may differ."""
+    _, bf, _, _ = _mods()
+    g = torch.Generator().manual_seed(M + K + N)
+    x = (torch.randn(M, K, generator=g)).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N, generator=g)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    if act:
+        ref = torch.tanh(ref)
+    y = bf.linear_bf16(x.cuda(), w.cuda(), b.cuda(), act, f32)
+    torch.cuda.synchronize()
+    y = y[:, :N].float()
+    tol = 2e-3 if (f32 and not act) else 1e-2
+    assert rel_err(y, ref) <= tol, rel_err(y, ref)
+
+
+def test_fcnn_fp32_and_bf16_vs_reference():
+    ops, bf, flows, _ = _mods()
+    g = golden("nsfcl_d64.npz")
+    sd = sub_sd(g, "m1.sd.psi.")
+    net = flows.FCNN(32, 23 * 32, 24)
+    net.load_state_dict(sd)
+    net = net.cuda()
+    x = T(g["m1.x"]).reshape(-1, 32, 2)[:, :, 1].contiguous()
+    ref = T(g["m1.params"]).reshape(x.shape[0], -1)
+    with torch.no_grad():
+        y32 = net(x.cuda())
+        net.precision = "bf16"
+        y16 = net(x.cuda())
+    assert rel_err(y32, ref) <= RTOL_FP32
+    assert rel_err(y16, ref) <= RTOL_BF16
+
+
+def test_realnvp_matches_reference():
+    _, _, flows, _ = _mods()
+    g = golden("realnvp.npz")
+    for tag in ("d2", "d64", "d6"):
+        d, H = int(g[tag + ".d"]), int(g[tag + ".H"])
+        layer = flows.RealNVP(d, hidden_dim=H)
+        layer.load_state_dict(sub_sd(g, tag + ".sd."))
+        layer = layer.cuda()
+        with torch.no_grad():
+            z, ld = layer.forward(T(g[tag + ".x"]).cuda())
+            x, ldi = layer.inverse(T(g[tag + ".zin"]).cuda())
+        assert rel_err(z, g[tag + ".z"]) <= RTOL_FP32 and rel_err(ld, g[tag + ".ld"]) <= RTOL_FP32
+        assert rel_err(x, g[tag + ".x_inv"]) <= RTOL_FP32 and rel_err(ldi, g[tag + ".ld_inv"]) <= RTOL_FP32
+
+
+def test_planar_radial_match_reference():
+    _, _, flows, _ = _mods()
+    g = golden("planar_radial.npz")
+    for tag, d in (("d128", 128), ("d5", 5)):
+        x = T(g[tag + ".x"]).cuda()
+        pl = flows.Planar(d)
+        pl.load_state_dict({k: T(g[f"{tag}.planar.{k}"]) for k in ("w", "u", "b")})
+        rd = flows.Radial(d)
+        rd.load_state_dict({k: T(g[f"{tag}.radial.{k}"]) for k in ("x0", "log_alpha", "beta")})
+        pl, rd = pl.cuda(), rd.cuda()
+        with torch.no_grad():
+            z, ld = pl.forward(x)
+            zr, ldr = rd.forward(x)
+        assert rel_err(z, g[tag + ".planar.z"]) <= RTOL_FP32 and rel_err(ld, g[tag + ".planar.ld"]) <= RTOL_FP32
+        assert ldr.shape == (1,)                                       # Q9
+        assert rel_err(zr, g[tag + ".radial.z"]) <= RTOL_FP32 and rel_err(ldr, g[tag + ".radial.ld"]) <= RTOL_FP32
+        with pytest.raises(NotImplementedError):
+            pl.inverse(x)
+
+
+def test_nsf_cl_layers_whole_layer():
+    _, _, flows, _ = _mods()
+    for name in ("nsfcl_d64.npz", "nsfcl_lj38.npz"):
+        g = golden(name)
+        size, dim, K, B, H = int(g["size"]), int(g["dim"]), int(g["K"]), float(g["B"]), int(g["H"])
+        for mi, mask in enumerate(parse_masks(g)):
+            p = f"m{mi}."
+            layer = flows.NSF_CL(size, dim=dim, K=K, B=B, hidden_dim=H, mask=mask)
+            layer.load_state_dict(sub_sd(g, p + "sd."))
+            layer = layer.cuda()
+            with torch.no_grad():
+                z, ld = layer.forward(T(g[p + "x"]).cuda())
+                xi, ldi = layer.inverse(T(g[p + "zin"]).cuda())
+            # conditioner in fp32 differs from the reference's addmm by round-off only
+            assert rel_err(z, g[p + "z"]) <= 2e-5 and rel_err(ld, g[p + "ld"]) <= 5e-5, (name, mask)
+            assert rel_err(xi, g[p + "x_inv"]) <= 2e-5 and rel_err(ldi, g[p + "ld_inv"]) <= 5e-5, (name, mask)
+
+
+def test_models_match_reference():
+    _, _, flows, models = _mods()
+    g = golden("models.npz")
+    dev = torch.device("cuda")
+    fl = [flows.NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=16, mask=[i % 2]) for i in range(8)]
+    m = models.NormalizingFlowModel(models.GaussianPrior(64, device=dev), fl, device=dev)
+    m.load_state_dict(sub_sd(g, "nsf.sd."))
+    m = m.to(dev)
+    z, plp, ld = m.forward(T(g["nsf.x"]).cuda())
+    assert ld.dtype == torch.float32 and ld.shape == (64,)
+    for a, k in ((z, "nsf.z"), (plp, "nsf.prior_lp"), (ld, "nsf.ld")):
+        assert rel_err(a.detach(), g[k]) <= 5e-5, k
+    ev = m.evaluate(T(g["nsf.x"]).cuda())
+    assert not ev.requires_grad and rel_err(ev, g["nsf.evaluate"]) <= 5e-5
+    x, ldi = m.inverse(T(g["nsf.zin"]).cuda())
+    assert rel_err(x.detach(), g["nsf.x_inv"]) <= 5e-5 and rel_err(ldi.detach(), g["nsf.ld_inv"]) <= 5e-5
+    xs, lpx, zs = m.sample(10)
+    assert xs.shape == (10, 64) and lpx.shape == (10,) and zs.shape == (10, 64) and not xs.requires_grad
+    # bf16 conditioner: 1e-2 class
+    for f in fl:
+        f.psi.precision = "bf16"
+    with torch.no_grad():
+        z16, plp16, ld16 = m.forward(T(g["nsf.x"]).cuda())
+    assert rel_err(z16, g["nsf.z"]) <= 5e-2 and rel_err(ld16, g["nsf.ld"]) <= 5e-2
+
+    fl = [flows.RealNVP(2, hidden_dim=12) for _ in range(8)]
+    m = models.NormalizingFlowModel(models.GaussianPrior(2, device=dev), fl, device=dev)
+    m.load_state_dict(sub_sd(g, "rnvp.sd."))
+    m = m.to(dev)
+    with torch.no_grad():
+        z, plp, ld = m.forward(T(g["rnvp.x"]).cuda())
+        x, ldi = m.inverse(T(g["rnvp.x"]).cuda())
+    assert rel_err(z, g["rnvp.z"]) <= 2e-5 and rel_err(ld, g["rnvp.ld"]) <= 2e-5 and rel_err(plp, g["rnvp.prior_lp"]) <= 2e-5
+    assert rel_err(x, g["rnvp.x_inv"]) <= 2e-5 and rel_err(ldi, g["rnvp.ld_inv"]) <= 2e-5
+
+    fl = [flows.Planar(16) for _ in range(6)]
+    m = models.NormalizingFlowModel(models.GaussianPrior(16, device=dev), fl, device=dev)
+    m.load_state_dict(sub_sd(g, "planar.sd."))
+    m = m.to(dev)
+    with torch.no_grad():
+        z, plp, ld = m.forward(T(g["planar.x"]).cuda())          # six layers, ONE fused launch
+    assert rel_err(z, g["planar.z"]) <= 2e-5 and rel_err(ld, g["planar.ld"]) <= 2e-5
+    assert rel_err(plp, g["planar.prior_lp"]) <= 2e-5
