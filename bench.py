@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="run the layer as separate GEMM + spline kernels")
     return ap.parse_args()
 
 
@@ -197,6 +198,7 @@ def run_native(a):
              for i in range(LAYERS)]
     for f in flows:
         f.psi.precision = cond
+        f.fused = not a.no_fused
     model = NormalizingFlowModel(GaussianPrior(D, device=dev), flows, device=dev)
     model.load_state_dict(sd)
     model = model.to(dev)
@@ -294,17 +296,26 @@ def run_native(a):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        n_l, k_ms = ksum.get("rqs_coupling", (0, 0.0))
+        # dominant kernel of the step: the fused layer kernel when the layers are eligible for it,
+        # else the stand-alone spline kernel.  Either way "achieved" is quoted on the ALGORITHMIC
+        # bytes of the unfused transform (3,464 B per row per layer pass), so a
+        # fused kernel that keeps the spline parameters on chip can read above 1.0.
+        kname, (n_l, k_ms) = max(ksum.items(), key=lambda kv: kv[1][1]) if ksum else ("none", (0, 0.0))
         avg_ms = k_ms / max(1, n_l)
         achieved = ROW_BYTES_PER_LAYER * N / (avg_ms * 1e-3) / 1e9 if n_l else None
-        roofline = {"bound": "hbm", "kernel": "rqs_coupling_tiled", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        actual_row_bytes = {"nsf_pairs_fused": 64 * 4 * 2 + 8, "rqs_coupling": ROW_BYTES_PER_LAYER}.get(kname)
+        roofline = {"bound": "hbm", "kernel": {"nsf_pairs_fused": "nsf_pairs_fused_kernel (conditioner GEMMs + RQS "
+                                               "epilogue, one launch per layer pass)",
+                                               "rqs_coupling": "rqs_coupling_pairs"}.get(kname, kname),
+                    "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": ROW_BYTES_PER_LAYER * N, "avg_launch_ms": avg_ms,
-                    "launches_timed": n_l, "share_of_step": (k_ms / ms) if ms else None}
+                    "algorithmic_bytes_per_launch": ROW_BYTES_PER_LAYER * N,
+                    "hbm_bytes_per_launch_by_design": actual_row_bytes * N if actual_row_bytes else None,
+                    "avg_launch_ms": avg_ms, "launches_timed": n_l, "share_of_step": (k_ms / ms) if ms else None}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                roofline["traffic"] = json.load(open(tp)).get("rqs_coupling_tiled_bytes_per_launch")
+                roofline["traffic"] = json.load(open(tp)).get(kname + "_bytes_per_launch")
             except Exception:
                 pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
@@ -312,7 +323,7 @@ def run_native(a):
                 "vs_baseline": None, "dtype": "f32" if cond == "fp32" else "f32 transforms / bf16 conditioner GEMMs",
                 "data": "synthetic",
                 "config": {"workload": workload_name(a), "hidden": a.hidden, "arith": a.arith, "conditioner": cond,
-                           "global_batch": world * N, "parallelism": f"batch-sharded x{world}",
+                           "fused_layer_kernel": bool(not a.no_fused and cond == "bf16"), "global_batch": world * N, "parallelism": f"batch-sharded x{world}",
                            "l2": "inputs larger than L2 (x 268 MB, spline params 3.1 GB per layer)"},
                 "roofline": roofline, "clocks": clk, "gpu_launches": launches, "e2e": e2e}
         if not a.no_cpu_baseline:

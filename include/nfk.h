@@ -149,6 +149,20 @@ int nfk_linear_bf16(const void* X, int64_t ldx, const void* W, int64_t ldw, cons
                     void* Y, int64_t ldy, int64_t M, int K, int Nout, int act, int out_f32,
                     void* stream);
 
+/* ---- fused NSF coupling layer: conditioner MLP (tcgen05 bf16 GEMMs, fp32 accumulation in TMEM)
+ * with the RQS transform as the epilogue of its last GEMM -- replaces NSF_CL.forward/inverse
+ * (nf/flows.py:227-253) in one launch for size = 32, dim = 2, one masked column (mask_col),
+ * K = 8, hidden width <= 128.  x, out [N, 64] fp32, N a multiple of
+ * nfk_nsf_fused_rows_per_tile(); logdet [N] (+= when accumulate).  w1_img / w2_img / w3_img are
+ * the bf16 weights padded to 128 x 64, 128 x 128 and 8 chunks of 96 x 128 (each feature's 23
+ * rows padded to 24) in the K-major SWIZZLE_128B shared-memory layout (16-byte chunk j of row r
+ * holds source chunk j ^ (r % 8)); b1, b2 [128], b3 [32*24] fp32 padded the same way. */
+int nfk_nsf_fused_rows_per_tile(void);
+int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w1_img,
+                        const void* w2_img, const void* w3_img, const float* b1, const float* b2,
+                        const float* b3, int64_t N, int mask_col, float B, int inverse,
+                        int accumulate, int arith, void* stream);
+
 /* x[:, cols] gather -> dense fp32 or bf16 [N, size*n_cols] (conditioner input, flows.py:230) */
 int nfk_gather_cols(const float* x, void* out, int64_t N, int size, int dim,
                     const int32_t* cols, int n_cols, int out_bf16, int64_t ld_out,

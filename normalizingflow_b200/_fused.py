@@ -1,0 +1,95 @@
+"""Host side of the fused NSF coupling-layer kernel (csrc/nsf_fused.cu): packs the conditioner
+weights once per parameter version into the bf16 SWIZZLE_128B shared-memory images the kernel
+bulk-copies, and launches it.  Eligible layers: size = 32, dim = 2, one masked column, K = 8,
+hidden width <= 128 (padded with zero rows/columns to 128, which leaves the MLP unchanged:
+tanh(0) = 0 feeds zero weights)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, _ops
+from ._lib import call, f32c, ptr, require_cuda, stream_ptr
+
+ROWS = 128
+HP, K1P, NF, PC, CF = 128, 64, 32, 24, 4
+
+
+def eligible(layer) -> bool:
+    return (layer.size == 32 and layer.dim == 2 and len(layer._mask) == 1 and layer.K == 8
+            and getattr(layer.psi, "precision", None) == "bf16" and _lib.have("nfk_nsf_pairs_fused")
+            and hasattr(layer.psi, "network") and layer.psi.network[0].out_features <= HP
+            and layer.psi.network[0].in_features == 32)
+
+
+def _swizzle_image(mat):
+    """[rows, 64*KB] bf16 -> [KB, rows, 8, 8]: K blocks of 128-byte rows whose 16-byte chunk j holds
+    source chunk j ^ (row % 8) (the canonical K-major SWIZZLE_128B layout tcgen05.mma reads)."""
+    rows, kp = mat.shape
+    kb = kp // 64
+    blk = mat.reshape(rows, kb, 8, 8).permute(1, 0, 2, 3)
+    r = torch.arange(rows, device=mat.device)[:, None]
+    j = torch.arange(8, device=mat.device)[None, :]
+    src = j ^ (r & 7)
+    return blk[:, r, src, :].contiguous()
+
+
+def packed(layer):
+    net = layer.psi.network
+    l0, l2, l4 = net[0], net[2], net[4]
+    key = tuple((l.weight._version, l.weight.data_ptr(), l.bias._version) for l in (l0, l2, l4))
+    cache = getattr(layer, "_fused_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    dev = l0.weight.device
+    H = l0.out_features
+    bf = torch.bfloat16
+    w1 = torch.zeros((HP, K1P), dtype=bf, device=dev)
+    w1[:H, :32] = l0.weight.detach().to(bf)
+    w2 = torch.zeros((HP, HP), dtype=bf, device=dev)
+    w2[:H, :H] = l2.weight.detach().to(bf)
+    w3 = torch.zeros((NF, PC, HP), dtype=bf, device=dev)
+    w3[:, :23, :H] = l4.weight.detach().to(bf).reshape(NF, 23, H)
+    w3 = w3.reshape(NF // CF, CF * PC, HP)
+    b1 = torch.zeros(HP, dtype=torch.float32, device=dev)
+    b1[:H] = l0.bias.detach().float()
+    b2 = torch.zeros(HP, dtype=torch.float32, device=dev)
+    b2[:H] = l2.bias.detach().float()
+    b3 = torch.zeros((NF, PC), dtype=torch.float32, device=dev)
+    b3[:, :23] = l4.bias.detach().float().reshape(NF, 23)
+    pk = dict(w1=_swizzle_image(w1), w2=_swizzle_image(w2),
+              w3=torch.stack([_swizzle_image(w3[c]) for c in range(NF // CF)]).contiguous(),
+              b1=b1, b2=b2, b3=b3.reshape(-1).contiguous())
+    layer._fused_cache = (key, pk)
+    return pk
+
+
+def run(layer, x, inverse, logdet=None):
+    """(out, logdet) of one NSF_CL layer through the fused kernel; rows beyond the last full
+    128-row tile go through the unfused kernels."""
+    dev = require_cuda(x, logdet)
+    x = f32c(x)
+    N = x.shape[0]
+    pk = packed(layer)
+    out = torch.empty((N, 64), dtype=torch.float32, device=dev)
+    accumulate = logdet is not None
+    if not accumulate:
+        logdet = torch.empty((N,), dtype=torch.float32, device=dev)
+    n_main = N // ROWS * ROWS
+    if n_main:
+        with torch.cuda.device(dev):
+            tm = _ops.KERNEL_TIMER
+            ev = tm.start("nsf_pairs_fused", dev) if tm is not None else None
+            call("nfk_nsf_pairs_fused", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
+                 ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), n_main, layer._mask[0], float(layer.B),
+                 int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), stream_ptr(dev))
+            if ev is not None:
+                tm.stop(ev, dev)
+    if n_main < N:
+        xt = x[n_main:]
+        params = layer.psi(layer._lower(xt)).reshape(N - n_main, 32, 23)
+        ot, lt, _ = _ops.rqs_coupling(xt, params, 32, 2, layer._mask, 8, float(layer.B), inverse, layer.arith,
+                                      logdet=logdet[n_main:] if accumulate else None)
+        out[n_main:] = ot
+        if not accumulate:
+            logdet[n_main:] = lt
+    return out, logdet

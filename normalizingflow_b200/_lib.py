@@ -49,6 +49,9 @@ SIGNATURES = {
     "nfk_gauss_logprob": (c_int, [_P, _P, c_float, _P, c_int64, c_int, c_float, _P]),
     "nfk_linear_f32": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "nfk_linear_bf16": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "nfk_nsf_fused_rows_per_tile": (c_int, []),
+    "nfk_nsf_pairs_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int,
+                                    c_int, _P]),
     "nfk_gemm_f32": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int64,
                              c_int, _P]),
     "nfk_gather_cols": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int64, _P]),

@@ -1,0 +1,375 @@
+// One NSF coupling layer in ONE kernel: conditioner MLP on the tensor cores + RQS transform as
+// the epilogue of its last GEMM.  Replaces NSF_CL.forward/inverse entirely (reference
+// nf/flows.py:227-253 incl. FCNN nf/flows.py:26-35 and nf/utils.py:20-152) for the headline
+// geometry: size = 32, dim = 2 (32 conditioning + 32 transformed columns), K = 8 bins,
+// hidden width <= 128.  The [N, 32, 23] spline-parameter tensor (2,944 B/row each way) never
+// exists in HBM: per row the kernel reads 256 B of x and writes 256 B of z plus the log-det.
+//
+// Persistent CTA (16 warps), 128 rows per tile:
+//   P1  x tile (TMA bulk, double buffered) -> conditioning columns -> bf16 -> A operand in the
+//       K-major SWIZZLE_128B layout (shared memory)
+//   P2  GEMM1  D12[128x128] = A1 W1^T      (tcgen05.mma, M=128 N=128 K=16 x4, accumulators in TMEM)
+//   P3  epilogue 1: tcgen05.ld -> +b1 -> tanh -> bf16 -> A operand (same buffer)
+//   P4  GEMM2  D12 = A2 W2^T ; P5 epilogue 2 -> A3
+//   P6  for each of 8 chunks of 4 features (4 x 24 = 96 accumulator columns, the 23 parameters
+//       of a feature padded to 24): GEMM3 chunk into one of two TMEM buffers while the previous
+//       chunk's epilogue runs: thread (row, feature) pulls its 24 raw parameters out of TMEM,
+//       adds b3 and evaluates bin search + spline + log|det| in registers (rqs_math.cuh), writing
+//       the output pair in place into the x tile.  W3 chunks stream L2 -> shared memory through a
+//       3-stage TMA bulk ring (weights are pre-swizzled into their shared-memory image once).
+//   P7  row log-det = sum over the 32 features (4 partial sums per row), output tile -> TMA
+//       bulk store.
+#include "rqs_math.cuh"
+#include "tc05.cuh"
+
+namespace nfk {
+
+constexpr int FU_ROWS = 128;
+constexpr int FU_THREADS = 512;
+constexpr int FU_HP = 128;        // padded hidden width
+constexpr int FU_K1P = 64;        // padded conditioner input width
+constexpr int FU_NF = 32;         // transformed features
+constexpr int FU_PC = 24;         // accumulator columns per feature (23 used)
+constexpr int FU_CF = 4;          // features per GEMM3 chunk
+constexpr int FU_NC = FU_CF * FU_PC;      // 96 columns per chunk
+constexpr int FU_NCHUNK = FU_NF / FU_CF;  // 8
+constexpr int FU_W3STAGES = 3;
+
+constexpr uint32_t FU_W1_BYTES = FU_HP * 128;                    // [128 x 64] bf16
+constexpr uint32_t FU_W2_BYTES = 2 * FU_HP * 128;                // 2 K blocks of [128 x 64]
+constexpr uint32_t FU_A_BYTES = 2 * FU_ROWS * 128;               // 2 K blocks of [128 x 64]
+constexpr uint32_t FU_W3C_BYTES = 2 * FU_NC * 128;               // 2 K blocks of [96 x 64]
+constexpr int FU_XLD = 68;        // padded x-tile row stride in floats (272 B): the 32 rows a warp
+                                  // touches at one column then fall on 8 bank groups, not 1
+constexpr uint32_t FU_XROW_BYTES = 64 * 4;
+constexpr uint32_t FU_X_BYTES = FU_ROWS * FU_XLD * 4;            // padded fp32 [128 x 64] tile
+
+struct FusedArgs {
+  const float* x;
+  float* out;
+  float* logdet;
+  const void* w1_img;     // FU_W1_BYTES, pre-swizzled
+  const void* w2_img;     // FU_W2_BYTES
+  const void* w3_img;     // FU_NCHUNK * FU_W3C_BYTES
+  const float* b1;        // [128]
+  const float* b2;        // [128]
+  const float* b3;        // [32*24]
+  long long n_tiles;
+  int cond_first;         // 1: conditioning column is column 0 of each pair (mask = [0])
+  int accumulate;
+  RqsConsts c;
+};
+
+// 24 raw parameters of one feature held in registers (+ bias from shared memory)
+struct RegParams {
+  const uint32_t* v;
+  const float* b;
+  __device__ __forceinline__ float operator()(int i) const { return __uint_as_float(v[i]) + b[i]; }
+  __device__ __forceinline__ float dyn(int base, int i) const {
+    // K = 8: D logits are entries 16..22; select without indexing the register array
+    float r = __uint_as_float(v[16]) + b[16];
+#pragma unroll
+    for (int j = 1; j < 7; ++j)
+      if (i == j) r = __uint_as_float(v[16 + j]) + b[16 + j];
+    return r;
+  }
+};
+
+template <int MODE, bool INVERSE>
+__global__ void __launch_bounds__(FU_THREADS, 1)
+nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  unsigned char* sW1 = sm;
+  unsigned char* sW2 = sW1 + FU_W1_BYTES;
+  unsigned char* sA = sW2 + FU_W2_BYTES;
+  unsigned char* sW3 = sA + FU_A_BYTES;
+  float* sX = reinterpret_cast<float*>(sW3 + FU_W3STAGES * FU_W3C_BYTES);      // 2 tiles
+  float* sB1 = sX + 2 * FU_ROWS * FU_XLD;
+  float* sB2 = sB1 + FU_HP;
+  float* sB3 = sB2 + FU_HP;
+  float* sLad = reinterpret_cast<float*>(sA);       // [4][128], aliases the A operand (idle in P7)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB3 + FU_NF * FU_PC);
+  uint64_t* bar_w = bars;            // W1 + W2 resident
+  uint64_t* bar_x = bars + 1;        // [2]
+  uint64_t* bar_w3 = bars + 3;       // [3]
+  uint64_t* bar_mma = bars + 6;      // GEMM1 / GEMM2 done
+  uint64_t* bar_d3 = bars + 7;       // [2] GEMM3 chunk done
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3;            // TMEM lane quadrant of this warp
+  const int slice = warp >> 2;       // column slice (epilogues 1/2) or feature-in-chunk (epilogue 3)
+  const int row = q * 32 + lane;     // row of the tile this thread owns in every epilogue
+
+  const unsigned first = blockIdx.x, stride = gridDim.x;
+  const unsigned n_tiles = (unsigned)a.n_tiles;
+  const unsigned my_tiles = (n_tiles > first) ? (n_tiles - first + stride - 1) / stride : 0;
+  const unsigned total_chunks = my_tiles * FU_NCHUNK;
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < FU_HP; i += FU_THREADS) {
+    sB1[i] = a.b1[i];
+    sB2[i] = a.b2[i];
+  }
+  for (int i = tid; i < FU_NF * FU_PC; i += FU_THREADS) sB3[i] = a.b3[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tD12 = tmem;                       // 128 columns
+  const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+
+  // warp 0, all lanes: one 256-byte bulk copy per row into the padded tile
+  auto issue_x = [&](unsigned it) {
+    const size_t tile = first + (size_t)it * stride;
+    const int s = it & 1;
+    if (lane == 0) mbar_expect_tx(&bar_x[s], FU_ROWS * FU_XROW_BYTES);
+    __syncwarp();
+    for (int r = lane; r < FU_ROWS; r += 32)
+      bulk_g2s(sX + (s * FU_ROWS + r) * FU_XLD, a.x + (tile * FU_ROWS + r) * 64, FU_XROW_BYTES, &bar_x[s]);
+  };
+  auto issue_w3 = [&](unsigned g) {   // g: running chunk counter of this CTA
+    const int s = g % FU_W3STAGES;
+    const int c = g % FU_NCHUNK;
+    mbar_expect_tx(&bar_w3[s], FU_W3C_BYTES);
+    bulk_g2s(sW3 + s * FU_W3C_BYTES, reinterpret_cast<const unsigned char*>(a.w3_img) + (size_t)c * FU_W3C_BYTES,
+             FU_W3C_BYTES, &bar_w3[s]);
+  };
+  if (tid == 0 && my_tiles) {
+    mbar_expect_tx(bar_w, FU_W1_BYTES + FU_W2_BYTES);
+    bulk_g2s(sW1, a.w1_img, FU_W1_BYTES, bar_w);
+    bulk_g2s(sW2, a.w2_img, FU_W2_BYTES, bar_w);
+    for (unsigned g = 0; g < FU_W3STAGES && g < total_chunks; ++g) issue_w3(g);
+  }
+  if (warp == 0 && my_tiles) issue_x(0);
+
+  const uint32_t idesc12 = make_idesc_bf16(FU_ROWS, FU_HP);
+  const uint32_t idesc3 = make_idesc_bf16(FU_ROWS, FU_NC);
+  const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+
+  // GEMM3 chunk issue (thread 0): D3[g & 1] = A3 * W3chunk^T
+  auto issue_mma3 = [&](unsigned g) {
+    const int s = g % FU_W3STAGES;
+    mbar_wait(&bar_w3[s], (g / FU_W3STAGES) & 1);
+    tc_fence_after();
+    const uint32_t d = tmem + 128 + (g & 1) * FU_NC;
+    const uint32_t bbase = aW3 + s * FU_W3C_BYTES;
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(d, make_desc_sw128(aA + kb * (FU_ROWS * 128) + k * 32),
+                  make_desc_sw128(bbase + kb * (FU_NC * 128) + k * 32), idesc3, (kb | k) ? 1u : 0u);
+    umma_commit(&bar_d3[g & 1]);
+  };
+
+  // epilogue of GEMM1/GEMM2: this warp's 32 columns -> +bias -> tanh -> bf16 -> A operand
+  auto hidden_epilogue = [&](const float* bias) {
+    uint32_t v[32];
+    tmem_ld32(tD12 + lane_sel + slice * 32, v);
+    tmem_ld_wait();
+    const int kb = slice >> 1;
+    unsigned char* dst = sA + kb * (FU_ROWS * 128) + row * 128;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint4 u;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = tanh_approx(__uint_as_float(v[t * 8 + j]) + bias[slice * 32 + t * 8 + j]);
+      u.x = pack_bf16x2(f[0], f[1]);
+      u.y = pack_bf16x2(f[2], f[3]);
+      u.z = pack_bf16x2(f[4], f[5]);
+      u.w = pack_bf16x2(f[6], f[7]);
+      const int ch = (slice & 1) * 4 + t;
+      *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = u;
+    }
+  };
+
+  if (my_tiles) mbar_wait(bar_w, 0);
+
+  unsigned g = 0;                 // running GEMM3 chunk counter
+  for (unsigned it = 0; it < my_tiles; ++it) {
+    const size_t tile = first + (size_t)it * stride;
+    float* xs = sX + (it & 1) * FU_ROWS * FU_XLD;
+
+    // ---- P1: conditioning columns -> A1 (K block 0; columns 32..63 are zero padding)
+    mbar_wait(&bar_x[it & 1], (it >> 1) & 1);
+    for (int i = tid; i < FU_ROWS * 8; i += FU_THREADS) {
+      const int r = i >> 3, ch = i & 7;
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (ch < 4) {
+        const float* xr = xs + r * FU_XLD + (a.cond_first ? 0 : 1);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = xr[2 * (ch * 8 + j)];
+        u.x = pack_bf16x2(f[0], f[1]);
+        u.y = pack_bf16x2(f[2], f[3]);
+        u.z = pack_bf16x2(f[4], f[5]);
+        u.w = pack_bf16x2(f[6], f[7]);
+      }
+      *reinterpret_cast<uint4*>(sA + r * 128 + ((ch ^ (r & 7)) << 4)) = u;
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- P2: GEMM1
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < FU_K1P / 16; ++k)
+        umma_bf16(tD12, make_desc_sw128(aA + k * 32), make_desc_sw128(aW1 + k * 32), idesc12, k ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    // ---- P3: epilogue 1 -> A2
+    hidden_epilogue(sB1);
+    tc_fence_before();
+    fence_proxy_async();
+    __syncthreads();
+    // ---- P4: GEMM2
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tD12, make_desc_sw128(aA + kb * (FU_ROWS * 128) + k * 32),
+                    make_desc_sw128(aW2 + kb * (FU_HP * 128) + k * 32), idesc12, (kb | k) ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 1);
+    tc_fence_after();
+    // ---- P5: epilogue 2 -> A3
+    hidden_epilogue(sB2);
+    tc_fence_before();
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- P6: GEMM3 chunks with the spline transform as their epilogue
+    if (tid == 0) issue_mma3(g);
+    float lad_acc = 0.f;
+    for (int c = 0; c < FU_NCHUNK; ++c, ++g) {
+      if (tid == 0 && c + 1 < FU_NCHUNK) issue_mma3(g + 1);
+      if (warp == 0 && c == 2 && it + 1 < my_tiles) {
+        bulk_wait_read<0>();            // this lane's stores that drained the other x buffer are done
+        __syncwarp();
+        issue_x(it + 1);
+      }
+      mbar_wait(&bar_d3[c & 1], (c >> 1) & 1);
+      tc_fence_after();
+      {
+        const int f = c * FU_CF + slice;                     // feature of this thread
+        uint32_t v[24];
+        const uint32_t t = tmem + 128 + (c & 1) * FU_NC + lane_sel + slice * FU_PC;
+        tmem_ld16(t, v);
+        tmem_ld8(t + 16, v + 16);
+        tmem_ld_wait();
+        float2* pr = reinterpret_cast<float2*>(xs + row * FU_XLD + 2 * f);
+        const float2 xc = *pr;
+        const RqsOut o = rqs_element<MODE, 8, INVERSE, true>(RegParams{v, sB3 + f * FU_PC},
+                                                              a.cond_first ? xc.y : xc.x, a.c);
+        *pr = make_float2(a.cond_first ? xc.x : xc.y, o.y);  // (conditioning, transformed): Q5
+        lad_acc += o.lad;
+      }
+      tc_fence_before();
+      __syncthreads();                  // D3[c&1] and the W3 stage of chunk g are free
+      if (tid == 0 && g + FU_W3STAGES < total_chunks) issue_w3(g + FU_W3STAGES);
+    }
+
+    // ---- P7: row log-det and output tile
+    sLad[slice * FU_ROWS + row] = lad_acc;
+    fence_proxy_async();
+    __syncthreads();
+    if (tid < FU_ROWS) {
+      const float t = (sLad[tid] + sLad[FU_ROWS + tid]) + (sLad[2 * FU_ROWS + tid] + sLad[3 * FU_ROWS + tid]);
+      float* ldp = a.logdet + tile * FU_ROWS + tid;
+      *ldp = a.accumulate ? *ldp + t : t;
+    }
+    if (warp == 0) {
+      for (int r = lane; r < FU_ROWS; r += 32)
+        bulk_s2g(a.out + (tile * FU_ROWS + r) * 64, xs + r * FU_XLD, FU_XROW_BYTES);
+      bulk_commit();
+    }
+    __syncthreads();                    // sLad (= the A operand buffer) is rewritten by the next tile
+  }
+  if (warp == 0) bulk_wait_all<0>();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+constexpr size_t FU_SMEM = FU_W1_BYTES + FU_W2_BYTES + FU_A_BYTES + FU_W3STAGES * FU_W3C_BYTES + 2 * FU_X_BYTES +
+                           (2 * FU_HP + FU_NF * FU_PC) * 4 + 16 * 8 + 1024;
+static_assert(FU_SMEM <= 227 * 1024, "fused layer kernel exceeds the 227 KB shared-memory limit");
+
+RqsConsts make_rqs_consts(int K, float B);   // rqs_coupling.cu
+
+template <int MODE, bool INVERSE>
+static int launch_fused(const FusedArgs& a, cudaStream_t st) {
+  auto kern = nsf_pairs_fused_kernel<MODE, INVERSE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM);
+  if (e != cudaSuccess) {
+    set_error("nsf_fused: cannot set %zu B dynamic shared memory: %s", FU_SMEM, cudaGetErrorString(e));
+    return NFK_ECUDA;
+  }
+  const long long cap = sm_count();
+  const long long grid = a.n_tiles < cap ? a.n_tiles : cap;
+  kern<<<(unsigned)grid, FU_THREADS, FU_SMEM, st>>>(a);
+  count_launch();
+  return check_launch("nsf_pairs_fused");
+}
+
+}  // namespace nfk
+
+using namespace nfk;
+
+extern "C" {
+
+int nfk_nsf_fused_rows_per_tile(void) { return FU_ROWS; }
+
+int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w1_img, const void* w2_img,
+                        const void* w3_img, const float* b1, const float* b2, const float* b3, int64_t N,
+                        int mask_col, float B, int inverse, int accumulate, int arith, void* stream) {
+  NFK_REQUIRE(N >= 0 && N % FU_ROWS == 0, "nsf_pairs_fused: N must be a multiple of %d (got %lld)", FU_ROWS,
+              (long long)N);
+  NFK_REQUIRE(mask_col == 0 || mask_col == 1, "nsf_pairs_fused: mask column must be 0 or 1");
+  NFK_REQUIRE(arith >= NFK_ARITH_EXACT && arith <= NFK_ARITH_FAST, "nsf_pairs_fused: bad arith %d", arith);
+  NFK_REQUIRE(B > 0.f, "nsf_pairs_fused: tail bound must be positive");
+  if (N == 0) return NFK_OK;
+  NFK_REQUIRE(x && out && logdet && w1_img && w2_img && w3_img && b1 && b2 && b3,
+              "nsf_pairs_fused: null device pointer");
+  NFK_REQUIRE(x != out, "nsf_pairs_fused: out must not alias x");
+  NFK_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                reinterpret_cast<uintptr_t>(w1_img) | reinterpret_cast<uintptr_t>(w2_img) |
+                reinterpret_cast<uintptr_t>(w3_img)) & 15) == 0,
+              "nsf_pairs_fused: pointers must be 16-byte aligned");
+  FusedArgs a{};
+  a.x = x;
+  a.out = out;
+  a.logdet = logdet;
+  a.w1_img = w1_img;
+  a.w2_img = w2_img;
+  a.w3_img = w3_img;
+  a.b1 = b1;
+  a.b2 = b2;
+  a.b3 = b3;
+  a.n_tiles = N / FU_ROWS;
+  a.cond_first = (mask_col == 0);
+  a.accumulate = accumulate;
+  a.c = make_rqs_consts(8, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool inv = inverse != 0;
+  if (arith == NFK_ARITH_EXACT)
+    return inv ? launch_fused<NFK_ARITH_EXACT, true>(a, st) : launch_fused<NFK_ARITH_EXACT, false>(a, st);
+  if (arith == NFK_ARITH_HYBRID)
+    return inv ? launch_fused<NFK_ARITH_HYBRID, true>(a, st) : launch_fused<NFK_ARITH_HYBRID, false>(a, st);
+  return inv ? launch_fused<NFK_ARITH_FAST, true>(a, st) : launch_fused<NFK_ARITH_FAST, false>(a, st);
+}
+
+}  // extern "C"

@@ -36,6 +36,7 @@ struct CouplingArgs {
 struct SmemPtr {
   const float* p;
   __device__ __forceinline__ float operator()(int i) const { return p[i]; }
+  __device__ __forceinline__ float dyn(int base, int i) const { return p[base + i]; }
 };
 
 // Generic geometry: one element per thread per tile (the launcher sizes the CTA to the tile), so
@@ -217,6 +218,7 @@ rqs_coupling_pairs(const __grid_constant__ CouplingArgs a) {
 struct GmemPtr {
   const float* p;
   __device__ __forceinline__ float operator()(int i) const { return __ldg(p + i); }
+  __device__ __forceinline__ float dyn(int base, int i) const { return __ldg(p + base + i); }
 };
 
 // One CTA per row, plain global accesses: tail rows (N % R), tiny batches and shapes whose
@@ -263,6 +265,7 @@ struct SplitPtr {
   __device__ __forceinline__ float operator()(int i) const {
     return i < K ? __ldg(w + i) : (i < 2 * K ? __ldg(h + (i - K)) : __ldg(dd + (i - 2 * K)));
   }
+  __device__ __forceinline__ float dyn(int base, int i) const { return (*this)(base + i); }
 };
 
 template <int MODE, int KT, bool INVERSE>
@@ -317,6 +320,8 @@ static RqsConsts make_consts(int K, float B) {
   c.scan_order = scan_order();
   return c;
 }
+
+RqsConsts make_rqs_consts(int K, float B) { return make_consts(K, B); }
 
 static int g_tune_R = 0, g_tune_threads = 0, g_tune_stages = 0, g_tune_ctas = 0;
 

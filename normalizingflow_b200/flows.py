@@ -107,6 +107,7 @@ class NSF_CL(nn.Module):
         self._mask = [int(m) for m in mask]
         self._unmasked = [c for c in range(dim) if c not in self._mask]
         self.arith = arith
+        self.fused = True          # use the fused layer kernel when the layer is eligible (see _fused.py)
         self.psi = base_network(len(mask) * self.size,
                                 (3 * K - 1) * (self.dim - len(self.mask)) * self.size, hidden_dim).to(self.device)
 
@@ -121,6 +122,12 @@ class NSF_CL(nn.Module):
         return _ops.gather_cols(x, self.size, self.dim, self._mask)
 
     def _transform(self, x, inverse, logdet=None):
+        no_grad = not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))
+        if no_grad and self.fused:
+            from . import _fused
+            if _fused.eligible(self):
+                # conditioner GEMMs + spline in ONE kernel; the parameter tensor never reaches HBM
+                return _fused.run(self, x, inverse, logdet)
         n_t = self.size * (self.dim - len(self._mask))
         params = self.psi(self._lower(x)).reshape(-1, n_t, 3 * self.K - 1)   # flows.py:231
         if torch.is_grad_enabled() and (x.requires_grad or params.requires_grad):

@@ -163,3 +163,40 @@ def test_models_match_reference():
         z, plp, ld = m.forward(T(g["planar.x"]).cuda())          # six layers, ONE fused launch
     assert rel_err(z, g["planar.z"]) <= 2e-5 and rel_err(ld, g["planar.ld"]) <= 2e-5
     assert rel_err(plp, g["planar.prior_lp"]) <= 2e-5
+
+
+@pytest.mark.parametrize("H", [128, 24, 100])
+def test_fused_layer_kernel_matches_unfused_and_reference(H):
+    """nsf_fused.cu (MLP on tcgen05 + spline epilogue, one launch) vs (a) the unfused bf16 path
+    on the same weights — same bf16 operands, so the spline parameters agree to accumulation
+    order and results to ~1e-3 — and (b) the fp32 oracle within the bf16 class (1e-2 on z; the
+    log-det sums 32 terms whose parameters carry bf16 noise)."""
+    from oracle import nf_oracle as O
+    _, _, flows, _ = _mods()
+    from normalizingflow_b200 import _fused
+    torch.manual_seed(H)
+    for mask in ([0], [1]):
+        layer = flows.NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=H, mask=mask)
+        layer.psi.precision = "bf16"
+        layer = layer.cuda()
+        assert _fused.eligible(layer)
+        N = 128 * 5 + 37
+        x = (torch.randn(N, 64, generator=torch.Generator().manual_seed(3)) * 1.5)
+        sd = {k: v.detach().cpu() for k, v in layer.state_dict().items()}
+        for inv in (False, True):
+            with torch.no_grad():
+                layer.fused = True
+                zf, lf = layer._transform(x.cuda(), inv)
+                layer.fused = False
+                zu, lu = layer._transform(x.cuda(), inv)
+            ro, rl, _, _ = O.nsf_cl(x, sd, 32, 2, mask, 8, 3.0, inv, prefix="psi.")
+            assert zf.shape == (N, 64) and lf.shape == (N,)
+            assert rel_err(zf, zu) <= 5e-3 and rel_err(lf, lu) <= 2e-2, (mask, inv, rel_err(zf, zu), rel_err(lf, lu))
+            assert rel_err(zf, ro) <= 2e-2 and rel_err(lf, rl) <= 5e-2, (mask, inv, rel_err(zf, ro), rel_err(lf, rl))
+            # conditioning columns pass through bit-exactly, in the reference's column order (Q5)
+            assert torch.equal(zf.cpu().reshape(N, 32, 2)[:, :, 0], x.reshape(N, 32, 2)[:, :, mask[0]])
+            acc = torch.full((N,), 1.5, device="cuda")
+            with torch.no_grad():
+                layer.fused = True
+                _, la = layer._transform(x.cuda(), inv, acc)
+            assert rel_err(la, lf + 1.5) <= 1e-6
