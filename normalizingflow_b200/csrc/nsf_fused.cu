@@ -25,7 +25,8 @@
 namespace nfk {
 
 constexpr int FU_ROWS = 128;
-constexpr int FU_THREADS = 512;
+constexpr int FU_EPI_WARPS = 16;
+constexpr int FU_THREADS = (FU_EPI_WARPS + 1) * 32;   // 16 epilogue warps + 1 control warp
 constexpr int FU_HP = 128;        // padded hidden width
 constexpr int FU_K1P = 64;        // padded conditioner input width
 constexpr int FU_NF = 32;         // transformed features
@@ -75,6 +76,14 @@ struct RegParams {
   }
 };
 
+__device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp roles: warps 0..15 are epilogue warps (TMEM lane quadrant q = warp % 4, column slice /
+// feature-in-chunk = warp / 4); warp 16 is the control warp: it issues every tcgen05.mma and
+// every TMA bulk copy and never waits on arithmetic, so tensor work and weight streaming run
+// ahead of the epilogues.  All hand-offs are mbarriers; there is no CTA-wide barrier in the loop.
 template <int MODE, bool INVERSE>
 __global__ void __launch_bounds__(FU_THREADS, 1)
 nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
@@ -84,24 +93,22 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
   unsigned char* sW2 = sW1 + FU_W1_BYTES;
   unsigned char* sA = sW2 + FU_W2_BYTES;
   unsigned char* sW3 = sA + FU_A_BYTES;
-  float* sX = reinterpret_cast<float*>(sW3 + FU_W3STAGES * FU_W3C_BYTES);      // 2 tiles
+  float* sX = reinterpret_cast<float*>(sW3 + FU_W3STAGES * FU_W3C_BYTES);      // 2 padded tiles
   float* sB1 = sX + 2 * FU_ROWS * FU_XLD;
   float* sB2 = sB1 + FU_HP;
   float* sB3 = sB2 + FU_HP;
-  float* sLad = reinterpret_cast<float*>(sA);       // [4][128], aliases the A operand (idle in P7)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB3 + FU_NF * FU_PC);
-  uint64_t* bar_w = bars;            // W1 + W2 resident
-  uint64_t* bar_x = bars + 1;        // [2]
-  uint64_t* bar_w3 = bars + 3;       // [3]
-  uint64_t* bar_mma = bars + 6;      // GEMM1 / GEMM2 done
-  uint64_t* bar_d3 = bars + 7;       // [2] GEMM3 chunk done
+  uint64_t* bar_w = bars;            // W1 + W2 resident                 (1)
+  uint64_t* bar_x = bars + 1;        // [2] x tile landed                (1 + tx)
+  uint64_t* bar_w3 = bars + 3;       // [3] W3 chunk landed              (1 + tx)
+  uint64_t* bar_mma = bars + 6;      // GEMM1 / GEMM2 done               (1, tcgen05.commit)
+  uint64_t* bar_d3f = bars + 7;      // [2] GEMM3 chunk done             (1, tcgen05.commit)
+  uint64_t* bar_d3e = bars + 9;      // [2] D3 buffer drained            (16 warps)
+  uint64_t* bar_a = bars + 11;       // A operand written                (16 warps)
+  uint64_t* bar_out = bars + 12;     // output tile + log-det partials   (16 warps)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3;            // TMEM lane quadrant of this warp
-  const int slice = warp >> 2;       // column slice (epilogues 1/2) or feature-in-chunk (epilogue 3)
-  const int row = q * 32 + lane;     // row of the tile this thread owns in every epilogue
-
   const unsigned first = blockIdx.x, stride = gridDim.x;
   const unsigned n_tiles = (unsigned)a.n_tiles;
   const unsigned my_tiles = (n_tiles > first) ? (n_tiles - first + stride - 1) / stride : 0;
@@ -110,6 +117,10 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bar_d3e[0], FU_EPI_WARPS);
+    mbar_init(&bar_d3e[1], FU_EPI_WARPS);
+    mbar_init(bar_a, FU_EPI_WARPS);
+    mbar_init(bar_out, FU_EPI_WARPS);
     fence_barrier_init();
   }
   for (int i = tid; i < FU_HP; i += FU_THREADS) {
@@ -122,154 +133,181 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t tD12 = tmem;                       // 128 columns
-  const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
 
-  // warp 0, all lanes: one 256-byte bulk copy per row into the padded tile
-  auto issue_x = [&](unsigned it) {
-    const size_t tile = first + (size_t)it * stride;
-    const int s = it & 1;
-    if (lane == 0) mbar_expect_tx(&bar_x[s], FU_ROWS * FU_XROW_BYTES);
-    __syncwarp();
-    for (int r = lane; r < FU_ROWS; r += 32)
-      bulk_g2s(sX + (s * FU_ROWS + r) * FU_XLD, a.x + (tile * FU_ROWS + r) * 64, FU_XROW_BYTES, &bar_x[s]);
-  };
-  auto issue_w3 = [&](unsigned g) {   // g: running chunk counter of this CTA
-    const int s = g % FU_W3STAGES;
-    const int c = g % FU_NCHUNK;
-    mbar_expect_tx(&bar_w3[s], FU_W3C_BYTES);
-    bulk_g2s(sW3 + s * FU_W3C_BYTES, reinterpret_cast<const unsigned char*>(a.w3_img) + (size_t)c * FU_W3C_BYTES,
-             FU_W3C_BYTES, &bar_w3[s]);
-  };
-  if (tid == 0 && my_tiles) {
-    mbar_expect_tx(bar_w, FU_W1_BYTES + FU_W2_BYTES);
-    bulk_g2s(sW1, a.w1_img, FU_W1_BYTES, bar_w);
-    bulk_g2s(sW2, a.w2_img, FU_W2_BYTES, bar_w);
-    for (unsigned g = 0; g < FU_W3STAGES && g < total_chunks; ++g) issue_w3(g);
-  }
-  if (warp == 0 && my_tiles) issue_x(0);
-
-  const uint32_t idesc12 = make_idesc_bf16(FU_ROWS, FU_HP);
-  const uint32_t idesc3 = make_idesc_bf16(FU_ROWS, FU_NC);
-  const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
-
-  // GEMM3 chunk issue (thread 0): D3[g & 1] = A3 * W3chunk^T
-  auto issue_mma3 = [&](unsigned g) {
-    const int s = g % FU_W3STAGES;
-    mbar_wait(&bar_w3[s], (g / FU_W3STAGES) & 1);
-    tc_fence_after();
-    const uint32_t d = tmem + 128 + (g & 1) * FU_NC;
-    const uint32_t bbase = aW3 + s * FU_W3C_BYTES;
-#pragma unroll
-    for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(d, make_desc_sw128(aA + kb * (FU_ROWS * 128) + k * 32),
-                  make_desc_sw128(bbase + kb * (FU_NC * 128) + k * 32), idesc3, (kb | k) ? 1u : 0u);
-    umma_commit(&bar_d3[g & 1]);
-  };
-
-  // epilogue of GEMM1/GEMM2: this warp's 32 columns -> +bias -> tanh -> bf16 -> A operand
-  auto hidden_epilogue = [&](const float* bias) {
-    uint32_t v[32];
-    tmem_ld32(tD12 + lane_sel + slice * 32, v);
-    tmem_ld_wait();
-    const int kb = slice >> 1;
-    unsigned char* dst = sA + kb * (FU_ROWS * 128) + row * 128;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      uint4 u;
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = tanh_approx(__uint_as_float(v[t * 8 + j]) + bias[slice * 32 + t * 8 + j]);
-      u.x = pack_bf16x2(f[0], f[1]);
-      u.y = pack_bf16x2(f[2], f[3]);
-      u.z = pack_bf16x2(f[4], f[5]);
-      u.w = pack_bf16x2(f[6], f[7]);
-      const int ch = (slice & 1) * 4 + t;
-      *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = u;
+  if (warp == FU_EPI_WARPS) {
+    // =============================== control warp ===============================
+    const uint32_t idesc12 = make_idesc_bf16(FU_ROWS, FU_HP);
+    const uint32_t idesc3 = make_idesc_bf16(FU_ROWS, FU_NC);
+    const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+    auto issue_x = [&](unsigned it) {        // all lanes: one 256-byte bulk copy per row
+      const size_t tile = first + (size_t)it * stride;
+      const int s = it & 1;
+      if (lane == 0) mbar_expect_tx(&bar_x[s], FU_ROWS * FU_XROW_BYTES);
+      __syncwarp();
+      for (int r = lane; r < FU_ROWS; r += 32)
+        bulk_g2s(sX + (s * FU_ROWS + r) * FU_XLD, a.x + (tile * FU_ROWS + r) * 64, FU_XROW_BYTES, &bar_x[s]);
+    };
+    auto issue_w3 = [&](unsigned g) {        // lane 0
+      const int s = g % FU_W3STAGES;
+      const int c = g % FU_NCHUNK;
+      mbar_expect_tx(&bar_w3[s], FU_W3C_BYTES);
+      bulk_g2s(sW3 + s * FU_W3C_BYTES,
+               reinterpret_cast<const unsigned char*>(a.w3_img) + (size_t)c * FU_W3C_BYTES, FU_W3C_BYTES,
+               &bar_w3[s]);
+    };
+    if (my_tiles) {
+      if (lane == 0) {
+        mbar_expect_tx(bar_w, FU_W1_BYTES + FU_W2_BYTES);
+        bulk_g2s(sW1, a.w1_img, FU_W1_BYTES, bar_w);
+        bulk_g2s(sW2, a.w2_img, FU_W2_BYTES, bar_w);
+        for (unsigned g = 0; g < FU_W3STAGES && g < total_chunks; ++g) issue_w3(g);
+      }
+      issue_x(0);
+      if (lane == 0) mbar_wait(bar_w, 0);
+      __syncwarp();
     }
-  };
+    unsigned g = 0, na = 0;          // running GEMM3 chunk counter, running bar_a phase counter
+    for (unsigned it = 0; it < my_tiles; ++it) {
+      const size_t tile = first + (size_t)it * stride;
+      if (lane == 0) {
+        // GEMM1: D12 = A1 W1^T
+        mbar_wait(bar_a, na++ & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < FU_K1P / 16; ++k)
+          umma_bf16(tD12, make_desc_sw128(aA + k * 32), make_desc_sw128(aW1 + k * 32), idesc12, k ? 1u : 0u);
+        umma_commit(bar_mma);
+      }
+      __syncwarp();
+      if (it + 1 < my_tiles) {
+        bulk_wait_read<0>();          // this lane's stores out of the other x buffer have drained
+        __syncwarp();
+        issue_x(it + 1);
+      }
+      if (lane == 0) {
+        // GEMM2: D12 = A2 W2^T
+        mbar_wait(bar_a, na++ & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tD12, make_desc_sw128(aA + kb * (FU_ROWS * 128) + k * 32),
+                      make_desc_sw128(aW2 + kb * (FU_HP * 128) + k * 32), idesc12, (kb | k) ? 1u : 0u);
+        umma_commit(bar_mma);
+        // GEMM3 chunks: D3[g & 1] = A3 W3chunk^T
+        mbar_wait(bar_a, na++ & 1);
+        for (int c = 0; c < FU_NCHUNK; ++c, ++g) {
+          const int s = g % FU_W3STAGES;
+          mbar_wait(&bar_w3[s], (g / FU_W3STAGES) & 1);
+          if (g >= 2) mbar_wait(&bar_d3e[g & 1], ((g >> 1) + 1) & 1);   // chunk g-2 left this buffer
+          tc_fence_after();
+          const uint32_t d = tmem + 128 + (g & 1) * FU_NC;
+          const uint32_t bbase = aW3 + s * FU_W3C_BYTES;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d, make_desc_sw128(aA + kb * (FU_ROWS * 128) + k * 32),
+                        make_desc_sw128(bbase + kb * (FU_NC * 128) + k * 32), idesc3, (kb | k) ? 1u : 0u);
+          umma_commit(&bar_d3f[g & 1]);
+          if (g >= 1 && g + 2 < total_chunks) {
+            // chunk g-1 has been consumed by the tensor core: refill its ring slot with chunk g+2
+            mbar_wait(&bar_d3f[(g - 1) & 1], ((g - 1) >> 1) & 1);
+            issue_w3(g + 2);
+          }
+        }
+        mbar_wait(bar_out, it & 1);   // every epilogue warp has finished this tile
+      }
+      __syncwarp();
+      // row log-det = sum of the four per-slice partial sums parked in the row padding
+      const float* xs = sX + (it & 1) * FU_ROWS * FU_XLD;
+      for (int r = lane; r < FU_ROWS; r += 32) {
+        const float* pr = xs + r * FU_XLD + 64;
+        const float t = (pr[0] + pr[1]) + (pr[2] + pr[3]);                 // flows.py:238
+        float* ldp = a.logdet + tile * FU_ROWS + r;
+        *ldp = a.accumulate ? *ldp + t : t;
+        bulk_s2g(a.out + (tile * FU_ROWS + r) * 64, xs + r * FU_XLD, FU_XROW_BYTES);
+      }
+      bulk_commit();
+    }
+    bulk_wait_all<0>();
+  } else {
+    // =============================== epilogue warps ===============================
+    const int q = warp & 3;            // TMEM lane quadrant
+    const int slice = warp >> 2;       // column slice (epilogues 1/2) / feature-in-chunk (epilogue 3)
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
 
-  if (my_tiles) mbar_wait(bar_w, 0);
-
-  unsigned g = 0;                 // running GEMM3 chunk counter
-  for (unsigned it = 0; it < my_tiles; ++it) {
-    const size_t tile = first + (size_t)it * stride;
-    float* xs = sX + (it & 1) * FU_ROWS * FU_XLD;
-
-    // ---- P1: conditioning columns -> A1 (K block 0; columns 32..63 are zero padding)
-    mbar_wait(&bar_x[it & 1], (it >> 1) & 1);
-    for (int i = tid; i < FU_ROWS * 8; i += FU_THREADS) {
-      const int r = i >> 3, ch = i & 7;
-      uint4 u = make_uint4(0u, 0u, 0u, 0u);
-      if (ch < 4) {
-        const float* xr = xs + r * FU_XLD + (a.cond_first ? 0 : 1);
+    auto hidden_epilogue = [&](const float* bias) {
+      uint32_t v[32];
+      tmem_ld32(tD12 + lane_sel + slice * 32, v);
+      tmem_ld_wait();
+      unsigned char* dst = sA + (slice >> 1) * (FU_ROWS * 128) + row * 128;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
         float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = xr[2 * (ch * 8 + j)];
+        for (int j = 0; j < 8; ++j)
+          f[j] = tanh_approx(__uint_as_float(v[t * 8 + j]) + bias[slice * 32 + t * 8 + j]);
+        uint4 u;
         u.x = pack_bf16x2(f[0], f[1]);
         u.y = pack_bf16x2(f[2], f[3]);
         u.z = pack_bf16x2(f[4], f[5]);
         u.w = pack_bf16x2(f[6], f[7]);
+        const int ch = (slice & 1) * 4 + t;
+        *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = u;
       }
-      *reinterpret_cast<uint4*>(sA + r * 128 + ((ch ^ (r & 7)) << 4)) = u;
-    }
-    fence_proxy_async();
-    __syncthreads();
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cnt(bar_a);
+    };
 
-    // ---- P2: GEMM1
-    if (tid == 0) {
-      tc_fence_after();
+    for (unsigned it = 0; it < my_tiles; ++it) {
+      float* xs = sX + (it & 1) * FU_ROWS * FU_XLD;
+      // ---- P1: conditioning columns -> A1 (K block 0; columns 32..63 are zero padding)
+      mbar_wait(&bar_x[it & 1], (it >> 1) & 1);
+      for (int i = tid; i < FU_ROWS * 8; i += FU_EPI_WARPS * 32) {
+        const int r = i >> 3, ch = i & 7;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (ch < 4) {
+          const float* xr = xs + r * FU_XLD + (a.cond_first ? 0 : 1);
+          float f[8];
 #pragma unroll
-      for (int k = 0; k < FU_K1P / 16; ++k)
-        umma_bf16(tD12, make_desc_sw128(aA + k * 32), make_desc_sw128(aW1 + k * 32), idesc12, k ? 1u : 0u);
-      umma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, 0);
-    tc_fence_after();
-    // ---- P3: epilogue 1 -> A2
-    hidden_epilogue(sB1);
-    tc_fence_before();
-    fence_proxy_async();
-    __syncthreads();
-    // ---- P4: GEMM2
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tD12, make_desc_sw128(aA + kb * (FU_ROWS * 128) + k * 32),
-                    make_desc_sw128(aW2 + kb * (FU_HP * 128) + k * 32), idesc12, (kb | k) ? 1u : 0u);
-      umma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, 1);
-    tc_fence_after();
-    // ---- P5: epilogue 2 -> A3
-    hidden_epilogue(sB2);
-    tc_fence_before();
-    fence_proxy_async();
-    __syncthreads();
-
-    // ---- P6: GEMM3 chunks with the spline transform as their epilogue
-    if (tid == 0) issue_mma3(g);
-    float lad_acc = 0.f;
-    for (int c = 0; c < FU_NCHUNK; ++c, ++g) {
-      if (tid == 0 && c + 1 < FU_NCHUNK) issue_mma3(g + 1);
-      if (warp == 0 && c == 2 && it + 1 < my_tiles) {
-        bulk_wait_read<0>();            // this lane's stores that drained the other x buffer are done
-        __syncwarp();
-        issue_x(it + 1);
+          for (int j = 0; j < 8; ++j) f[j] = xr[2 * (ch * 8 + j)];
+          u.x = pack_bf16x2(f[0], f[1]);
+          u.y = pack_bf16x2(f[2], f[3]);
+          u.z = pack_bf16x2(f[4], f[5]);
+          u.w = pack_bf16x2(f[6], f[7]);
+        }
+        *reinterpret_cast<uint4*>(sA + r * 128 + ((ch ^ (r & 7)) << 4)) = u;
       }
-      mbar_wait(&bar_d3[c & 1], (c >> 1) & 1);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cnt(bar_a);
+      // ---- P3 / P5: hidden-layer epilogues
+      mbar_wait(bar_mma, 0);
       tc_fence_after();
-      {
+      hidden_epilogue(sB1);
+      mbar_wait(bar_mma, 1);
+      tc_fence_after();
+      hidden_epilogue(sB2);
+      // ---- P6: spline transform as the epilogue of the GEMM3 chunks
+      float lad_acc = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < FU_NCHUNK; ++c) {
+        mbar_wait(&bar_d3f[c & 1], (c >> 1) & 1);
+        tc_fence_after();
         const int f = c * FU_CF + slice;                     // feature of this thread
         uint32_t v[24];
         const uint32_t t = tmem + 128 + (c & 1) * FU_NC + lane_sel + slice * FU_PC;
         tmem_ld16(t, v);
         tmem_ld8(t + 16, v + 16);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cnt(&bar_d3e[c & 1]);      // the buffer may be overwritten
         float2* pr = reinterpret_cast<float2*>(xs + row * FU_XLD + 2 * f);
         const float2 xc = *pr;
         const RqsOut o = rqs_element<MODE, 8, INVERSE, true>(RegParams{v, sB3 + f * FU_PC},
@@ -277,28 +315,13 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
         *pr = make_float2(a.cond_first ? xc.x : xc.y, o.y);  // (conditioning, transformed): Q5
         lad_acc += o.lad;
       }
-      tc_fence_before();
-      __syncthreads();                  // D3[c&1] and the W3 stage of chunk g are free
-      if (tid == 0 && g + FU_W3STAGES < total_chunks) issue_w3(g + FU_W3STAGES);
+      // ---- P7: park the partial log-det in the row padding; the control warp finishes the tile
+      xs[row * FU_XLD + 64 + slice] = lad_acc;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cnt(bar_out);
     }
-
-    // ---- P7: row log-det and output tile
-    sLad[slice * FU_ROWS + row] = lad_acc;
-    fence_proxy_async();
-    __syncthreads();
-    if (tid < FU_ROWS) {
-      const float t = (sLad[tid] + sLad[FU_ROWS + tid]) + (sLad[2 * FU_ROWS + tid] + sLad[3 * FU_ROWS + tid]);
-      float* ldp = a.logdet + tile * FU_ROWS + tid;
-      *ldp = a.accumulate ? *ldp + t : t;
-    }
-    if (warp == 0) {
-      for (int r = lane; r < FU_ROWS; r += 32)
-        bulk_s2g(a.out + (tile * FU_ROWS + r) * 64, xs + r * FU_XLD, FU_XROW_BYTES);
-      bulk_commit();
-    }
-    __syncthreads();                    // sLad (= the A operand buffer) is rewritten by the next tile
   }
-  if (warp == 0) bulk_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
