@@ -158,6 +158,8 @@ int nfk_linear_bf16(const void* X, int64_t ldx, const void* W, int64_t ldw, cons
  * rows padded to 24) in the K-major SWIZZLE_128B shared-memory layout (16-byte chunk j of row r
  * holds source chunk j ^ (r % 8)); b1, b2 [128], b3 [32*24] fp32 padded the same way. */
 int nfk_nsf_fused_rows_per_tile(void);
+/* test hook: device buffer of 64 int64 receiving clock64 stamps of CTA 0, third tile (NULL = off) */
+int nfk_set_fused_trace(void* dev_buf);
 int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w1_img,
                         const void* w2_img, const void* w3_img, const float* b1, const float* b2,
                         const float* b3, int64_t N, int mask_col, float B, int inverse,

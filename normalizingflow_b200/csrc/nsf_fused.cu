@@ -58,6 +58,7 @@ struct FusedArgs {
   long long n_tiles;
   int cond_first;         // 1: conditioning column is column 0 of each pair (mask = [0])
   int accumulate;
+  long long* trace;       // optional [2][32] clock64 stamps of CTA 0, tile 2 (tools/trace_fused.py)
   RqsConsts c;
 };
 
@@ -99,13 +100,12 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
   float* sB3 = sB2 + FU_HP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB3 + FU_NF * FU_PC);
   uint64_t* bar_w = bars;            // W1 + W2 resident                 (1)
-  uint64_t* bar_x = bars + 1;        // [2] x tile landed                (1 + tx)
+  uint64_t* bar_x = bars + 1;        // [2] x tile landed                (16 warps + tx)
   uint64_t* bar_w3 = bars + 3;       // [3] W3 chunk landed              (1 + tx)
   uint64_t* bar_mma = bars + 6;      // GEMM1 / GEMM2 done               (1, tcgen05.commit)
   uint64_t* bar_d3f = bars + 7;      // [2] GEMM3 chunk done             (1, tcgen05.commit)
   uint64_t* bar_d3e = bars + 9;      // [2] D3 buffer drained            (16 warps)
   uint64_t* bar_a = bars + 11;       // A operand written                (16 warps)
-  uint64_t* bar_out = bars + 12;     // output tile + log-det partials   (16 warps)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -116,11 +116,10 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
 
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
-    for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 9; ++i) mbar_init(&bars[i], (i == 1 || i == 2) ? FU_EPI_WARPS : 1);
     mbar_init(&bar_d3e[0], FU_EPI_WARPS);
     mbar_init(&bar_d3e[1], FU_EPI_WARPS);
     mbar_init(bar_a, FU_EPI_WARPS);
-    mbar_init(bar_out, FU_EPI_WARPS);
     fence_barrier_init();
   }
   for (int i = tid; i < FU_HP; i += FU_THREADS) {
@@ -139,14 +138,6 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
     const uint32_t idesc12 = make_idesc_bf16(FU_ROWS, FU_HP);
     const uint32_t idesc3 = make_idesc_bf16(FU_ROWS, FU_NC);
     const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
-    auto issue_x = [&](unsigned it) {        // all lanes: one 256-byte bulk copy per row
-      const size_t tile = first + (size_t)it * stride;
-      const int s = it & 1;
-      if (lane == 0) mbar_expect_tx(&bar_x[s], FU_ROWS * FU_XROW_BYTES);
-      __syncwarp();
-      for (int r = lane; r < FU_ROWS; r += 32)
-        bulk_g2s(sX + (s * FU_ROWS + r) * FU_XLD, a.x + (tile * FU_ROWS + r) * 64, FU_XROW_BYTES, &bar_x[s]);
-    };
     auto issue_w3 = [&](unsigned g) {        // lane 0
       const int s = g % FU_W3STAGES;
       const int c = g % FU_NCHUNK;
@@ -162,31 +153,32 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
         bulk_g2s(sW2, a.w2_img, FU_W2_BYTES, bar_w);
         for (unsigned g = 0; g < FU_W3STAGES && g < total_chunks; ++g) issue_w3(g);
       }
-      issue_x(0);
       if (lane == 0) mbar_wait(bar_w, 0);
       __syncwarp();
     }
     unsigned g = 0, na = 0;          // running GEMM3 chunk counter, running bar_a phase counter
     for (unsigned it = 0; it < my_tiles; ++it) {
       const size_t tile = first + (size_t)it * stride;
+      const bool tr = a.trace && blockIdx.x == 0 && it == 2 && lane == 0;
+      int ts = 0;
+#define NFK_STAMP(base) do { if (tr) a.trace[(base) + ts++] = clock64(); } while (0)
       if (lane == 0) {
         // GEMM1: D12 = A1 W1^T
+        NFK_STAMP(0);
         mbar_wait(bar_a, na++ & 1);
+        NFK_STAMP(0);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < FU_K1P / 16; ++k)
           umma_bf16(tD12, make_desc_sw128(aA + k * 32), make_desc_sw128(aW1 + k * 32), idesc12, k ? 1u : 0u);
         umma_commit(bar_mma);
-      }
-      __syncwarp();
-      if (it + 1 < my_tiles) {
-        bulk_wait_read<0>();          // this lane's stores out of the other x buffer have drained
-        __syncwarp();
-        issue_x(it + 1);
+        NFK_STAMP(0);
       }
       if (lane == 0) {
         // GEMM2: D12 = A2 W2^T
+        NFK_STAMP(0);
         mbar_wait(bar_a, na++ & 1);
+        NFK_STAMP(0);
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
@@ -195,8 +187,10 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
             umma_bf16(tD12, make_desc_sw128(aA + kb * (FU_ROWS * 128) + k * 32),
                       make_desc_sw128(aW2 + kb * (FU_HP * 128) + k * 32), idesc12, (kb | k) ? 1u : 0u);
         umma_commit(bar_mma);
+        NFK_STAMP(0);
         // GEMM3 chunks: D3[g & 1] = A3 W3chunk^T
         mbar_wait(bar_a, na++ & 1);
+        NFK_STAMP(0);
         for (int c = 0; c < FU_NCHUNK; ++c, ++g) {
           const int s = g % FU_W3STAGES;
           mbar_wait(&bar_w3[s], (g / FU_W3STAGES) & 1);
@@ -211,27 +205,16 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
               umma_bf16(d, make_desc_sw128(aA + kb * (FU_ROWS * 128) + k * 32),
                         make_desc_sw128(bbase + kb * (FU_NC * 128) + k * 32), idesc3, (kb | k) ? 1u : 0u);
           umma_commit(&bar_d3f[g & 1]);
+          NFK_STAMP(0);
           if (g >= 1 && g + 2 < total_chunks) {
             // chunk g-1 has been consumed by the tensor core: refill its ring slot with chunk g+2
             mbar_wait(&bar_d3f[(g - 1) & 1], ((g - 1) >> 1) & 1);
             issue_w3(g + 2);
           }
         }
-        mbar_wait(bar_out, it & 1);   // every epilogue warp has finished this tile
       }
       __syncwarp();
-      // row log-det = sum of the four per-slice partial sums parked in the row padding
-      const float* xs = sX + (it & 1) * FU_ROWS * FU_XLD;
-      for (int r = lane; r < FU_ROWS; r += 32) {
-        const float* pr = xs + r * FU_XLD + 64;
-        const float t = (pr[0] + pr[1]) + (pr[2] + pr[3]);                 // flows.py:238
-        float* ldp = a.logdet + tile * FU_ROWS + r;
-        *ldp = a.accumulate ? *ldp + t : t;
-        bulk_s2g(a.out + (tile * FU_ROWS + r) * 64, xs + r * FU_XLD, FU_XROW_BYTES);
-      }
-      bulk_commit();
     }
-    bulk_wait_all<0>();
   } else {
     // =============================== epilogue warps ===============================
     const int q = warp & 3;            // TMEM lane quadrant
@@ -264,10 +247,34 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
       if (lane == 0) mbar_arrive_cnt(bar_a);
     };
 
+    // lanes 0..7 of every epilogue warp move 8 rows of the x / output tile each (256-byte TMA bulk
+    // copies into the padded rows): the copy work is spread over 16 warps instead of serialising
+    // on the control warp, and a lane reloads exactly the row it stored, so buffer reuse needs
+    // no cross-thread hand-off beyond its own bulk-group wait.
+    const int myrow = q * 32 + slice * 8 + (lane & 7);
+    auto load_rows = [&](unsigned it2) {
+      const size_t tile2 = first + (size_t)it2 * stride;
+      const int s = it2 & 1;
+      if (lane == 0) mbar_expect_tx(&bar_x[s], 8 * FU_XROW_BYTES);       // arrive (1 of 16) + expect
+      __syncwarp();
+      if (lane < 8)
+        bulk_g2s(sX + (s * FU_ROWS + myrow) * FU_XLD, a.x + (tile2 * FU_ROWS + myrow) * 64, FU_XROW_BYTES,
+                 &bar_x[s]);
+    };
+    if (my_tiles) load_rows(0);
+    if (my_tiles > 1) load_rows(1);
+
     for (unsigned it = 0; it < my_tiles; ++it) {
+      const size_t tile = first + (size_t)it * stride;
       float* xs = sX + (it & 1) * FU_ROWS * FU_XLD;
+      float ld_old = 0.f;
+      if (lane < 8 && a.accumulate) ld_old = __ldg(a.logdet + tile * FU_ROWS + myrow);   // consumed in P7
+      const bool tr = a.trace && blockIdx.x == 0 && it == 2 && tid == 0;
+      int ts = 0;
       // ---- P1: conditioning columns -> A1 (K block 0; columns 32..63 are zero padding)
+      NFK_STAMP(32);
       mbar_wait(&bar_x[it & 1], (it >> 1) & 1);
+      NFK_STAMP(32);
       for (int i = tid; i < FU_ROWS * 8; i += FU_EPI_WARPS * 32) {
         const int r = i >> 3, ch = i & 7;
         uint4 u = make_uint4(0u, 0u, 0u, 0u);
@@ -286,18 +293,30 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive_cnt(bar_a);
+      NFK_STAMP(32);
+      // prefetch the next tile into the other buffer (this lane stored that row one tile ago)
+      if (it >= 1 && it + 1 < my_tiles) {
+        if (lane < 8) bulk_wait_read<0>();
+        __syncwarp();
+        load_rows(it + 1);
+      }
       // ---- P3 / P5: hidden-layer epilogues
       mbar_wait(bar_mma, 0);
+      NFK_STAMP(32);
       tc_fence_after();
       hidden_epilogue(sB1);
+      NFK_STAMP(32);
       mbar_wait(bar_mma, 1);
+      NFK_STAMP(32);
       tc_fence_after();
       hidden_epilogue(sB2);
+      NFK_STAMP(32);
       // ---- P6: spline transform as the epilogue of the GEMM3 chunks
       float lad_acc = 0.f;
 #pragma unroll 1
       for (int c = 0; c < FU_NCHUNK; ++c) {
         mbar_wait(&bar_d3f[c & 1], (c >> 1) & 1);
+        NFK_STAMP(32);
         tc_fence_after();
         const int f = c * FU_CF + slice;                     // feature of this thread
         uint32_t v[24];
@@ -314,13 +333,22 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
                                                               a.cond_first ? xc.y : xc.x, a.c);
         *pr = make_float2(a.cond_first ? xc.x : xc.y, o.y);  // (conditioning, transformed): Q5
         lad_acc += o.lad;
+        NFK_STAMP(32);
       }
-      // ---- P7: park the partial log-det in the row padding; the control warp finishes the tile
+      // ---- P7: the four warps of this lane quadrant own these 32 rows: exchange the partial
+      // log-dets through the row padding, then lanes 0..7 finish 8 rows each
       xs[row * FU_XLD + 64 + slice] = lad_acc;
       fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cnt(bar_out);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+      if (lane < 8) {
+        const float* pr = xs + myrow * FU_XLD + 64;
+        const float t = (pr[0] + pr[1]) + (pr[2] + pr[3]);                   // flows.py:238
+        a.logdet[tile * FU_ROWS + myrow] = a.accumulate ? ld_old + t : t;
+        bulk_s2g(a.out + (tile * FU_ROWS + myrow) * 64, xs + myrow * FU_XLD, FU_XROW_BYTES);
+        bulk_commit();
+      }
     }
+    if (lane < 8) bulk_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -352,7 +380,15 @@ static int launch_fused(const FusedArgs& a, cudaStream_t st) {
 
 using namespace nfk;
 
+static long long* g_fused_trace = nullptr;
+
 extern "C" {
+
+/* test hook: device buffer of 64 int64 that receives clock64 stamps of CTA 0 / tile 2 */
+int nfk_set_fused_trace(void* dev_buf) {
+  g_fused_trace = reinterpret_cast<long long*>(dev_buf);
+  return NFK_OK;
+}
 
 int nfk_nsf_fused_rows_per_tile(void) { return FU_ROWS; }
 
@@ -385,6 +421,7 @@ int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w
   a.n_tiles = N / FU_ROWS;
   a.cond_first = (mask_col == 0);
   a.accumulate = accumulate;
+  a.trace = g_fused_trace;
   a.c = make_rqs_consts(8, B);
   cudaStream_t st = (cudaStream_t)stream;
   const bool inv = inverse != 0;
