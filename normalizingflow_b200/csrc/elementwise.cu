@@ -181,6 +181,119 @@ planar_stack_kernel(const float* __restrict__ x, const float* __restrict__ w,
   }
 }
 
+// backward of the fused stack.  Forward is recomputed keeping tanh(lin_l) per layer (L <= 64);
+// going back, x_l = x_{l+1} - uhat_l th_l reconstructs each layer's input.  Parameter gradients
+// are reduced over the rows of a warp with shuffles, then accumulated with atomics.
+constexpr int PL_MAXL = 64;
+template <int G, int NV>
+__global__ void __launch_bounds__(256)
+planar_stack_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                        const float* __restrict__ uhat, const float* __restrict__ wuhat,
+                        const float* __restrict__ b, const float* __restrict__ gout,
+                        const float* __restrict__ gld, float* __restrict__ gx,
+                        float* __restrict__ gw, float* __restrict__ guhat, float* __restrict__ gb,
+                        float* __restrict__ gwuhat, long long N, int d, int L) {
+  extern __shared__ float sm[];
+  float* sw = sm;
+  float* su = sm + (size_t)L * d;
+  float* sb = su + (size_t)L * d;
+  float* sd = sb + L;
+  for (int i = threadIdx.x; i < L * d; i += blockDim.x) {
+    sw[i] = w[i];
+    su[i] = uhat[i];
+  }
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    sb[i] = b[i];
+    sd[i] = wuhat[i];
+  }
+  __syncthreads();
+  const int g = threadIdx.x % G;
+  const long long rows_per_block = blockDim.x / G;
+  for (long long row0 = (long long)blockIdx.x * rows_per_block; row0 < N;
+       row0 += (long long)gridDim.x * rows_per_block) {
+    const long long row = row0 + threadIdx.x / G;
+    const bool live = row < N;
+    float xv[NV], gz[NV];
+    float th[PL_MAXL];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = g + G * i;
+      const bool ok = live && col < d;
+      xv[i] = ok ? x[row * d + col] : 0.f;
+      gz[i] = ok ? gout[row * d + col] : 0.f;
+    }
+    const float gl = (live && gld) ? gld[row] : 0.f;
+    for (int l = 0; l < L; ++l) {
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = g + G * i;
+        if (col < d) dot = fmaf(xv[i], sw[l * d + col], dot);
+      }
+      dot = group_sum<G>(dot);
+      const float t = tanhf(dot + sb[l]);
+      th[l] = t;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = g + G * i;
+        if (col < d) xv[i] = fmaf(su[l * d + col], t, xv[i]);
+      }
+    }
+    for (int l = L - 1; l >= 0; --l) {
+      const float t = th[l];
+      const float psi = 1.f - t * t;
+      const float qv = 1.f + psi * sd[l];
+      const float dld_dq = (qv >= 0.f ? 1.f : -1.f) / (fabsf(qv) + 1e-4f);
+      float gth = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = g + G * i;
+        if (col < d) {
+          xv[i] = fmaf(-su[l * d + col], t, xv[i]);            // input of layer l
+          gth = fmaf(gz[i], su[l * d + col], gth);
+        }
+      }
+      gth = group_sum<G>(gth);
+      gth += gl * dld_dq * (-2.f * t) * sd[l];
+      const float glin = live ? gth * psi : 0.f;
+      // parameter gradients: reduce over the row-groups of this warp, then one atomic per column
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = g + G * i;
+        float a_w = glin * xv[i], a_u = live ? gz[i] * t : 0.f;
+#pragma unroll
+        for (int o = G; o < 32; o <<= 1) {
+          a_w += __shfl_xor_sync(0xffffffffu, a_w, o);
+          a_u += __shfl_xor_sync(0xffffffffu, a_u, o);
+        }
+        if (col < d && (threadIdx.x & 31) < G) {
+          atomicAdd(gw + (size_t)l * d + col, a_w);
+          atomicAdd(guhat + (size_t)l * d + col, a_u);
+        }
+      }
+      float a_b = (g == 0) ? glin : 0.f, a_q = (g == 0 && live) ? gl * dld_dq * psi : 0.f;
+      a_b = warp_sum(a_b);
+      a_q = warp_sum(a_q);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(gb + l, a_b);
+        atomicAdd(gwuhat + l, a_q);
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = g + G * i;
+        if (col < d) gz[i] = fmaf(glin, sw[l * d + col], gz[i]);   // grad w.r.t. layer input
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int col = g + G * i;
+        if (col < d) gx[row * d + col] = gz[i];
+      }
+    }
+  }
+}
+
 // ---- radial (nf/flows_1.py:85-97, quirk Q9) -------------------------------------------------
 __global__ void __launch_bounds__(256)
 radial_sumsq_kernel(const float* __restrict__ x, const float* __restrict__ x0,
@@ -433,6 +546,45 @@ int nfk_planar_stack(const float* x, const float* w, const float* uhat, const fl
 #undef NFK_PL
   count_launch();
   return check_launch("planar_stack");
+}
+
+int nfk_planar_stack_bwd(const float* x, const float* w, const float* uhat, const float* wuhat,
+                         const float* b, const float* grad_out, const float* grad_logdet,
+                         float* grad_x, float* grad_w, float* grad_uhat, float* grad_b,
+                         float* grad_wuhat, int64_t N, int d, int L, void* stream) {
+  NFK_REQUIRE(N >= 0 && d > 0 && L > 0, "planar_stack_bwd: bad shape");
+  NFK_REQUIRE(d <= 1024 && L <= PL_MAXL, "planar_stack_bwd: d <= 1024 and L <= %d supported", PL_MAXL);
+  if (N == 0) return NFK_OK;
+  NFK_REQUIRE(x && w && uhat && wuhat && b && grad_out && grad_x && grad_w && grad_uhat && grad_b && grad_wuhat,
+              "planar_stack_bwd: null device pointer");
+  const size_t smem = ((size_t)2 * L * d + 2 * L) * sizeof(float);
+  NFK_REQUIRE(smem <= 200 * 1024, "planar_stack_bwd: L*d too large for shared memory; split the stack");
+  cudaStream_t st = (cudaStream_t)stream;
+  int G, NV;
+  if (d <= 8) { G = 1; NV = 8; }
+  else if (d <= 32) { G = 4; NV = 8; }
+  else if (d <= 128) { G = 8; NV = 16; }
+  else if (d <= 512) { G = 32; NV = 16; }
+  else { G = 32; NV = 32; }
+  const long long rows_per_block = 256 / G;
+  long long grid = (N + rows_per_block - 1) / rows_per_block;
+  const long long cap = (long long)sm_count() * 2;
+  if (grid > cap) grid = cap;
+#define NFK_PLB(GG, VV)                                                                            \
+  do {                                                                                             \
+    cudaFuncSetAttribute(planar_stack_bwd_kernel<GG, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                         (int)smem);                                                               \
+    planar_stack_bwd_kernel<GG, VV><<<(unsigned)grid, 256, smem, st>>>(                            \
+        x, w, uhat, wuhat, b, grad_out, grad_logdet, grad_x, grad_w, grad_uhat, grad_b, grad_wuhat, N, d, L); \
+  } while (0)
+  if (G == 1) NFK_PLB(1, 8);
+  else if (G == 4) NFK_PLB(4, 8);
+  else if (G == 8) NFK_PLB(8, 16);
+  else if (NV == 16) NFK_PLB(32, 16);
+  else NFK_PLB(32, 32);
+#undef NFK_PLB
+  count_launch();
+  return check_launch("planar_stack_bwd");
 }
 
 int nfk_radial_sumsq(const float* x, const float* x0, float* sumsq, int64_t N, int d,
