@@ -1,0 +1,91 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), batch sharded by rows.
+
+Sampling, density evaluation and HMC need no data-path collective — rows are independent
+(nf/models.py:16-18), weights are replicated.  Training adds ONE flat-bucket all-reduce of the
+gradients per step (NCCL over NVLink on a GPU box, gloo in the CPU tests), to be called between
+``loss.backward()`` and ``optimizer.step()`` (the reference's applications/src/train.py:27-28).
+Bug-compatible ``Radial`` all-reduces one float per layer inside its op (quirk Q9).
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, world, local_rank) from torchrun's environment; initialises the default group when
+    WORLD_SIZE > 1 (nccl when CUDA is present, else gloo)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def shard_rows(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous row range [start, stop) of ``rank``; sizes differ by at most one row."""
+    base, rem = divmod(n_total, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], average: bool = True, group=None) -> int:
+    """Sum (or average) the gradients of ``params`` over the ranks with ONE all-reduce on a flat
+    fp32 bucket.  Returns the bucket size in bytes (0 when not distributed)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 0
+    plist = [p for p in params if p.grad is not None]
+    if not plist:
+        return 0
+    flat = torch.cat([p.grad.reshape(-1).float() for p in plist])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= world
+    off = 0
+    for p in plist:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return flat.numel() * 4
+
+
+def global_mean(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Mean of a per-row quantity over all ranks (e.g. the reported mean log-prob)."""
+    s = torch.stack([t.float().sum(), torch.tensor(float(t.numel()), device=t.device)])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(s, group=group)
+    return s[0] / s[1]
+
+
+def sharded_sample(model, n_total: int, rank: int, world: int, seed: int = 0):
+    """Each rank draws and pushes forward its own rows of a global sample of ``n_total`` rows.
+    The latent rows are generated from a per-rank generator so the union over ranks does not
+    depend on the order in which ranks run."""
+    start, stop = shard_rows(n_total, rank, world)
+    prior = model.prior
+    if hasattr(prior, "generator"):
+        g = torch.Generator(device=prior.device)
+        g.manual_seed(seed * 1_000_003 + rank)
+        prior.generator = g
+    x, log_px, z = model.sample(stop - start)
+    return x, log_px, z, (start, stop)

@@ -1,0 +1,181 @@
+"""HMC driver with the reference's interface (nf/hmc.py:8-65) plus a batched, flow-backed
+``simulation`` object.
+
+``HMC`` drives any object that offers the reference's duck type (hmc.py:15-19, 39-40, 48-50, 63):
+``nparticles``, ``get_position()``, ``get_potential()``, ``set_position(p)``, ``set_velocity(v)``,
+``integration_step(path_len, dt) -> (position, potential)``.  As in the reference, velocities
+are drawn from N(0, diag(1/m)/init_beta) and the Metropolis test uses the potential only
+(quirk Q12).  When the simulation exposes ``n_chains > 1`` every chain is advanced and
+accepted/rejected independently in one batched step.
+
+``FlowSimulation`` is the flow-preconditioned target of BASELINE config 5: potential
+U(q) = -log p(q) under a NormalizingFlowModel, force = grad_q log p(q) through the flow's custom
+backward kernels, velocity-Verlet integration with the kick/drift kernels of libnfk.  Unlike the
+reference's pure-torch integrators (applications/src/systems.py:331-336, quirk Q13) the force is
+re-evaluated at the new position every step.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch.distributions import MultivariateNormal
+
+from . import _ops
+
+
+class HMC:
+    def __init__(self, simulation, init_pos=None, path_len=1, dt=None, mass=None, dim=3, beta=1.0, init_beta=None):
+        self.simulation = simulation
+        self.dt = dt
+        self.path_len = path_len
+        self.beta = beta
+        self.dim = dim
+        self.nparticles = simulation.nparticles
+        self.n_chains = int(getattr(simulation, "n_chains", 1))
+        self.position = simulation.get_position()
+        self.potential = simulation.get_potential()
+        if init_pos is not None:
+            self.simulation.set_position(init_pos)
+        self.mass = torch.ones(self.nparticles) if mass is None else mass
+        if init_beta is None:
+            init_beta = beta
+        self.init_beta = init_beta
+        # per-coordinate 1/m, particle-major like the reference (hmc.py:23)
+        self._inv_mass = (1 / self.mass).expand(self.dim, self.nparticles).transpose(0, 1).flatten()
+        self.v_dist = MultivariateNormal(torch.zeros(self.dim * self.nparticles),
+                                         torch.diag(self._inv_mass) / init_beta)
+
+    # ---- velocities ---------------------------------------------------------------------
+    def generate_v(self):
+        if self.n_chains == 1:
+            v = self.v_dist.sample((1,))
+            return v.flatten(), self.v_dist.log_prob(v)
+        dev = self.simulation.device
+        std = torch.sqrt(self._inv_mass / self.init_beta).to(dev)
+        v = torch.randn(self.n_chains, self.dim * self.nparticles, device=dev,
+                        generator=getattr(self.simulation, "generator", None)) * std
+        return v, self._log_prob_v(v)
+
+    def _log_prob_v(self, v):
+        var = (self._inv_mass / self.init_beta).to(v.device)
+        return (-0.5 * (v * v / var).sum(-1) - 0.5 * torch.log(2 * math.pi * var).sum())
+
+    def run_sim(self, v=None):
+        if v is None:
+            v, log_prob = self.generate_v()
+        else:
+            log_prob = self.v_dist.log_prob(v) if self.n_chains == 1 else self._log_prob_v(v)
+        self.simulation.set_velocity(v)
+        position, potential = self.simulation.integration_step(self.path_len, self.dt)
+        return position, potential, log_prob
+
+    # ---- chain --------------------------------------------------------------------------
+    def hmc(self, epochs=1, init_pos=None):
+        if init_pos is not None:
+            self.simulation.set_position(init_pos)
+            self.position = init_pos
+            self.potential = self.simulation.get_potential()
+        if self.n_chains > 1:
+            return self._hmc_batched(epochs)
+        positions, potentials, naccept, log_prob = [], [], 0, None
+        for _ in range(epochs):
+            positions.append(torch.as_tensor(self.position).detach().clone().float().flatten())
+            potentials.append(self.potential)
+            position, potential, log_prob = self.run_sim()
+            acc_prob = math.exp((self.potential - potential) * self.beta)      # potential only (Q12)
+            if torch.rand(1) < acc_prob:
+                self.position = position.flatten()
+                self.potential = potential
+                naccept += 1
+            else:
+                self.simulation.set_position(self.position)
+        return (torch.stack(positions), torch.tensor([float(p) for p in potentials]),
+                torch.as_tensor(log_prob), naccept / epochs)
+
+    def _hmc_batched(self, epochs):
+        sim = self.simulation
+        pos = sim.get_position().clone()
+        pot = sim.get_potential().clone()
+        positions, potentials, accepted, log_prob = [], [], 0.0, None
+        for _ in range(epochs):
+            positions.append(pos.clone())
+            potentials.append(pot.clone())
+            new_pos, new_pot, log_prob = self.run_sim()
+            u = torch.rand(self.n_chains, device=pos.device, generator=getattr(sim, "generator", None))
+            acc = u < torch.exp((pot - new_pot) * self.beta)
+            pos = torch.where(acc[:, None], new_pos, pos)
+            pot = torch.where(acc, new_pot, pot)
+            accepted += float(acc.float().mean())
+            sim.set_position(pos)
+        self.position, self.potential = pos, pot
+        return torch.stack(positions), torch.stack(potentials), log_prob, accepted / epochs
+
+
+class FlowSimulation:
+    """Batched ``simulation`` for ``HMC``: ``n_chains`` independent chains in the d-dimensional
+    space of a NormalizingFlowModel, potential U = -log p_flow."""
+
+    def __init__(self, model, n_chains, nparticles=None, dim=None, init_pos=None, mass=1.0, generator=None):
+        self.model = model
+        self.n_chains = int(n_chains)
+        p = next(model.parameters())
+        self.device = p.device
+        self.generator = generator
+        if init_pos is None:
+            init_pos = model.sample(self.n_chains)[0]          # chains start from flow samples (dynamics.py:60-62)
+        self.position = init_pos.to(self.device, torch.float32).reshape(self.n_chains, -1).contiguous().clone()
+        self.d = self.position.shape[1]
+        self.dim = dim if dim is not None else 1
+        self.nparticles = nparticles if nparticles is not None else self.d // self.dim
+        self.inv_mass = 1.0 / float(mass)
+        self.velocity = torch.zeros_like(self.position)
+        self.grad_evals = 0
+
+    # duck type ---------------------------------------------------------------------------
+    def get_position(self):
+        return self.position
+
+    def set_position(self, position):
+        self.position = position.to(self.device, torch.float32).reshape(self.n_chains, -1).contiguous().clone()
+
+    def set_velocity(self, velocity):
+        self.velocity = velocity.to(self.device, torch.float32).reshape(self.n_chains, -1).contiguous().clone()
+
+    def potential(self, x):
+        return -self.model.evaluate(x)
+
+    def get_potential(self, x=None):
+        return self.potential(self.position if x is None else x)
+
+    def potential_and_force(self, q):
+        """U(q) [C] and F(q) = -grad U = grad log p [C, d] — one forward + one backward through the flow."""
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        for p in params:
+            p.requires_grad_(False)              # dgrad only: no weight gradients in the leapfrog
+        try:
+            with torch.enable_grad():
+                x = q.detach().requires_grad_(True)
+                z, prior_lp, log_det = self.model.forward(x)
+                logp = prior_lp + log_det
+                (force,) = torch.autograd.grad(logp.sum(), x)
+        finally:
+            for p in params:
+                p.requires_grad_(True)
+        self.grad_evals += 1
+        return -logp.detach(), force.contiguous()
+
+    def integration_step(self, path_len=1, dt=0.005, init_pos=None, init_velocity=None):
+        if init_pos is not None:
+            self.set_position(init_pos)
+        if init_velocity is not None:
+            self.set_velocity(init_velocity)
+        if dt is None:
+            dt = 0.005
+        q, p = self.position, self.velocity       # unit-mass convention: p is the velocity
+        pot, force = self.potential_and_force(q)
+        for _ in range(path_len):
+            _ops.leapfrog_kick_drift(q, p, force, dt, self.inv_mass)      # p += dt/2 F ; q += dt p / m
+            pot, force = self.potential_and_force(q)
+            _ops.leapfrog_kick(p, force, dt)                               # p += dt/2 F(q_new)
+        return q, pot

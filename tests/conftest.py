@@ -1,4 +1,5 @@
 import os
+import subprocess
 import sys
 
 import pytest
@@ -10,6 +11,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    # the package refuses to import without libnfk.so (there is no fallback): build it once
+    lib = os.path.join(ROOT, "normalizingflow_b200", "libnfk.so")
+    if not os.path.exists(lib):
+        subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT, check=True)
 
 
 def pytest_collection_modifyitems(config, items):

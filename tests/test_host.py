@@ -1,0 +1,200 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports everything include/nfk.h
+declares, the layer classes keep the reference's constructor signatures / state-dict keys /
+error behaviour, the HMC driver reproduces the reference's chain, weight packing for the fused
+kernel, and the multi-rank helpers (gloo, world size 2)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import T, golden, sub_sd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from normalizingflow_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "nfk.h")).read()
+    declared = set(re.findall(r"\b(nfk_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    missing = [n for n in sorted(declared) if not hasattr(_lib.lib, n)]
+    assert not missing, missing
+    # every declared function has a ctypes signature and vice versa
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.MISSING == []
+    assert _lib.lib.nfk_abi_version() == 1
+    assert _lib.lib.nfk_nsf_fused_rows_per_tile() == 128
+
+
+def test_argument_errors_without_touching_a_gpu():
+    """shape checks run on the host before any launch: NFK_EINVAL -> ValueError (nf/utils.py:64-71)"""
+    import ctypes
+    from normalizingflow_b200 import _lib
+    bad_mask = (ctypes.c_int32 * 1)(5)
+    rc = _lib.lib.nfk_rqs_coupling(None, None, None, None, None, 4, 32, 2, bad_mask, 1, 8, 3.0, 0, 0, 1, None)
+    assert rc == _lib.NFK_EINVAL and b"mask" in _lib.lib.nfk_last_error()
+    ok_mask = (ctypes.c_int32 * 1)(1)
+    rc = _lib.lib.nfk_rqs_coupling(None, None, None, None, None, 4, 32, 2, ok_mask, 1, 2000, 3.0, 0, 0, 1, None)
+    assert rc == _lib.NFK_EINVAL
+    assert _lib.lib.nfk_rqs_coupling(None, None, None, None, None, 0, 32, 2, ok_mask, 1, 8, 3.0, 0, 0, 1, None) == 0
+    with pytest.raises(ValueError):
+        _lib.check(_lib.NFK_EINVAL, "x")
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.NFK_ECUDA, "x")
+
+
+def test_state_dict_keys_and_ctor_signatures_match_reference():
+    import inspect
+    from nf.flows import FCNN, NSF_CL, Planar, Radial, RealNVP
+    from nf.models import NormalizingFlowModel
+    g = golden("nsfcl_d64.npz")
+    ref_keys = sorted(k[len("m0.sd."):] for k in g.files if k.startswith("m0.sd."))
+    layer = NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=24, mask=[0])
+    assert sorted(layer.state_dict().keys()) == ref_keys
+    layer.load_state_dict(sub_sd(g, "m0.sd."))                        # reference checkpoint loads
+    assert isinstance(layer.mask, torch.Tensor) and layer.mask.dtype == torch.int64      # Q14
+    assert "mask" not in layer.state_dict()
+    sig = inspect.signature(NSF_CL.__init__).parameters
+    assert [sig[k].default for k in ("dim", "K", "B", "hidden_dim", "device", "mask")] == [3, 32, 3, 800, "cpu", [1]]
+    g = golden("realnvp.npz")
+    ref_keys = sorted(k[len("d6.sd."):] for k in g.files if k.startswith("d6.sd."))
+    assert sorted(RealNVP(6, hidden_dim=40).state_dict().keys()) == ref_keys
+    assert inspect.signature(RealNVP.__init__).parameters["hidden_dim"].default == 800
+    assert sorted(Planar(5).state_dict().keys()) == ["b", "u", "w"]
+    assert sorted(Radial(5).state_dict().keys()) == ["beta", "log_alpha", "x0"]
+    g = golden("models.npz")
+    ref_keys = sorted(k[len("nsf.sd."):] for k in g.files if k.startswith("nsf.sd."))
+    m = NormalizingFlowModel(None, [NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=16, mask=[i % 2]) for i in range(8)])
+    assert sorted(m.state_dict().keys()) == ref_keys
+    assert list(FCNN(3, 4, 5).state_dict().keys()) == [f"network.{i}.{p}" for i in (0, 2, 4) for p in ("weight", "bias")]
+
+
+def test_no_cpu_path_and_reference_error_behaviour():
+    from nf.flows import NSF_CL, Planar, Radial
+    from nf.utils import unconstrained_RQS
+    layer = NSF_CL(4, dim=3, K=8, B=3.0, hidden_dim=8, mask=[1])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        layer.forward(torch.zeros(2, 12))
+    with pytest.raises(NotImplementedError):
+        Planar(4).inverse(torch.zeros(1, 4))                            # flows_1.py:62-63
+    with pytest.raises(NotImplementedError):
+        Radial(4).inverse(torch.zeros(1, 4))
+    with pytest.raises(NotImplementedError):
+        Planar(4, nonlinearity=torch.nn.functional.elu)
+    with pytest.raises(ValueError, match="Minimal bin width"):           # utils.py:68-69
+        unconstrained_RQS(torch.zeros(1), torch.zeros(1, 2000), torch.zeros(1, 2000), torch.zeros(1, 1999))
+
+
+class _HarmonicSim:
+    """the duck-typed simulation oracle/gen_golden.py drove the reference HMC with"""
+
+    def __init__(self, nparticles, dim, k=1.0):
+        self.nparticles, self.dim, self.k = nparticles, dim, k
+        self.position = torch.linspace(-1, 1, nparticles * dim)
+        self.velocity = torch.zeros(nparticles * dim)
+
+    def get_position(self):
+        return self.position
+
+    def get_potential(self):
+        return 0.5 * self.k * torch.sum(self.position ** 2)
+
+    def set_position(self, p):
+        self.position = p.flatten().clone()
+
+    def set_velocity(self, v):
+        self.velocity = v.flatten().clone()
+
+    def integration_step(self, path_len, dt):
+        q, v = self.position, self.velocity
+        f = -self.k * q
+        for _ in range(path_len):
+            v = v + 0.5 * dt * f
+            q = q + dt * v
+            f = -self.k * q
+            v = v + 0.5 * dt * f
+        self.position, self.velocity = q, v
+        return q, self.get_potential()
+
+
+def test_hmc_driver_reproduces_reference_chain():
+    """velocity law, potential-only Metropolis rule (Q12) and bookkeeping of nf/hmc.py:43-65"""
+    from nf.hmc import HMC
+    g = golden("hmc.npz")
+    sim = _HarmonicSim(int(g["nparticles"]), int(g["dim"]), k=float(g["k"]))
+    torch.manual_seed(int(g["seed"]))
+    h = HMC(sim, path_len=int(g["path_len"]), dt=float(g["dt"]), dim=int(g["dim"]), beta=float(g["beta"]))
+    pos, pot, logp, acc = h.hmc(epochs=int(g["epochs"]))
+    assert pos.shape == g["positions"].shape
+    np.testing.assert_allclose(pos.numpy(), g["positions"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(pot.numpy(), g["potentials"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(logp.numpy(), g["last_logp"], rtol=1e-6, atol=1e-6)
+    assert acc == pytest.approx(float(g["accept"]))
+
+
+def test_fused_weight_image_is_the_sw128_layout():
+    from normalizingflow_b200._fused import _swizzle_image
+    rows, kb = 24, 2
+    m = torch.arange(rows * 64 * kb, dtype=torch.float32).reshape(rows, 64 * kb).to(torch.bfloat16)
+    img = _swizzle_image(m)
+    assert img.shape == (kb, rows, 8, 8)
+    flat = img.reshape(kb, rows * 64)
+    for b in range(kb):
+        for r in (0, 1, 7, 8, 13, 23):
+            for c in range(8):
+                src = m[r, b * 64 + c * 8: b * 64 + c * 8 + 8]
+                dst = flat[b, r * 64 + ((c ^ (r & 7)) * 8): r * 64 + ((c ^ (r & 7)) * 8) + 8]
+                assert torch.equal(src, dst)
+
+
+def test_shard_rows_partitions_the_batch():
+    from normalizingflow_b200.dist import shard_rows
+    for n, w in ((1 << 20, 8), (10, 3), (7, 8), (0, 2)):
+        spans = [shard_rows(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    from normalizingflow_b200 import dist as nd
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = nd.init_from_env("gloo")
+    torch.manual_seed(100 + rank)                       # ranks start from DIFFERENT weights
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    nd.broadcast_parameters(net, src=0)
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(64, 6, generator=gen)               # the GLOBAL batch; each rank takes its rows
+    a, b = nd.shard_rows(64, r, w)
+    loss = net(x[a:b]).pow(2).mean()
+    loss.backward()
+    nbytes = nd.allreduce_gradients(net.parameters(), average=True)
+    gm = nd.global_mean(net(x[a:b]).detach().flatten())
+    flat = torch.cat([p.grad.flatten() for p in net.parameters()])
+    wts = torch.cat([p.detach().flatten() for p in net.parameters()])
+    if rank == 0:
+        torch.save({"grad": flat, "w": wts, "bytes": nbytes, "gm": gm}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_matches_single_process_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r0.pt")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(100)                              # rank 0's weights were broadcast
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    x = torch.randn(64, 6, generator=torch.Generator().manual_seed(7))
+    net(x).pow(2).mean().backward()                     # equal shard sizes: mean of means == global mean
+    ref = torch.cat([p.grad.flatten() for p in net.parameters()])
+    assert torch.allclose(got["w"], torch.cat([p.detach().flatten() for p in net.parameters()]))
+    assert torch.allclose(got["grad"], ref, rtol=1e-5, atol=1e-6)
+    assert got["bytes"] == ref.numel() * 4
+    assert torch.allclose(got["gm"], net(x).detach().mean(), rtol=1e-5, atol=1e-6)
