@@ -32,7 +32,7 @@ ROW_BYTES_PER_LAYER = 32 * 23 * 4 + 64 * 4 + 64 * 4 + 8      # SURVEY.md §8(d):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="rows per GPU")
@@ -138,7 +138,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -151,7 +151,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -266,15 +266,9 @@ def run_native(a):
         out_lpx = torch.empty(N, dtype=torch.float32).pin_memory()
 
         def e2e_step():
-            xd = hx.to(dev, non_blocking=True)
-            zd = hz.to(dev, non_blocking=True)
-            lp = model.evaluate(xd)                                    # log p(x): forward + prior
-            with torch.no_grad():
-                xs, ldi = model.inverse(zd)                            # sampling direction
-                lpx = model.prior.log_prob(zd) - ldi
-            out_lp.copy_(lp, non_blocking=True)
-            out_x.copy_(xs, non_blocking=True)
-            out_lpx.copy_(lpx, non_blocking=True)
+            # public host-buffer API: row chunks stream through the GPU, copies overlap kernels
+            model.evaluate_host(hx, out=out_lp)                        # log p(x): forward + prior
+            model.inverse_host(hz, out_x=out_x, out_log_px=out_lpx)    # sampling direction
 
         for _ in range(2):
             e2e_step()
@@ -293,7 +287,8 @@ def run_native(a):
         ems = float(t.item()) / a.steps
         e2e = {"value": world * N / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems,
                "h2d_bytes_per_step": 2 * N * D * 4, "d2h_bytes_per_step": N * D * 4 + 2 * N * 4,
-               "api": "NormalizingFlowModel.evaluate(x) + NormalizingFlowModel.inverse(z) on pinned host buffers"}
+               "api": "NormalizingFlowModel.evaluate_host(x) + inverse_host(z): pinned host buffers, 131072-row chunks, "
+                      "H2D / kernels / D2H on three streams"}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -108,3 +108,70 @@ class NormalizingFlowModel(nn.Module):
             z, prior_logprob, log_det = self.forward(x)
             log_px = prior_logprob + log_det
         return log_px.data
+
+
+    # ------------------------------------------------------------------------------------
+    # host-buffer entry points: batches that live in (pinned) host memory are streamed through
+    # the GPU in row chunks, with the host->device copy of chunk i+1 and the device->host copy of
+    # chunk i-1 overlapping the kernels of chunk i (three CUDA streams, rotating device buffers).
+    # Same results as evaluate()/inverse() on the whole batch: rows are independent.
+    # ------------------------------------------------------------------------------------
+    def _stream_rows(self, host_in, fn, outs, chunk_rows):
+        dev = next(self.parameters()).device
+        n, d = host_in.shape
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        nbuf = 3
+        bufs = [torch.empty((min(chunk_rows, n), d), dtype=torch.float32, device=dev) for _ in range(nbuf)]
+        free = [None] * nbuf
+        with torch.no_grad():
+            for i, a in enumerate(range(0, n, chunk_rows)):
+                b = min(n, a + chunk_rows)
+                k = i % nbuf
+                with torch.cuda.stream(s_in):
+                    if free[k] is not None:
+                        s_in.wait_event(free[k])
+                    xin = bufs[k][: b - a]
+                    xin.copy_(host_in[a:b], non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(s_in)
+                cur.wait_event(ready)
+                res = fn(xin)
+                done = torch.cuda.Event()
+                done.record(cur)
+                free[k] = done
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(done)
+                    for r, o in zip(res, outs):
+                        o[a:b].copy_(r, non_blocking=True)
+                        r.record_stream(s_out)
+        cur.wait_stream(s_out)
+        cur.wait_stream(s_in)
+        return outs
+
+    def evaluate_host(self, x_host, out=None, chunk_rows=131072):
+        """log p(x) for a batch in host memory -> host tensor [N] (pinned when allocated here)."""
+        if out is None:
+            out = torch.empty(x_host.shape[0], dtype=torch.float32).pin_memory()
+
+        def fn(x):
+            z, prior_logprob, log_det = self.forward(x)
+            return (prior_logprob + log_det,)
+        self._stream_rows(x_host, fn, (out,), chunk_rows)
+        return out
+
+    def inverse_host(self, z_host, out_x=None, out_log_px=None, chunk_rows=131072):
+        """sampling direction for latents in host memory -> (x, log_px) host tensors, as sample()."""
+        n, d = z_host.shape
+        if out_x is None:
+            out_x = torch.empty((n, d), dtype=torch.float32).pin_memory()
+        if out_log_px is None:
+            out_log_px = torch.empty(n, dtype=torch.float32).pin_memory()
+
+        def fn(z):
+            x, log_det = self.inverse(z)
+            return x, self.prior.log_prob(z) - log_det
+        self._stream_rows(z_host, fn, (out_x, out_log_px), chunk_rows)
+        return out_x, out_log_px

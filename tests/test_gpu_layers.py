@@ -200,3 +200,20 @@ def test_fused_layer_kernel_matches_unfused_and_reference(H):
                 layer.fused = True
                 _, la = layer._transform(x.cuda(), inv, acc)
             assert rel_err(la, lf + 1.5) <= 1e-6
+
+
+def test_host_streaming_entry_points_equal_device_calls():
+    _, _, flows, models = _mods()
+    dev = torch.device("cuda")
+    torch.manual_seed(1)
+    fl = [flows.NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=16, mask=[i % 2]) for i in range(3)]
+    m = models.NormalizingFlowModel(models.GaussianPrior(64, device=dev), fl, device=dev).to(dev)
+    x = torch.randn(1000, 64).pin_memory()
+    lp = m.evaluate_host(x, chunk_rows=256)
+    xs, lpx = m.inverse_host(x, chunk_rows=300)
+    torch.cuda.synchronize()
+    ref = m.evaluate(x.cuda())
+    with torch.no_grad():
+        rx, rld = m.inverse(x.cuda())
+        rlpx = m.prior.log_prob(x.cuda()) - rld
+    assert torch.equal(lp, ref.cpu()) and torch.equal(xs, rx.cpu()) and torch.equal(lpx, rlpx.cpu())
