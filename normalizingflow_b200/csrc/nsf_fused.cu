@@ -69,14 +69,23 @@ struct RegParams {
   __device__ __forceinline__ float operator()(int i) const { return __uint_as_float(v[i]) + b[i]; }
   __device__ __forceinline__ float dyn(int base, int i) const {
     // K = 8: D logits are entries 16..22; select without indexing the register array
-    float r = __uint_as_float(v[16]) + b[16];
+    uint32_t r = v[16];
 #pragma unroll
     for (int j = 1; j < 7; ++j)
-      if (i == j) r = __uint_as_float(v[16 + j]) + b[16 + j];
-    return r;
+      if (i == j) r = v[16 + j];
+    return __uint_as_float(r) + b[16 + i];
   }
 };
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -157,29 +166,31 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
       __syncwarp();
     }
     unsigned g = 0, na = 0;          // running GEMM3 chunk counter, running bar_a phase counter
+    // every lane runs the same control flow (waits included); only the tcgen05 / TMA issue
+    // instructions sit under elect.sync, so the compiler keeps their operands uniform
     for (unsigned it = 0; it < my_tiles; ++it) {
-      const size_t tile = first + (size_t)it * stride;
       const bool tr = a.trace && blockIdx.x == 0 && it == 2 && lane == 0;
       int ts = 0;
 #define NFK_STAMP(base) do { if (tr) a.trace[(base) + ts++] = clock64(); } while (0)
-      if (lane == 0) {
-        // GEMM1: D12 = A1 W1^T
-        NFK_STAMP(0);
-        mbar_wait(bar_a, na++ & 1);
-        NFK_STAMP(0);
-        tc_fence_after();
+      // GEMM1: D12 = A1 W1^T
+      NFK_STAMP(0);
+      mbar_wait(bar_a, na++ & 1);
+      NFK_STAMP(0);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < FU_K1P / 16; ++k)
           umma_bf16(tD12, make_desc_sw128(aA + k * 32), make_desc_sw128(aW1 + k * 32), idesc12, k ? 1u : 0u);
         umma_commit(bar_mma);
-        NFK_STAMP(0);
       }
-      if (lane == 0) {
-        // GEMM2: D12 = A2 W2^T
-        NFK_STAMP(0);
-        mbar_wait(bar_a, na++ & 1);
-        NFK_STAMP(0);
-        tc_fence_after();
+      __syncwarp();
+      NFK_STAMP(0);
+      // GEMM2: D12 = A2 W2^T
+      NFK_STAMP(0);
+      mbar_wait(bar_a, na++ & 1);
+      NFK_STAMP(0);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -187,17 +198,20 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
             umma_bf16(tD12, make_desc_sw128(aA + kb * (FU_ROWS * 128) + k * 32),
                       make_desc_sw128(aW2 + kb * (FU_HP * 128) + k * 32), idesc12, (kb | k) ? 1u : 0u);
         umma_commit(bar_mma);
-        NFK_STAMP(0);
-        // GEMM3 chunks: D3[g & 1] = A3 W3chunk^T
-        mbar_wait(bar_a, na++ & 1);
-        NFK_STAMP(0);
-        for (int c = 0; c < FU_NCHUNK; ++c, ++g) {
-          const int s = g % FU_W3STAGES;
-          mbar_wait(&bar_w3[s], (g / FU_W3STAGES) & 1);
-          if (g >= 2) mbar_wait(&bar_d3e[g & 1], ((g >> 1) + 1) & 1);   // chunk g-2 left this buffer
-          tc_fence_after();
-          const uint32_t d = tmem + 128 + (g & 1) * FU_NC;
-          const uint32_t bbase = aW3 + s * FU_W3C_BYTES;
+      }
+      __syncwarp();
+      NFK_STAMP(0);
+      // GEMM3 chunks: D3[g & 1] = A3 W3chunk^T
+      mbar_wait(bar_a, na++ & 1);
+      NFK_STAMP(0);
+      for (int c = 0; c < FU_NCHUNK; ++c, ++g) {
+        const int s = g % FU_W3STAGES;
+        mbar_wait(&bar_w3[s], (g / FU_W3STAGES) & 1);
+        if (g >= 2) mbar_wait(&bar_d3e[g & 1], ((g >> 1) + 1) & 1);   // chunk g-2 left this buffer
+        tc_fence_after();
+        const uint32_t d = tmem + 128 + (g & 1) * FU_NC;
+        const uint32_t bbase = aW3 + s * FU_W3C_BYTES;
+        if (elect_one()) {
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -205,15 +219,16 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
               umma_bf16(d, make_desc_sw128(aA + kb * (FU_ROWS * 128) + k * 32),
                         make_desc_sw128(bbase + kb * (FU_NC * 128) + k * 32), idesc3, (kb | k) ? 1u : 0u);
           umma_commit(&bar_d3f[g & 1]);
-          NFK_STAMP(0);
-          if (g >= 1 && g + 2 < total_chunks) {
-            // chunk g-1 has been consumed by the tensor core: refill its ring slot with chunk g+2
-            mbar_wait(&bar_d3f[(g - 1) & 1], ((g - 1) >> 1) & 1);
-            issue_w3(g + 2);
-          }
+        }
+        __syncwarp();
+        NFK_STAMP(0);
+        if (g >= 1 && g + 2 < total_chunks) {
+          // chunk g-1 has been consumed by the tensor core: refill its ring slot with chunk g+2
+          mbar_wait(&bar_d3f[(g - 1) & 1], ((g - 1) >> 1) & 1);
+          if (lane == 0) issue_w3(g + 2);
+          __syncwarp();
         }
       }
-      __syncwarp();
     }
   } else {
     // =============================== epilogue warps ===============================
