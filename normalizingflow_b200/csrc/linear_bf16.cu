@@ -14,7 +14,7 @@ namespace nfk {
 
 constexpr int LB_M = 128;      // rows per CTA = TMEM lanes
 constexpr int LB_K = 64;       // K block: 64 bf16 = 128 bytes = one swizzle row
-constexpr int LB_THREADS = 128;
+constexpr int LB_THREADS = 256;   // 8 warps: all load operands; epilogue = 4 lane quadrants x 2 column halves
 
 // rows x 64 bf16 tile of a row-major matrix -> swizzled smem (zero fill outside the matrix)
 __device__ __forceinline__ void load_tile_sw128(unsigned char* smem_tile, const __nv_bfloat16* g,
@@ -31,15 +31,38 @@ __device__ __forceinline__ void load_tile_sw128(unsigned char* smem_tile, const 
   }
 }
 
-template <bool OUT_F32>
+// same tile, but with cp.async (LDGSTS): 16-byte chunks go global -> shared without passing through
+// registers, so several K blocks can be in flight per thread (src-size 0 zero-fills)
+__device__ __forceinline__ void load_tile_sw128_async(unsigned char* smem_tile, const __nv_bfloat16* g,
+                                                      long long ld, long long row0, long long n_rows,
+                                                      int k0, int K, int rows, int tid) {
+  for (int i = tid; i < rows * 8; i += LB_THREADS) {
+    const int r = i >> 3, c = i & 7;
+    const long long gr = row0 + r;
+    const int gk = k0 + c * 8;
+    const bool ok = gr < n_rows && gk < K;
+    const __nv_bfloat16* src = ok ? g + gr * ld + gk : g;
+    const uint32_t dst = smem_u32(smem_tile + r * 128 + ((c ^ (r & 7)) << 4));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool OUT_F32, int LB_STAGES>
 __global__ void __launch_bounds__(LB_THREADS)
 linear_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
                    const __nv_bfloat16* __restrict__ W, long long ldw,
                    const float* __restrict__ bias, void* __restrict__ Y, long long ldy,
                    long long M, int K, int N, int BN, int act, uint32_t tmem_cols) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t mma_done[2];
+  __shared__ uint64_t mma_done[LB_STAGES];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float sbias[256];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long m0 = (long long)blockIdx.x * LB_M;
   const int n0 = blockIdx.y * BN;
@@ -51,107 +74,108 @@ linear_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
 
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
   if (tid == 0) {
-    mbar_init(&mma_done[0], 1);
-    mbar_init(&mma_done[1], 1);
+    for (int s = 0; s < LB_STAGES; ++s) mbar_init(&mma_done[s], 1);
     fence_barrier_init();
   }
+  for (int i = tid; i < bn; i += LB_THREADS) sbias[i] = (bias && n0 + i < N) ? bias[n0 + i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t idesc = make_idesc_bf16(LB_M, bn);
 
+  // LB_STAGES-deep cp.async ring over the K blocks; the tensor core drains a stage (tracked by
+  // tcgen05.commit on mma_done[stage]) before it is refilled
   const int KB = (K + LB_K - 1) / LB_K;
-  uint32_t ph[2] = {0u, 0u};
+  auto issue_loads = [&](int kb) {
+    unsigned char* sa = sbase + (kb % LB_STAGES) * stage_bytes;
+    load_tile_sw128_async(sa, X, ldx, m0, M, kb * LB_K, K, LB_M, tid);
+    load_tile_sw128_async(sa + a_bytes, W, ldw, n0, N, kb * LB_K, K, bn, tid);
+  };
+  for (int kb = 0; kb < LB_STAGES - 1; ++kb) {
+    if (kb < KB) issue_loads(kb);
+    cp_async_commit();
+  }
   for (int kb = 0; kb < KB; ++kb) {
-    const int s = kb & 1;
-    if (kb >= 2) {                       // the MMAs that read this stage two blocks ago are done
-      mbar_wait(&mma_done[s], ph[s]);
-      ph[s] ^= 1u;
+    const int s = kb % LB_STAGES;
+    // refill the stage K block kb-1 used (its MMAs must have completed) with block kb+STAGES-1
+    const int nxt = kb + LB_STAGES - 1;
+    if (nxt < KB) {
+      if (kb >= 1) mbar_wait(&mma_done[(kb - 1) % LB_STAGES], ((kb - 1) / LB_STAGES) & 1);
+      issue_loads(nxt);
     }
-    unsigned char* sa = sbase + s * stage_bytes;
-    unsigned char* sb = sa + a_bytes;
-    load_tile_sw128(sa, X, ldx, m0, M, kb * LB_K, K, LB_M, tid);
-    load_tile_sw128(sb, W, ldw, n0, N, kb * LB_K, K, bn, tid);
-    fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core
+    cp_async_commit();
+    cp_async_wait<LB_STAGES - 1>();      // this thread's part of block kb has landed
+    fence_proxy_async();                 // ... and is visible to the tensor core
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(sa), b_addr = smem_u32(sb);
+      const uint32_t a_addr = smem_u32(sbase + s * stage_bytes), b_addr = a_addr + a_bytes;
 #pragma unroll
-      for (int k = 0; k < LB_K / 16; ++k) {
-        const uint64_t da = make_desc_sw128(a_addr + k * 32);
-        const uint64_t db = make_desc_sw128(b_addr + k * 32);
-        umma_bf16(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
-      }
+      for (int k = 0; k < LB_K / 16; ++k)
+        umma_bf16(tmem_d, make_desc_sw128(a_addr + k * 32), make_desc_sw128(b_addr + k * 32), idesc,
+                  (kb | k) ? 1u : 0u);
       umma_commit(&mma_done[s]);         // implies tcgen05.fence::before_thread_sync
     }
   }
-  // wait for the last commit of each stage that is still outstanding
-  {
-    const int last = (KB - 1) & 1;
-    if (KB >= 2) {
-      mbar_wait(&mma_done[last ^ 1], ph[last ^ 1]);
-    }
-    mbar_wait(&mma_done[last], ph[last]);
-  }
+  // MMAs complete in order: the last block's commit covers all of them
+  mbar_wait(&mma_done[(KB - 1) % LB_STAGES], ((KB - 1) / LB_STAGES) & 1);
   tc_fence_after();
+  __syncthreads();                       // every thread sees the operand stages as free (staging reuse)
 
-  // ---- epilogue: thread = row (TMEM lane), 32 columns per tcgen05.ld
-  const long long row = m0 + warp * 32 + lane;
-  const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
-  for (int c0 = 0; c0 < bn; c0 += 32) {
+  // ---- epilogue: thread = row (TMEM lane), 32 columns per tcgen05.ld.  The 32x32 block of a warp
+  // is transposed through a padded shared-memory tile (the operand stages are idle now) so that
+  // every global store instruction writes one contiguous row segment (128 B fp32 / 64 B bf16)
+  // instead of 32 scattered 16-byte pieces.
+  float* stg = reinterpret_cast<float*>(sbase) + warp * (32 * 33);
+  const int q = warp & 3;                                  // TMEM lane quadrant of this warp
+  const long long row_w0 = m0 + q * 32;                    // first row of this warp
+  const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
+  const bool last_tile = (n0 + bn >= N);
+  for (int c0 = (warp >> 2) * 32; c0 < bn; c0 += 64) {
     uint32_t v[32];
     tmem_ld32(lane_addr + (uint32_t)c0, v);
     tmem_ld_wait();
-    if (row < M) {
-      const int ncol = min(min(32, bn - c0), N - (n0 + c0));   // columns this tile owns in the chunk
-      float f[32];
+    const int ncol = min(min(32, bn - c0), N - (n0 + c0));   // columns this tile owns in the chunk
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(v[j]);
-        if (j < ncol) {
-          if (bias) t += __ldg(bias + n0 + c0 + j);
-          if (act == 1) t = tanh_approx(t);
-        } else {
-          t = 0.f;
-        }
-        f[j] = t;
-      }
-      if (OUT_F32) {
-        float* yp = reinterpret_cast<float*>(Y) + row * ldy + n0 + c0;
-        if (ncol == 32 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(yp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-          for (int j = 0; j < ncol; ++j) yp[j] = f[j];
-        }
+    for (int j = 0; j < 32; ++j) {
+      float t = __uint_as_float(v[j]);
+      if (j < ncol) {
+        t += sbias[c0 + j];
+        if (act == 1) t = tanh_approx(t);
       } else {
-        __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(Y) + row * ldy + n0 + c0;
-        // pad columns up to ldy are written as zeros so the next layer can read K = ldy
-        // the last N tile also zero-fills the pad columns [N, ldy) so the next layer reads K = ldy
-        const long long left = ldy - (n0 + c0);
-        const int nwrite = (n0 + bn >= N && c0 + 32 >= bn) ? (left < 32 ? (int)left : 32) : ncol;
-        if (nwrite == 32 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-            __nv_bfloat162 p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-            __nv_bfloat162 p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&p0);
-            u.y = *reinterpret_cast<uint32_t*>(&p1);
-            u.z = *reinterpret_cast<uint32_t*>(&p2);
-            u.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(yp + j) = u;
+        t = 0.f;
+      }
+      stg[lane * 33 + j] = t;
+    }
+    __syncwarp();
+    if (OUT_F32) {
+      float* yb = reinterpret_cast<float*>(Y) + n0 + c0;
+      if (lane < ncol)
+        for (int r = 0; r < 32; ++r)
+          if (row_w0 + r < M) yb[(row_w0 + r) * ldy + lane] = stg[r * 33 + lane];
+    } else {
+      // the last N tile also zero-fills the pad columns [N, ldy) so the next layer reads K = ldy
+      const long long left = ldy - (n0 + c0);
+      const int nwrite = (last_tile && c0 + 32 >= bn) ? (left < 32 ? (int)left : 32) : ncol;
+      __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(Y) + n0 + c0;
+      // two rows per instruction: lanes 0..15 -> row r, lanes 16..31 -> row r+1, 2 columns each
+      const int half = lane >> 4, cp = (lane & 15) * 2;
+      for (int r = 0; r < 32; r += 2) {
+        const long long gr = row_w0 + r + half;
+        if (gr < M && cp < nwrite) {
+          const float f0 = stg[(r + half) * 33 + cp], f1 = stg[(r + half) * 33 + cp + 1];
+          __nv_bfloat16* dst = yb + gr * ldy + cp;
+          if (cp + 1 < nwrite && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
+            *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(f0, f1);
+          } else {
+            dst[0] = __float2bfloat16_rn(f0);
+            if (cp + 1 < nwrite) dst[1] = __float2bfloat16_rn(f1);
           }
-        } else {
-          for (int j = 0; j < nwrite; ++j) yp[j] = __float2bfloat16_rn(f[j]);
         }
       }
     }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -183,23 +207,30 @@ int nfk_linear_bf16(const void* X, int64_t ldx, const void* W, int64_t ldw, cons
   if (BN < 16) BN = 16;
   uint32_t cols = 32;
   while ((int)cols < BN) cols <<= 1;
-  const size_t smem = 2 * ((size_t)LB_M * 128 + (size_t)BN * 128) + 1024;
+  const int KBh = (K + LB_K - 1) / LB_K;
+  const int stages = KBh <= 2 ? 2 : 4;
+  const size_t smem = stages * ((size_t)LB_M * 128 + (size_t)BN * 128) + 1024;
   const long long gm = (M + LB_M - 1) / LB_M;
   NFK_REQUIRE(gm < (1LL << 31), "linear_bf16: too many rows");
   dim3 grid((unsigned)gm, (unsigned)n_tiles);
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* Xb = reinterpret_cast<const __nv_bfloat16*>(X);
   const __nv_bfloat16* Wb = reinterpret_cast<const __nv_bfloat16*>(W);
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+#define NFK_LB(F32, ST)                                                                                   \
+  do {                                                                                                    \
+    e = cudaFuncSetAttribute(linear_bf16_kernel<F32, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                             (int)smem);                                                                  \
+    if (e == cudaSuccess)                                                                                 \
+      linear_bf16_kernel<F32, ST><<<grid, LB_THREADS, smem, st>>>(Xb, ldx, Wb, ldw, b, Y, ldy, M, K, Nout, \
+                                                                  BN, act, cols);                         \
+  } while (0)
   if (out_f32) {
-    e = cudaFuncSetAttribute(linear_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-      linear_bf16_kernel<true><<<grid, LB_THREADS, smem, st>>>(Xb, ldx, Wb, ldw, b, Y, ldy, M, K, Nout, BN, act, cols);
+    if (stages == 2) NFK_LB(true, 2); else NFK_LB(true, 4);
   } else {
-    e = cudaFuncSetAttribute(linear_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-      linear_bf16_kernel<false><<<grid, LB_THREADS, smem, st>>>(Xb, ldx, Wb, ldw, b, Y, ldy, M, K, Nout, BN, act, cols);
+    if (stages == 2) NFK_LB(false, 2); else NFK_LB(false, 4);
   }
+#undef NFK_LB
   if (e != cudaSuccess) {
     set_error("linear_bf16: cannot set %zu B dynamic shared memory: %s", smem, cudaGetErrorString(e));
     return NFK_ECUDA;
