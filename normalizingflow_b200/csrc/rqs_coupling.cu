@@ -361,17 +361,31 @@ static int launch_coupling(CouplingArgs& a, long long N, cudaStream_t st) {
       }
     }
   } else if (aligned) {
-    // ---- generic geometry: one element per thread per tile
-    int R = g_tune_R > 0 ? g_tune_R : 4;
-    if (g_tune_R <= 0)
-      while ((2 * R) * F_t <= MAX_THREADS && R < 64) R *= 2;
-    R = (R + 3) & ~3;
+    // ---- generic geometry: one element per thread per tile.  Rows per tile (a multiple of 4 so
+    // every tile stays 16-byte aligned) are chosen to maximise resident warps per SM.
+    const size_t row_floats = (size_t)F_t * a.P + a.d;
+    const int stages = g_tune_stages > 0 ? g_tune_stages : 2;
+    int R = g_tune_R > 0 ? ((g_tune_R + 3) & ~3) : 0;
+    if (R == 0) {
+      int best_warps = -1;
+      for (int r = 4; r <= 64 && r * F_t <= MAX_THREADS; r += 4) {
+        const int thr = (r * F_t + 31) & ~31;
+        const size_t sm = (size_t)stages * r * row_floats * 4 + (size_t)2 * r * a.d * 4 + (size_t)2 * r * F_t * 4 + 320;
+        if (sm > 226 * 1024) break;
+        int ctas = (int)((227 * 1024) / (sm + 1024));
+        ctas = min(ctas, min(2048 / thr, 65536 / (thr * 80)));
+        const int warps = ctas * (thr / 32) * (r * F_t) / thr;      // discount idle lanes
+        if (warps > best_warps) {
+          best_warps = warps;
+          R = r;
+        }
+      }
+      if (R == 0) R = 4;
+    }
     const int n_el = R * F_t;
     const int threads = (n_el + 31) & ~31;
-    const size_t row_floats = (size_t)F_t * a.P + a.d;
     const size_t stage_bytes = (size_t)R * row_floats * 4;
     const size_t fixed = (size_t)2 * R * a.d * 4 + (size_t)2 * n_el * 4 + 8 * 8 + 128;
-    int stages = g_tune_stages > 0 ? g_tune_stages : 2;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     const long long n_tiles = N / R;
     if (threads <= MAX_THREADS && smem <= 226 * 1024 && n_tiles > 0 && n_tiles < (1LL << 31)) {
@@ -385,7 +399,7 @@ static int launch_coupling(CouplingArgs& a, long long N, cudaStream_t st) {
         return NFK_ECUDA;
       }
       int ctas_per_sm = g_tune_ctas > 0 ? g_tune_ctas : (int)((227 * 1024) / (smem + 1024));
-      ctas_per_sm = max(1, min(ctas_per_sm, 2048 / threads));
+      ctas_per_sm = max(1, min(ctas_per_sm, min(2048 / threads, 65536 / (threads * 80))));
       const long long cap = (long long)sm_count() * ctas_per_sm;
       const long long grid = n_tiles < cap ? n_tiles : cap;
       kern<<<(unsigned)grid, threads, smem, st>>>(a);

@@ -39,6 +39,7 @@ def main():
     if os.path.exists(pp):
         peak = float(json.load(open(pp))["hbm_gbs"])
     row_bytes = F_t * 23 * 4 + 2 * d * 4 + 8
+    print(f'size={a.size} dim={a.dim} mask={mask} F_t={F_t} row_bytes={row_bytes}')
     ld = torch.zeros(N, device=dev)
     for tune in a.tune:
         R, th, st, ct = (-1 if v == "g" else int(v) for v in tune.split(","))
