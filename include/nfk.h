@@ -126,6 +126,16 @@ int nfk_radial(const float* x, const float* x0, const float* log_alpha, const fl
                const float* sumsq, float* out, float* logdet, int64_t N, int d, int per_sample,
                int accumulate, void* stream);
 
+/* backward of the radial layer: grad_x [N,d]; grad_x0 [d], grad_log_alpha [1], grad_beta [1] are
+ * ACCUMULATED with atomics into zero-initialised buffers.  Batch-global mode needs sumsq (as the
+ * forward) and dot = sum(grad_out * (x - x0)) from nfk_radial_dot (all-reduced when sharded). */
+int nfk_radial_dot(const float* x, const float* x0, const float* grad_out, float* dot /*zeroed*/,
+                   int64_t N, int d, void* stream);
+int nfk_radial_bwd(const float* x, const float* x0, const float* log_alpha, const float* beta,
+                   const float* sumsq, const float* dot, const float* grad_out,
+                   const float* grad_logdet, float* grad_x, float* grad_x0, float* grad_log_alpha,
+                   float* grad_beta, int64_t N, int d, int per_sample, void* stream);
+
 /* ---- log-prob reduction: out[n] = -0.5*sum_j z[n,j]^2/var - 0.5*d*log(2*pi*var) (+ add[n]).
  * Replaces prior.log_prob + the additions at nf/models.py:19-20, :34, :39. */
 int nfk_gauss_logprob(const float* z, const float* add /*nullable*/, float add_sign, float* out,

@@ -291,9 +291,10 @@ def planar_stack(x, w, u, b, logdet=None):
     return out, logdet
 
 
-def radial(x, x0, log_alpha, beta, per_sample=False, logdet=None, group=None):
-    """Radial layer.  per_sample=False reproduces the reference's batch-global norm (Q9): the
-    sum of squares is all-reduced over ``group`` when the batch is sharded."""
+def radial(x, x0, log_alpha, beta, per_sample=False, logdet=None):
+    """Radial layer.  per_sample=False reproduces the reference's batch-global norm (Q9): when a
+    process group is initialised the sum of squares is all-reduced, so a sharded batch gives the
+    result of the whole batch."""
     dev = require_cuda(x, x0, log_alpha, beta)
     x, x0, log_alpha, beta = f32c(x), f32c(x0), f32c(log_alpha), f32c(beta)
     N, d = x.shape
@@ -303,9 +304,8 @@ def radial(x, x0, log_alpha, beta, per_sample=False, logdet=None, group=None):
         if not per_sample:
             sumsq = torch.zeros((1,), dtype=torch.float32, device=dev)
             call("nfk_radial_sumsq", ptr(x), ptr(x0), ptr(sumsq), N, d, stream_ptr(dev))
-            if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                     and group is not False):
-                torch.distributed.all_reduce(sumsq, group=group if group not in (None, False) else None)
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                torch.distributed.all_reduce(sumsq)
         accumulate = logdet is not None
         if not accumulate:
             logdet = torch.empty((N if per_sample else 1,), dtype=torch.float32, device=dev)
@@ -426,4 +426,27 @@ class RadialFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out, g_ld):
-        raise NotImplementedError("Radial backward kernel is not built yet")
+        x, x0, log_alpha, beta = ctx.saved_tensors
+        dev = x.device
+        xx, x0c, la, bb = f32c(x), f32c(x0), f32c(log_alpha), f32c(beta)
+        N, d = xx.shape
+        g_out = f32c(g_out) if g_out is not None else torch.zeros_like(xx)
+        g_ld = f32c(g_ld) if g_ld is not None else None
+        gx = torch.empty_like(xx)
+        gx0 = torch.zeros(d, dtype=torch.float32, device=dev)
+        gla = torch.zeros(1, dtype=torch.float32, device=dev)
+        gb = torch.zeros(1, dtype=torch.float32, device=dev)
+        sumsq = dot = None
+        with torch.cuda.device(dev):
+            if not ctx.per_sample:
+                sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+                dot = torch.zeros(1, dtype=torch.float32, device=dev)
+                call("nfk_radial_sumsq", ptr(xx), ptr(x0c), ptr(sumsq), N, d, stream_ptr(dev))
+                call("nfk_radial_dot", ptr(xx), ptr(x0c), ptr(g_out), ptr(dot), N, d, stream_ptr(dev))
+                if torch.distributed.is_available() and torch.distributed.is_initialized():
+                    both = torch.cat([sumsq, dot])
+                    torch.distributed.all_reduce(both)
+                    sumsq, dot = both[:1].contiguous(), both[1:].contiguous()
+            call("nfk_radial_bwd", ptr(xx), ptr(x0c), ptr(la), ptr(bb), ptr(sumsq), ptr(dot), ptr(g_out), ptr(g_ld),
+                 ptr(gx), ptr(gx0), ptr(gla), ptr(gb), N, d, int(bool(ctx.per_sample)), stream_ptr(dev))
+        return gx.view_as(x), gx0.view_as(x0), gla.view_as(log_alpha), gb.view_as(beta), None

@@ -357,6 +357,95 @@ radial_kernel(const float* __restrict__ x, const float* __restrict__ x0,
   }
 }
 
+// backward of the radial layer.  dot[0] must hold sum(gz * (x - x0)) over the whole batch in the
+// batch-global mode (radial_dot_kernel).  Parameter gradients are accumulated with atomics into
+// zero-initialised gx0 [d], gla [1], gbeta [1].
+__global__ void __launch_bounds__(256)
+radial_dot_kernel(const float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ gz,
+                  float* __restrict__ dot, long long total, int d) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    acc = fmaf(gz[i], x[i] - x0[i % d], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(dot, v);
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+radial_bwd_kernel(const float* __restrict__ x, const float* __restrict__ x0,
+                  const float* __restrict__ log_alpha, const float* __restrict__ beta_raw,
+                  const float* __restrict__ sumsq, const float* __restrict__ dot,
+                  const float* __restrict__ gz, const float* __restrict__ gld, float* __restrict__ gx,
+                  float* __restrict__ gx0, float* __restrict__ gla, float* __restrict__ gbeta,
+                  long long N, int d, int per_sample) {
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+  const long long row = gid / G;
+  const int g = (int)(gid % G);
+  const bool live = row < N;
+  const float alpha = expf(log_alpha[0]);
+  const float braw = beta_raw[0];
+  const float beta = -alpha + logf(1.f + expf(braw));
+  float r, S1, gl;
+  if (per_sample) {
+    float a2 = 0.f, a1 = 0.f;
+    if (live)
+      for (int j = g; j < d; j += G) {
+        const float df = x[row * d + j] - x0[j];
+        a2 = fmaf(df, df, a2);
+        a1 = fmaf(gz[row * d + j], df, a1);
+      }
+    r = sqrtf(group_sum<G>(a2));
+    S1 = group_sum<G>(a1);
+    gl = (live && gld) ? gld[row] : 0.f;
+  } else {
+    r = sqrtf(sumsq[0]);
+    S1 = dot[0];
+    gl = gld ? gld[0] : 0.f;
+  }
+  const float A = alpha + r, h = 1.f / A;
+  const float p = 1.f + beta * h, qv = 1.f + beta * h - beta * r * h * h;
+  const float n1 = (float)(d - 1);
+  // ld = (n-1) log p + log q  (flows_1.py:94-95)
+  float g_h = beta * S1 + gl * (n1 * beta / p + (beta - 2.f * beta * r * h) / qv);
+  float g_b = h * S1 + gl * (n1 * h / p + (h - r * h * h) / qv);
+  float g_r = gl * (-beta * h * h) / qv;
+  const float g_A = -g_h * h * h;
+  g_r += g_A;
+  float g_alpha = g_A - g_b;                                 // beta = -alpha + softplus(braw)
+  const float g_braw = g_b / (1.f + expf(-braw));
+  const float scale = 1.f + beta * h;
+  const float rinv = r > 0.f ? 1.f / r : 0.f;
+  if (live) {
+    for (int j = g; j < d; j += G) {
+      const float df = x[row * d + j] - x0[j];
+      const float v = gz[row * d + j] * scale + g_r * df * rinv;
+      gx[row * d + j] = v;
+      // z = x + beta h (x - x0): d/dx0 = -(beta h gz) - g_r df / r
+      atomicAdd(gx0 + j, -(gz[row * d + j] * beta * h) - g_r * df * rinv);
+    }
+  }
+  if (per_sample) {
+    float a = (live && g == 0) ? g_alpha * alpha : 0.f, b = (live && g == 0) ? g_braw : 0.f;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(gla, a);
+      atomicAdd(gbeta, b);
+    }
+  } else if (gid == 0) {
+    atomicAdd(gla, g_alpha * alpha);
+    atomicAdd(gbeta, g_braw);
+  }
+}
+
 // ---- log-prob reduction (nf/models.py:19-20, :34, :39) --------------------------------------
 template <int G>
 __global__ void __launch_bounds__(256)
@@ -615,6 +704,37 @@ int nfk_radial(const float* x, const float* x0, const float* log_alpha, const fl
                                                                 accumulate)));
   count_launch();
   return check_launch("radial");
+}
+
+int nfk_radial_dot(const float* x, const float* x0, const float* grad_out, float* dot, int64_t N, int d,
+                   void* stream) {
+  NFK_REQUIRE(N >= 0 && d > 0, "radial_dot: bad shape");
+  if (N == 0) return NFK_OK;
+  NFK_REQUIRE(x && x0 && grad_out && dot, "radial_dot: null device pointer");
+  const long long total = (long long)N * d;
+  radial_dot_kernel<<<ew_grid(total, 256 * 8), 256, 0, (cudaStream_t)stream>>>(x, x0, grad_out, dot, total, d);
+  count_launch();
+  return check_launch("radial_dot");
+}
+
+int nfk_radial_bwd(const float* x, const float* x0, const float* log_alpha, const float* beta,
+                   const float* sumsq, const float* dot, const float* grad_out, const float* grad_logdet,
+                   float* grad_x, float* grad_x0, float* grad_log_alpha, float* grad_beta, int64_t N, int d,
+                   int per_sample, void* stream) {
+  NFK_REQUIRE(N >= 0 && d > 0, "radial_bwd: bad shape");
+  if (N == 0) return NFK_OK;
+  NFK_REQUIRE(x && x0 && log_alpha && beta && grad_out && grad_x && grad_x0 && grad_log_alpha && grad_beta,
+              "radial_bwd: null device pointer");
+  NFK_REQUIRE(per_sample || (sumsq && dot), "radial_bwd: batch-global mode needs sumsq and dot");
+  const int G = pick_group(d);
+  const long long threads = (long long)N * G;
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  NFK_GROUP_SWITCH(G, (radial_bwd_kernel<GG><<<grid, 256, 0, st>>>(x, x0, log_alpha, beta, sumsq, dot, grad_out,
+                                                                    grad_logdet, grad_x, grad_x0, grad_log_alpha,
+                                                                    grad_beta, N, d, per_sample)));
+  count_launch();
+  return check_launch("radial_bwd");
 }
 
 int nfk_gauss_logprob(const float* z, const float* add, float add_sign, float* out, int64_t N,

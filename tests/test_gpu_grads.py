@@ -105,3 +105,38 @@ def test_planar_grads_single_and_fused_stack():
     assert rel_err(res[0][2], res[1][2]) <= GTOL
     for a, b in zip(res[0][3], res[1][3]):
         assert rel_err(a, b) <= GTOL
+
+
+def test_radial_grads_global_and_per_sample():
+    from normalizingflow_b200 import flows
+    from oracle import nf_oracle as O
+    g = golden("grads.npz")
+    rd = flows.Radial(16)
+    rd.load_state_dict(sub_sd(g, "radial.sd."))
+    rd = rd.cuda()
+    x = T(g["radial.x"]).cuda().requires_grad_()
+    out, ld = rd.forward(x)
+    ((out * T(g["radial.gz"]).cuda()).sum() + (ld * T(g["radial.gl"]).cuda()).sum()).backward()
+    assert ld.shape == (1,)
+    assert rel_err(out.detach(), g["radial.out"]) <= 1e-5 and rel_err(ld.detach(), g["radial.ld"]) <= 1e-5
+    assert rel_err(x.grad, g["radial.gx"]) <= GTOL
+    for k, v in rd.named_parameters():
+        assert rel_err(v.grad, g["radial.gw." + k]) <= GTOL, (k, rel_err(v.grad, g["radial.gw." + k]))
+    # corrected per-row-norm mode vs autograd through the oracle
+    rd2 = flows.Radial(16, per_sample=True)
+    rd2.load_state_dict(sub_sd(g, "radial.sd."))
+    rd2 = rd2.cuda()
+    gz, gl = T(g["radial.gz"]), T(g["radial.gl"])
+    xs = T(g["radial.x"])
+    x2 = xs.cuda().requires_grad_()
+    out2, ld2 = rd2.forward(x2)
+    ((out2 * gz.cuda()).sum() + (ld2 * gl.cuda()).sum()).backward()
+    ps = {k: T(g["radial.sd." + k]).clone().requires_grad_() for k in ("x0", "log_alpha", "beta")}
+    xr = xs.clone().requires_grad_()
+    ro, rl = O.radial(xr, ps["x0"], ps["log_alpha"], ps["beta"], per_sample=True)
+    ((ro * gz).sum() + (rl * gl).sum()).backward()
+    assert ld2.shape == (20,)
+    assert rel_err(out2.detach(), ro.detach()) <= 1e-5 and rel_err(ld2.detach(), rl.detach()) <= 1e-5
+    assert rel_err(x2.grad, xr.grad) <= GTOL
+    for k, v in rd2.named_parameters():
+        assert rel_err(v.grad, ps[k].grad) <= GTOL, k
