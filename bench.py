@@ -17,6 +17,11 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms (cpu_baseline, --impl reference)
+# run on rank 0 only and must see all host cores, so undo that before torch loads its OpenMP runtime
+if os.environ.get("RANK", "0") == "0" and os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -326,7 +331,7 @@ def run_native(a):
                            "fused_layer_kernel": bool(not a.no_fused and cond == "bf16"), "global_batch": world * N, "parallelism": f"batch-sharded x{world}",
                            "l2": "inputs larger than L2 (x 268 MB, spline params 3.1 GB per layer)"},
                 "roofline": roofline, "clocks": clk, "gpu_launches": launches, "e2e": e2e}
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:       # reported at N=1 only
             line["cpu_baseline"] = cpu_baseline(a, sd)
         print(json.dumps(line), flush=True)
     if world > 1:
