@@ -175,6 +175,26 @@ int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w
                         const float* b3, int64_t N, int mask_col, float B, int inverse,
                         int accumulate, int arith, void* stream);
 
+/* ---- wide conditioner path (hidden width > 128; the class default is 800, nf/flows.py:216):
+ * persistent warp-specialised tcgen05 GEMM  Y = act(A W^T + b)  over operands stored in HBM as
+ * *shared-memory images*: 128-row x 64-column bf16 blocks (16 KB) in the K-major SWIZZLE_128B
+ * layout (16-byte chunk j of row r holds source chunk j ^ (r % 8)), moved by 1-D TMA bulk copies.
+ *   a_img [ceil(M/128)][KB][128][64] bf16                    activations (rows >= M are zero)
+ *   w_img for N tile t of 64*tile_blocks[t] output columns:  [KB][64*tile_blocks[t]][64] bf16,
+ *         tiles concatenated; rows/columns beyond the real weight are zero
+ *   bias  [64 * sum(tile_blocks)] fp32, zero padded
+ *   out   out_f32 == 0: bf16 image [ceil(M/128)][sum(tile_blocks)][128][64] (next layer's a_img)
+ *         out_f32 != 0: fp32 rows [M, ldy], first n_out columns written
+ * kmma_last = ceil((K - 64*(KB-1)) / 16): tcgen05.mma count in the last K block.
+ * Replaces one nn.Linear(+Tanh) of FCNN (nf/flows.py:26-35). */
+int nfk_gemm_ws_rows_per_tile(void);
+int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* out, int64_t M,
+                int KB, int kmma_last, const int32_t* tile_blocks /*host*/, int n_tiles, int act,
+                int out_f32, int n_out, int64_t ldy, void* stream);
+/* x[:, :, cols].flatten(1) (nf/flows.py:230) -> bf16 a_img [ceil(N/128)][KB][128][64], zero padded */
+int nfk_pack_a_img(const float* x, void* img, int64_t N, int size, int dim, const int32_t* cols /*host*/,
+                   int n_cols, int KB, void* stream);
+
 /* x[:, cols] gather -> dense fp32 or bf16 [N, size*n_cols] (conditioner input, flows.py:230) */
 int nfk_gather_cols(const float* x, void* out, int64_t N, int size, int dim,
                     const int32_t* cols, int n_cols, int out_bf16, int64_t ld_out,

@@ -98,6 +98,10 @@ def mlp3(fcnn, x):
         x = x.reshape(x.shape[0], -1)
     if torch.is_grad_enabled() and (x.requires_grad or l0.weight.requires_grad):
         return MLP3Bf16Fn.apply(x, l0.weight, l0.bias, l2.weight, l2.bias, l4.weight, l4.bias, fcnn)
+    if x.dtype == torch.float32:
+        from . import _wide
+        if _wide.usable(fcnn):
+            return _wide.mlp3(fcnn, x)
     (p0, c0), (p2, c2), (p4, c4) = _packed_weights(fcnn)
     xb = to_bf16_padded(x)
     h1 = linear_bf16(xb, p0, c0, 1, False)

@@ -59,6 +59,9 @@ SIGNATURES = {
                                     c_int, _P]),
     "nfk_gemm_f32": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int64,
                              c_int, _P]),
+    "nfk_gemm_ws_rows_per_tile": (c_int, []),
+    "nfk_gemm_ws": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int64, _P]),
+    "nfk_pack_a_img": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, c_int, _P]),
     "nfk_gather_cols": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int64, _P]),
     "nfk_cast_f32_bf16": (c_int, [_P, _P, c_int64, _P]),
     "nfk_leapfrog_kick_drift": (c_int, [_P, _P, _P, c_int64, c_float, c_float, _P]),

@@ -1,0 +1,141 @@
+"""Host side of the wide conditioner path (csrc/gemm_ws.cu): FCNN (nf/flows.py:20-35) with a hidden
+width above 128 — e.g. the class default 800 (nf/flows.py:216) — as three launches of the
+persistent warp-specialised tcgen05 GEMM.  Every operand lives in HBM as the shared-memory image
+the tensor core reads (128 x 64 bf16 blocks, K-major SWIZZLE_128B), so the kernels move whole
+16 KB blocks with 1-D TMA bulk copies; weights are packed once per parameter version."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, _ops
+from ._lib import call, f32c, i32_array, ptr, require_cuda, stream_ptr
+
+ROWS = 128
+MIN_HIDDEN = 129      # narrower conditioners use the fused layer kernel / nfk_linear_bf16
+
+
+def available() -> bool:
+    return _lib.have("nfk_gemm_ws") and _lib.have("nfk_pack_a_img")
+
+
+def usable(fcnn) -> bool:
+    net = getattr(fcnn, "network", None)
+    return (available() and getattr(fcnn, "precision", None) == "bf16" and net is not None and len(net) == 5
+            and net[0].out_features >= MIN_HIDDEN)
+
+
+def blocks(n: int) -> int:
+    return (n + 63) // 64
+
+
+def plan_tiles(n_blocks: int):
+    """Split n_blocks 64-column blocks into the fewest N tiles of <= 4 blocks, evenly sized."""
+    n_tiles = (n_blocks + 3) // 4
+    base, rem = divmod(n_blocks, n_tiles)
+    return [base + (1 if t < rem else 0) for t in range(n_tiles)]
+
+
+def _swizzle_image(mat):
+    """[rows, 64*KB] bf16 -> [KB, rows, 8, 8]: 16-byte chunk j of row r holds source chunk
+    j ^ (r % 8) (the canonical K-major SWIZZLE_128B layout tcgen05.mma reads)."""
+    rows, kp = mat.shape
+    kb = kp // 64
+    blk = mat.reshape(rows, kb, 8, 8).permute(1, 0, 2, 3)
+    r = torch.arange(rows, device=mat.device)[:, None]
+    j = torch.arange(8, device=mat.device)[None, :]
+    return blk[:, r, j ^ (r & 7), :].contiguous()
+
+
+def weight_image(w, bias, kb: int, tiles):
+    """(w_img, bias_pad) for W [n_out, k_in] and the N-tile plan ``tiles``."""
+    n_out, k_in = w.shape
+    ob = sum(tiles)
+    dev = w.device
+    wp = torch.zeros((ob * 64, kb * 64), dtype=torch.bfloat16, device=dev)
+    wp[:n_out, :k_in] = w.detach().to(torch.bfloat16)
+    parts, r0 = [], 0
+    for nb in tiles:
+        parts.append(_swizzle_image(wp[r0:r0 + nb * 64]).reshape(-1))
+        r0 += nb * 64
+    bp = torch.zeros(ob * 64, dtype=torch.float32, device=dev)
+    if bias is not None:
+        bp[:n_out] = bias.detach().float()
+    return torch.cat(parts).contiguous(), bp
+
+
+def packed(fcnn):
+    """Per-layer (w_img, bias, KB, kmma_last, tiles, n_out) cached on the module."""
+    layers = (fcnn.network[0], fcnn.network[2], fcnn.network[4])
+    key = tuple((l.weight._version, l.weight.data_ptr(), l.bias._version if l.bias is not None else -1)
+                for l in layers)
+    cache = getattr(fcnn, "_wide_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    out = []
+    kb = blocks(layers[0].in_features)
+    for l in layers:
+        n_out, k_in = l.weight.shape
+        tiles = plan_tiles(blocks(n_out))
+        w_img, b = weight_image(l.weight, l.bias, kb, tiles)
+        kmma_last = (k_in - 64 * (kb - 1) + 15) // 16
+        out.append(dict(w=w_img, b=b, KB=kb, kmma_last=kmma_last, tiles=tiles, tiles_c=i32_array(tiles),
+                        n_out=n_out))
+        kb = sum(tiles)
+    fcnn._wide_cache = (key, out)
+    return out
+
+
+def pack_input(x, size, dim, cols, kb):
+    """x[:, :, cols].flatten(1) (nf/flows.py:230) -> bf16 A image."""
+    dev = require_cuda(x)
+    x = f32c(x)
+    N = x.shape[0]
+    m_tiles = (N + ROWS - 1) // ROWS
+    img = torch.empty((m_tiles, kb, ROWS, 64), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        call("nfk_pack_a_img", ptr(x), ptr(img), N, size, dim, i32_array(cols), len(cols), kb, stream_ptr(dev))
+    return img
+
+
+def gemm(a_img, layer, M, act, out_f32):
+    dev = a_img.device
+    m_tiles = (M + ROWS - 1) // ROWS
+    ob = sum(layer["tiles"])
+    if out_f32:
+        out = torch.empty((M, layer["n_out"]), dtype=torch.float32, device=dev)
+        ldy = layer["n_out"]
+    else:
+        out = torch.empty((m_tiles, ob, ROWS, 64), dtype=torch.bfloat16, device=dev)
+        ldy = 0
+    with torch.cuda.device(dev):
+        tm = _ops.KERNEL_TIMER
+        ev = tm.start("gemm_ws", dev) if tm is not None else None
+        call("nfk_gemm_ws", ptr(a_img), ptr(layer["w"]), ptr(layer["b"]), ptr(out), M, layer["KB"],
+             layer["kmma_last"], layer["tiles_c"], len(layer["tiles"]), act, int(out_f32), layer["n_out"], ldy,
+             stream_ptr(dev))
+        if ev is not None:
+            tm.stop(ev, dev)
+    return out
+
+
+def mlp3(fcnn, x, size=None, dim=1, cols=(0,)):
+    """FCNN(x[:, :, cols].flatten(1)) -> fp32 [N, out_dim]; with the defaults x is the plain
+    [N, in_dim] conditioner input."""
+    l1, l2, l3 = packed(fcnn)
+    if size is None:
+        size = x.shape[1]
+    N = x.shape[0]
+    a0 = pack_input(x, size, dim, list(cols), l1["KB"])
+    h1 = gemm(a0, l1, N, 1, False)
+    h2 = gemm(h1, l2, N, 1, False)
+    return gemm(h2, l3, N, 0, True)
+
+
+def image_to_rows(img, n_rows, n_cols):
+    """Inverse of the image layout (tests): [m_tiles, KB, 128, 64] bf16 image -> [n_rows, n_cols]."""
+    m_tiles, kb, rows, _ = img.shape
+    r = torch.arange(rows, device=img.device)[:, None]
+    j = torch.arange(8, device=img.device)[None, :]
+    blk = img.reshape(m_tiles, kb, rows, 8, 8)
+    un = blk[:, :, r, j ^ (r & 7), :]                    # chunk j of the source sits at slot j ^ (r % 8)
+    return un.permute(0, 2, 1, 3, 4).reshape(m_tiles * rows, kb * 64)[:n_rows, :n_cols]

@@ -1,0 +1,394 @@
+// Wide conditioner path (hidden width > 128, e.g. the class default 800 of NSF_CL, reference
+// nf/flows.py:216 / FCNN nf/flows.py:20-35): a persistent, warp-specialised tcgen05 GEMM
+//     Y = act(A W^T + b)
+// whose operands never need a tensor map because every matrix on this path lives in HBM in the
+// *shared-memory image* the tensor core reads: 128-row x 64-column bf16 blocks (16 KB), K-major
+// SWIZZLE_128B (16-byte chunk j of row r holds source chunk j ^ (r % 8)).  One 1-D TMA bulk
+// copy (UBLKCP) moves a block; the epilogue writes the next layer's operand in the same image,
+// so activations go HBM -> smem -> tensor core with no layout work anywhere.
+//
+//   A image   [m_tiles][KB][128 rows][128 B]                     (activations, 128 rows per tile)
+//   W image   per N tile t (64*nb_t output columns): [KB][64*nb_t rows][128 B]
+//   out image [m_tiles][sum nb][128 rows][128 B]  (bf16, tanh)  or fp32 rows [M, ldy]
+//
+// CTA = 10 warps, one CTA per SM, persistent over (m_tile, n_tile) work items:
+//   warp 0      producer: waits empty[s], issues the two bulk copies of a K block into stage s
+//   warp 1      MMA issuer: waits full[s], 4 x tcgen05.mma (M=128, N=64*nb, K=16) per K block,
+//               tcgen05.commit -> empty[s]; after the last K block commit -> tmem_full[acc]
+//   warps 2..9  epilogue: wait tmem_full[acc], tcgen05.ld 32 columns at a time (lane quadrant =
+//               warp % 4, column half = (warp-2) / 4), bias + tanh.approx, pack to bf16, write the
+//               swizzled 16 KB output block in shared memory, one thread bulk-stores it.
+// The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile i runs
+// under the MMAs of tile i+1.  Four 48 KB operand stages + 32 KB of output staging = 224 KB.
+#include "tc05.cuh"
+
+namespace nfk {
+
+constexpr int WS_M = 128;
+constexpr int WS_STAGES = 4;
+constexpr int WS_EPI_WARPS = 8;
+constexpr int WS_THREADS = (2 + WS_EPI_WARPS) * 32;
+constexpr int WS_MAX_TILES = 8;
+constexpr uint32_t WS_BLK = 128 * 128;                 // one 128 x 64 bf16 block
+constexpr uint32_t WS_A_BYTES = WS_BLK;
+constexpr uint32_t WS_B_BYTES = 256 * 128;
+constexpr uint32_t WS_STAGE_BYTES = WS_A_BYTES + WS_B_BYTES;
+constexpr uint32_t WS_STG_BYTES = 2 * WS_BLK;          // output staging
+constexpr size_t WS_SMEM = (size_t)WS_STAGES * WS_STAGE_BYTES + WS_STG_BYTES + 16 * 8 + 1024;
+static_assert(WS_SMEM <= 227 * 1024, "gemm_ws exceeds the 227 KB shared-memory limit");
+
+struct WsArgs {
+  const unsigned char* a_img;
+  const unsigned char* w_img;
+  const float* bias;       // [64 * sum nb], zero padded
+  void* out;
+  long long m_tiles;
+  long long M;             // real rows (fp32 row output is bounds-checked against it)
+  long long ldy;           // fp32 row stride in floats
+  int KB;                  // K blocks of 64
+  int kmma_last;           // tcgen05.mma (K=16) count in the last K block, 1..4
+  int n_tiles;
+  int nb[WS_MAX_TILES];    // 64-column blocks per N tile (1..4)
+  int n_out;               // real output columns (fp32 row output)
+  int act;                 // 0 identity, 1 tanh
+};
+
+__device__ __forceinline__ bool ws_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+template <bool OUT_F32>
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(const __grid_constant__ WsArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  unsigned char* stg = sm + WS_STAGES * WS_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + WS_STG_BYTES);
+  uint64_t* full = bars;                    // [4] operands landed           (1 + tx)
+  uint64_t* empty = bars + WS_STAGES;       // [4] stage consumed            (1, tcgen05.commit)
+  uint64_t* tfull = bars + 2 * WS_STAGES;   // [2] accumulator complete      (1, tcgen05.commit)
+  uint64_t* tempty = tfull + 2;             // [2] accumulator drained       (8 epilogue warps)
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 32) {
+    for (int i = 0; i < WS_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], WS_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const long long first = blockIdx.x, stride = gridDim.x;
+
+  if (warp == 0) {
+    // ================================ producer ================================
+    uint32_t s = 0, ph = 0;
+    for (long long mt = first; mt < a.m_tiles; mt += stride) {
+      const unsigned char* ag = a.a_img + (size_t)mt * a.KB * WS_BLK;
+      const unsigned char* wg = a.w_img;
+      for (int t = 0; t < a.n_tiles; ++t) {
+        const uint32_t bb = (uint32_t)a.nb[t] * 64u * 128u;
+        for (int kb = 0; kb < a.KB; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          if (lane == 0) {
+            unsigned char* st = sm + s * WS_STAGE_BYTES;
+            mbar_expect_tx(&full[s], WS_A_BYTES + bb);
+            bulk_g2s(st, ag + (size_t)kb * WS_BLK, WS_A_BYTES, &full[s]);
+            bulk_g2s(st + WS_A_BYTES, wg + (size_t)kb * bb, bb, &full[s]);
+          }
+          __syncwarp();
+          if (++s == WS_STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        wg += (size_t)a.KB * bb;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    uint32_t s = 0, ph = 0, tl = 0;
+    for (long long mt = first; mt < a.m_tiles; mt += stride) {
+      for (int t = 0; t < a.n_tiles; ++t, ++tl) {
+        const uint32_t acc = tl & 1;
+        const uint32_t idesc = make_idesc_bf16(WS_M, a.nb[t] * 64);
+        mbar_wait(&tempty[acc], ((tl >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + acc * 256;
+        for (int kb = 0; kb < a.KB; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          if (ws_elect_one()) {
+            const uint32_t aa = smem_u32(sm + s * WS_STAGE_BYTES), ba = aa + WS_A_BYTES;
+            const int nm = (kb == a.KB - 1) ? a.kmma_last : 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < nm)
+                umma_bf16(d, make_desc_sw128(aa + k * 32), make_desc_sw128(ba + k * 32), idesc,
+                          (kb | k) ? 1u : 0u);
+            umma_commit(&empty[s]);
+            if (kb == a.KB - 1) umma_commit(&tfull[acc]);
+          }
+          __syncwarp();
+          if (++s == WS_STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int ew = warp - 2;
+    const int q = warp & 3;              // TMEM lane quadrant this warp may read
+    const int h = ew >> 2;               // 32-column half of each 64-column block
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const bool issuer = (ew == 0 && lane == 0);
+    uint32_t tl = 0, bc = 0;
+    int ob_total = 0;
+    for (int t = 0; t < a.n_tiles; ++t) ob_total += a.nb[t];
+    for (long long mt = first; mt < a.m_tiles; mt += stride) {
+      int ob0 = 0;
+      for (int t = 0; t < a.n_tiles; ++t, ++tl) {
+        const uint32_t acc = tl & 1;
+        const int nb = a.nb[t];
+        mbar_wait(&tfull[acc], (tl >> 1) & 1);
+        tc_fence_after();
+        for (int b = 0; b < nb; ++b, ++bc) {
+          uint32_t v[32];
+          tmem_ld32(tmem + acc * 256 + lane_sel + (uint32_t)(b * 64 + h * 32), v);
+          tmem_ld_wait();
+          if (b == nb - 1) {
+            // every column of this accumulator is in registers: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          const int colb = (ob0 + b) * 64 + h * 32;        // first padded output column of v[]
+          const float4* bp = reinterpret_cast<const float4*>(a.bias + colb);
+          if (!OUT_F32) {
+            unsigned char* sb = stg + (bc & 1) * WS_BLK;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b0 = __ldg(bp + 2 * j), b1 = __ldg(bp + 2 * j + 1);
+              float f[8];
+              f[0] = __uint_as_float(v[8 * j + 0]) + b0.x;
+              f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
+              f[2] = __uint_as_float(v[8 * j + 2]) + b0.z;
+              f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
+              f[4] = __uint_as_float(v[8 * j + 4]) + b1.x;
+              f[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
+              f[6] = __uint_as_float(v[8 * j + 6]) + b1.z;
+              f[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+              if (a.act == 1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = tanh_approx(f[e]);
+              }
+              uint4 u;
+              u.x = pack_bf16x2(f[0], f[1]);
+              u.y = pack_bf16x2(f[2], f[3]);
+              u.z = pack_bf16x2(f[4], f[5]);
+              u.w = pack_bf16x2(f[6], f[7]);
+              const int ch = h * 4 + j;
+              *reinterpret_cast<uint4*>(sb + row * 128 + ((ch ^ (row & 7)) << 4)) = u;
+            }
+            fence_proxy_async();
+            // the store that used the *other* buffer must have finished reading shared memory
+            // before anyone passes this barrier and starts the next block in it
+            if (issuer) bulk_wait_read<0>();
+            asm volatile("bar.sync 1, %0;" ::"n"(WS_EPI_WARPS * 32) : "memory");
+            if (issuer) {
+              unsigned char* og = reinterpret_cast<unsigned char*>(a.out) +
+                                  ((size_t)mt * ob_total + (ob0 + b)) * WS_BLK;
+              bulk_s2g(og, sb, WS_BLK);
+              bulk_commit();
+            }
+          } else {
+            // fp32 rows: stage the 128 x 64 block (256 B per row, 16-byte chunk c of row r at
+            // c ^ (r % 16)), then every warp writes 16 rows as coalesced 128-byte segments
+            float* sf = reinterpret_cast<float*>(stg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(bp + j);
+              float4 o;
+              o.x = __uint_as_float(v[4 * j + 0]) + bv.x;
+              o.y = __uint_as_float(v[4 * j + 1]) + bv.y;
+              o.z = __uint_as_float(v[4 * j + 2]) + bv.z;
+              o.w = __uint_as_float(v[4 * j + 3]) + bv.w;
+              if (a.act == 1) {
+                o.x = tanh_approx(o.x);
+                o.y = tanh_approx(o.y);
+                o.z = tanh_approx(o.z);
+                o.w = tanh_approx(o.w);
+              }
+              const int ch = h * 8 + j;
+              *reinterpret_cast<float4*>(sf + row * 64 + ((ch ^ (row & 15)) << 2)) = o;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(WS_EPI_WARPS * 32) : "memory");
+            const int col0 = (ob0 + b) * 64;
+            float* og = reinterpret_cast<float*>(a.out);
+#pragma unroll 4
+            for (int rr = 0; rr < 16; ++rr) {
+              const int r = ew * 16 + rr;
+              const long long gr = mt * WS_M + r;
+              if (gr < a.M) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const int c = hh * 32 + lane;
+                  if (col0 + c < a.n_out)
+                    og[gr * a.ldy + col0 + c] = sf[r * 64 + (((c >> 2) ^ (r & 15)) << 2) + (c & 3)];
+                }
+              }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(WS_EPI_WARPS * 32) : "memory");
+          }
+        }
+        ob0 += nb;
+      }
+    }
+    if (!OUT_F32 && issuer) bulk_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// fp32 x[:, :, cols] gather (nf/flows.py:230) -> bf16 A image [m_tiles][KB][128][64], zero padded.
+// One thread per 16-byte chunk of the image: coalesced 16-byte stores.
+__global__ void __launch_bounds__(256)
+pack_a_img_kernel(const float* __restrict__ x, unsigned char* __restrict__ img, long long N, long long m_tiles,
+                  int size, int dim, int n_cols, int c0, int c1, int c2, int c3, int KB) {
+  const int per_row = size * n_cols;
+  const long long total = m_tiles * KB * 128 * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int slot = (int)(i & 7);
+    const int r = (int)((i >> 3) & 127);
+    const long long blk = i >> 10;
+    const int kb = (int)(blk % KB);
+    const long long mt = blk / KB;
+    const int ch = slot ^ (r & 7);
+    const long long row = mt * 128 + r;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (row < N) {
+      const float* xr = x + row * (long long)(size * dim);
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = kb * 64 + ch * 8 + e;
+        float v = 0.f;
+        if (k < per_row) {
+          const int s = k / n_cols, ci = k - s * n_cols;
+          const int col = ci == 0 ? c0 : ci == 1 ? c1 : ci == 2 ? c2 : c3;
+          v = xr[s * dim + col];
+        }
+        f[e] = v;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+    }
+    *reinterpret_cast<uint4*>(img + i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+}  // namespace nfk
+
+using namespace nfk;
+
+extern "C" {
+
+int nfk_gemm_ws_rows_per_tile(void) { return WS_M; }
+
+int nfk_pack_a_img(const float* x, void* img, int64_t N, int size, int dim, const int32_t* cols, int n_cols,
+                   int KB, void* stream) {
+  NFK_REQUIRE(N >= 0 && size > 0 && dim > 0 && KB > 0, "pack_a_img: bad shape");
+  NFK_REQUIRE(cols && n_cols >= 1 && n_cols <= 4, "pack_a_img: 1..4 columns supported");
+  NFK_REQUIRE((long long)size * n_cols <= (long long)KB * 64, "pack_a_img: %d columns do not fit %d K blocks",
+              size * n_cols, KB);
+  int c[4] = {0, 0, 0, 0};
+  for (int i = 0; i < n_cols; ++i) {
+    NFK_REQUIRE(cols[i] >= 0 && cols[i] < dim, "pack_a_img: column %d outside [0,%d)", cols[i], dim);
+    c[i] = cols[i];
+  }
+  if (N == 0) return NFK_OK;
+  NFK_REQUIRE(x && img, "pack_a_img: null device pointer");
+  NFK_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0, "pack_a_img: image must be 16-byte aligned");
+  const long long m_tiles = (N + WS_M - 1) / WS_M;
+  const long long total = m_tiles * KB * 128 * 8;
+  long long grid = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  pack_a_img_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      x, reinterpret_cast<unsigned char*>(img), N, m_tiles, size, dim, n_cols, c[0], c[1], c[2], c[3], KB);
+  count_launch();
+  return check_launch("pack_a_img");
+}
+
+int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* out, int64_t M, int KB,
+                int kmma_last, const int32_t* tile_blocks, int n_tiles, int act, int out_f32, int n_out,
+                int64_t ldy, void* stream) {
+  NFK_REQUIRE(M >= 0 && KB > 0, "gemm_ws: bad shape M=%lld KB=%d", (long long)M, KB);
+  NFK_REQUIRE(kmma_last >= 1 && kmma_last <= 4, "gemm_ws: kmma_last must be 1..4");
+  NFK_REQUIRE(tile_blocks && n_tiles >= 1 && n_tiles <= WS_MAX_TILES, "gemm_ws: 1..%d N tiles", WS_MAX_TILES);
+  NFK_REQUIRE(act == 0 || act == 1, "gemm_ws: act must be 0 (identity) or 1 (tanh)");
+  WsArgs a{};
+  int ob = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    NFK_REQUIRE(tile_blocks[t] >= 1 && tile_blocks[t] <= 4, "gemm_ws: N tile of %d blocks (1..4 allowed)",
+                tile_blocks[t]);
+    a.nb[t] = tile_blocks[t];
+    ob += tile_blocks[t];
+  }
+  if (out_f32) NFK_REQUIRE(n_out >= 1 && n_out <= ob * 64 && ldy >= n_out, "gemm_ws: bad fp32 output shape");
+  if (M == 0) return NFK_OK;
+  NFK_REQUIRE(a_img && w_img && bias && out, "gemm_ws: null device pointer");
+  NFK_REQUIRE(((reinterpret_cast<uintptr_t>(a_img) | reinterpret_cast<uintptr_t>(w_img) |
+                reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              "gemm_ws: pointers must be 16-byte aligned");
+  a.a_img = reinterpret_cast<const unsigned char*>(a_img);
+  a.w_img = reinterpret_cast<const unsigned char*>(w_img);
+  a.bias = bias;
+  a.out = out;
+  a.m_tiles = (M + WS_M - 1) / WS_M;
+  a.M = M;
+  a.ldy = ldy;
+  a.KB = KB;
+  a.kmma_last = kmma_last;
+  a.n_tiles = n_tiles;
+  a.n_out = n_out;
+  a.act = act;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long cap = sm_count();
+  const unsigned grid = (unsigned)(a.m_tiles < cap ? a.m_tiles : cap);
+  cudaError_t e;
+  if (out_f32) {
+    e = cudaFuncSetAttribute(gemm_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
+    if (e == cudaSuccess) gemm_ws_kernel<true><<<grid, WS_THREADS, WS_SMEM, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(gemm_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
+    if (e == cudaSuccess) gemm_ws_kernel<false><<<grid, WS_THREADS, WS_SMEM, st>>>(a);
+  }
+  if (e != cudaSuccess) {
+    set_error("gemm_ws: cannot set %zu B dynamic shared memory: %s", WS_SMEM, cudaGetErrorString(e));
+    return NFK_ECUDA;
+  }
+  count_launch();
+  return check_launch("gemm_ws");
+}
+
+}  // extern "C"

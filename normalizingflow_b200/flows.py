@@ -129,6 +129,14 @@ class NSF_CL(nn.Module):
                 # conditioner GEMMs + spline in ONE kernel; the parameter tensor never reaches HBM
                 return _fused.run(self, x, inverse, logdet)
         n_t = self.size * (self.dim - len(self._mask))
+        if no_grad and x.dtype == torch.float32:
+            from . import _wide
+            if _wide.usable(self.psi):
+                # wide conditioner: gather + 3 persistent tcgen05 GEMMs over image-layout operands
+                params = _wide.mlp3(self.psi, x, self.size, self.dim, self._mask).reshape(-1, n_t, 3 * self.K - 1)
+                out, ld, _ = _ops.rqs_coupling(x, params, self.size, self.dim, self._mask, self.K, float(self.B),
+                                               inverse, self.arith, logdet=logdet)
+                return out, ld
         params = self.psi(self._lower(x)).reshape(-1, n_t, 3 * self.K - 1)   # flows.py:231
         if torch.is_grad_enabled() and (x.requires_grad or params.requires_grad):
             out, ld = _ops.RqsCouplingFn.apply(x, params, self.size, self.dim, tuple(self._mask), self.K,

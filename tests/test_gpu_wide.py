@@ -1,0 +1,94 @@
+"""GPU parity tests of the wide conditioner path (csrc/gemm_ws.cu: persistent warp-specialised
+tcgen05 GEMM over image-layout operands) against fp64 matmuls of the same bf16-rounded operands,
+and of a whole NSF_CL layer with the class-default hidden width 800 (nf/flows.py:216) against
+the oracle."""
+import pytest
+import torch
+
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _wide():
+    from normalizingflow_b200 import _wide
+    return _wide
+
+
+def _layer(w, b, kb):
+    W = _wide()
+    n_out, k_in = w.shape
+    tiles = W.plan_tiles(W.blocks(n_out))
+    w_img, bp = W.weight_image(w.cuda(), b.cuda(), kb, tiles)
+    return dict(w=w_img, b=bp, KB=kb, kmma_last=(k_in - 64 * (kb - 1) + 15) // 16, tiles=tiles, n_out=n_out)
+
+
+@pytest.mark.parametrize("M,K,N,act,f32", [(128, 64, 64, 1, False), (1, 32, 800, 1, False), (300, 800, 800, 1, False),
+                                           (1000, 800, 736, 0, True), (129, 76, 874, 0, True),
+                                           (20000, 800, 1748, 0, True), (40000, 832, 832, 1, False),
+                                           (257, 16, 100, 0, True)])
+def test_gemm_ws_matches_fp64(M, K, N, act, f32):
+    W = _wide()
+    from normalizingflow_b200._lib import i32_array
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    kb = W.blocks(K)
+    a_img = W.pack_input(x.cuda(), K, 1, [0], kb)
+    # the packed image round-trips to the bf16-rounded input
+    back = W.image_to_rows(a_img, M, K).float().cpu()
+    assert torch.equal(back, x.to(torch.bfloat16).float())
+    lay = _layer(w, b, kb)
+    lay["tiles_c"] = i32_array(lay["tiles"])
+    y = W.gemm(a_img, lay, M, act, f32)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.linear(x.to(torch.bfloat16).double(), w.to(torch.bfloat16).double(), b.double())
+    if act:
+        ref = torch.tanh(ref)
+    if f32:
+        got = y.float().cpu()
+    else:
+        got = W.image_to_rows(y, M, N).float().cpu()
+        # padding columns of the image are exact zeros (they are the next layer's K padding)
+        full = W.image_to_rows(y, M, sum(lay["tiles"]) * 64).float().cpu()
+        assert torch.count_nonzero(full[:, N:]) == 0
+    tol = 2e-3 if (f32 and not act) else 1e-2
+    assert rel_err(got, ref) <= tol, rel_err(got, ref)
+
+
+def test_wide_mlp3_matches_bf16_chain():
+    """FCNN 32 -> 800 -> 800 -> 736 through the three wide GEMMs vs an fp64 evaluation that rounds
+    the operands to bf16 at the same places."""
+    W = _wide()
+    from normalizingflow_b200 import flows
+    torch.manual_seed(0)
+    net = flows.FCNN(32, 736, 800, precision="bf16").cuda()
+    x = torch.randn(3000, 64, generator=torch.Generator().manual_seed(5))
+    y = W.mlp3(net, x.cuda(), 32, 2, [1]).cpu()
+    bf = lambda t: t.to(torch.bfloat16).double()
+    l0, l2, l4 = net.network[0], net.network[2], net.network[4]
+    xc = bf(x.reshape(-1, 32, 2)[:, :, 1])
+    h1 = bf(torch.tanh(xc @ bf(l0.weight.cpu()).T + l0.bias.double().cpu()).float())
+    h2 = bf(torch.tanh(h1 @ bf(l2.weight.cpu()).T + l2.bias.double().cpu()).float())
+    ref = h2 @ bf(l4.weight.cpu()).T + l4.bias.double().cpu()
+    assert rel_err(y, ref) <= 1e-2, rel_err(y, ref)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_nsf_layer_h800_vs_oracle(inverse):
+    """Whole NSF_CL layer at the class-default hidden width: wide bf16 conditioner + spline kernel
+    vs the fp32 oracle (1e-2 class of the bf16 conditioner path)."""
+    from normalizingflow_b200 import flows
+    from oracle import nf_oracle as O
+    torch.manual_seed(1)
+    lay = flows.NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=800, mask=[1])
+    sd = {k: v.detach().clone() for k, v in lay.state_dict().items()}
+    lay.psi.precision = "bf16"
+    lay = lay.cuda()
+    x = torch.randn(2500, 64, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        out, ld = (lay.inverse if inverse else lay.forward)(x.cuda())
+    ro, rld = O.nsf_cl(x, sd, 32, 2, [1], 8, 3.0, inverse)[:2]
+    assert rel_err(out.cpu(), ro) <= 1e-2
+    assert rel_err(ld.cpu(), rld) <= 2e-2
