@@ -307,16 +307,38 @@ def run_native(a):
         # fused kernel that keeps the spline parameters on chip can read above 1.0.
         kname, (n_l, k_ms) = max(ksum.items(), key=lambda kv: kv[1][1]) if ksum else ("none", (0, 0.0))
         avg_ms = k_ms / max(1, n_l)
-        achieved = ROW_BYTES_PER_LAYER * N / (avg_ms * 1e-3) / 1e9 if n_l else None
-        actual_row_bytes = {"nsf_pairs_fused": 64 * 4 * 2 + 8, "rqs_coupling": ROW_BYTES_PER_LAYER}.get(kname)
-        roofline = {"bound": "hbm", "kernel": {"nsf_pairs_fused": "nsf_pairs_fused_kernel (conditioner GEMMs + RQS "
-                                               "epilogue, one launch per layer pass)",
-                                               "rqs_coupling": "rqs_coupling_pairs"}.get(kname, kname),
-                    "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": ROW_BYTES_PER_LAYER * N,
-                    "hbm_bytes_per_launch_by_design": actual_row_bytes * N if actual_row_bytes else None,
-                    "avg_launch_ms": avg_ms, "launches_timed": n_l, "share_of_step": (k_ms / ms) if ms else None}
+        H = a.hidden
+        labels = {"nsf_pairs_fused": "nsf_pairs_fused_kernel (conditioner GEMMs + RQS epilogue, one launch per layer pass)",
+                  "rqs_coupling": "rqs_coupling_pairs",
+                  "gemm_ws_l2": "gemm_ws_kernel<bf16 image> (hidden x hidden conditioner GEMM, persistent tcgen05)",
+                  "gemm_ws_l3": "gemm_ws_kernel<fp32 rows> (last conditioner GEMM)",
+                  "gemm_ws_rqs": "gemm_ws_kernel<RQS epilogue> (last conditioner GEMM + spline transform)"}
+        tensor_flops = {"gemm_ws_l1": 2.0 * N * SIZE * H, "gemm_ws_l2": 2.0 * N * H * H,
+                        "gemm_ws_l3": 2.0 * N * H * 23 * SIZE, "gemm_ws_rqs": 2.0 * N * H * 23 * SIZE}
+        if kname in tensor_flops:
+            # wide conditioner (H > 128): the step is bounded by the tensor pipe (SURVEY.md 8(d):
+            # 2*(32*H + H^2 + H*736) flop per row per layer pass); peak = sustained bf16 (kernel timed
+            # inside a long step)
+            pj = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+            tpeak = float(pj.get("bf16_tflops_sustained", 0) or 0)
+            tsrc = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+            if not tpeak:
+                tpeak, tsrc = 1500.0, "fallback (B200_PROFILING.md)"
+            achieved = tensor_flops[kname] / (avg_ms * 1e-3) / 1e12 if n_l else None
+            roofline = {"bound": "tensor", "kernel": labels.get(kname, kname), "achieved": achieved, "peak": tpeak,
+                        "unit": "TFLOP/s", "frac": (achieved / tpeak) if achieved else None, "traffic": None,
+                        "peak_source": tsrc, "algorithmic_flops_per_launch": tensor_flops[kname],
+                        "avg_launch_ms": avg_ms, "launches_timed": n_l, "share_of_step": (k_ms / ms) if ms else None,
+                        "kernels_ms_per_step": {k: v[1] / a.steps for k, v in ksum.items()}}
+        else:
+            achieved = ROW_BYTES_PER_LAYER * N / (avg_ms * 1e-3) / 1e9 if n_l else None
+            actual_row_bytes = {"nsf_pairs_fused": 64 * 4 * 2 + 8, "rqs_coupling": ROW_BYTES_PER_LAYER}.get(kname)
+            roofline = {"bound": "hbm", "kernel": labels.get(kname, kname),
+                        "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": ROW_BYTES_PER_LAYER * N,
+                        "hbm_bytes_per_launch_by_design": actual_row_bytes * N if actual_row_bytes else None,
+                        "avg_launch_ms": avg_ms, "launches_timed": n_l, "share_of_step": (k_ms / ms) if ms else None}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
@@ -328,7 +350,8 @@ def run_native(a):
                 "vs_baseline": None, "dtype": "f32" if cond == "fp32" else "f32 transforms / bf16 conditioner GEMMs",
                 "data": "synthetic",
                 "config": {"workload": workload_name(a), "hidden": a.hidden, "arith": a.arith, "conditioner": cond,
-                           "fused_layer_kernel": bool(not a.no_fused and cond == "bf16"), "global_batch": world * N, "parallelism": f"batch-sharded x{world}",
+                           "fused_layer_kernel": bool(not a.no_fused and cond == "bf16" and a.hidden <= 128),
+                           "spline_epilogue_on_last_gemm": bool(not a.no_fused and cond == "bf16" and a.hidden > 128), "global_batch": world * N, "parallelism": f"batch-sharded x{world}",
                            "l2": "inputs larger than L2 (x 268 MB, spline params 3.1 GB per layer)"},
                 "roofline": roofline, "clocks": clk, "gpu_launches": launches, "e2e": e2e}
         if not a.no_cpu_baseline and world == 1:       # reported at N=1 only

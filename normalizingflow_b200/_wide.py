@@ -97,7 +97,7 @@ def pack_input(x, size, dim, cols, kb):
     return img
 
 
-def gemm(a_img, layer, M, act, out_f32):
+def gemm(a_img, layer, M, act, out_f32, tag="gemm_ws"):
     dev = a_img.device
     m_tiles = (M + ROWS - 1) // ROWS
     ob = sum(layer["tiles"])
@@ -109,7 +109,7 @@ def gemm(a_img, layer, M, act, out_f32):
         ldy = 0
     with torch.cuda.device(dev):
         tm = _ops.KERNEL_TIMER
-        ev = tm.start("gemm_ws", dev) if tm is not None else None
+        ev = tm.start(tag, dev) if tm is not None else None
         call("nfk_gemm_ws", ptr(a_img), ptr(layer["w"]), ptr(layer["b"]), ptr(out), M, layer["KB"],
              layer["kmma_last"], layer["tiles_c"], len(layer["tiles"]), act, int(out_f32), layer["n_out"], ldy,
              stream_ptr(dev))
@@ -126,9 +126,61 @@ def mlp3(fcnn, x, size=None, dim=1, cols=(0,)):
         size = x.shape[1]
     N = x.shape[0]
     a0 = pack_input(x, size, dim, list(cols), l1["KB"])
-    h1 = gemm(a0, l1, N, 1, False)
-    h2 = gemm(h1, l2, N, 1, False)
-    return gemm(h2, l3, N, 0, True)
+    h1 = gemm(a0, l1, N, 1, False, "gemm_ws_l1")
+    h2 = gemm(h1, l2, N, 1, False, "gemm_ws_l2")
+    return gemm(h2, l3, N, 0, True, "gemm_ws_l3")
+
+
+def rqs_eligible(layer) -> bool:
+    """Layers whose last GEMM can carry the spline transform as its epilogue (nfk_gemm_ws_rqs)."""
+    return (_lib.have("nfk_gemm_ws_rqs") and layer.size == 32 and layer.dim == 2 and len(layer._mask) == 1
+            and layer.K == 8 and usable(layer.psi) and layer.psi.network[0].in_features == 32)
+
+
+def packed_rqs(layer):
+    """(l1, l2, l3) of the layer's conditioner with l3 in the per-feature padded (23 -> 24 rows)
+    layout of the fused spline epilogue."""
+    fcnn = layer.psi
+    l1, l2, _ = packed(fcnn)
+    last = fcnn.network[4]
+    key = (last.weight._version, last.weight.data_ptr(), last.bias._version)
+    cache = getattr(layer, "_wide_rqs_cache", None)
+    if cache is None or cache[0] != key:
+        H = last.in_features
+        dev = last.weight.device
+        w3 = torch.zeros((32, 24, H), dtype=torch.float32, device=dev)
+        w3[:, :23] = last.weight.detach().float().reshape(32, 23, H)
+        b3 = torch.zeros((32, 24), dtype=torch.float32, device=dev)
+        b3[:, :23] = last.bias.detach().float().reshape(32, 23)
+        kb = sum(l2["tiles"])
+        w_img, bp = weight_image(w3.reshape(768, H), b3.reshape(-1), kb, [3, 3, 3, 3])
+        l3 = dict(w=w_img, b=bp, KB=kb, kmma_last=(H - 64 * (kb - 1) + 15) // 16)
+        layer._wide_rqs_cache = cache = (key, l3)
+    return l1, l2, cache[1]
+
+
+def run_layer(layer, x, inverse, logdet=None):
+    """(out, logdet) of one eligible NSF_CL layer: pack + 2 GEMMs + GEMM-with-spline-epilogue."""
+    dev = require_cuda(x, logdet)
+    x = f32c(x)
+    N = x.shape[0]
+    l1, l2, l3 = packed_rqs(layer)
+    a0 = pack_input(x, 32, 2, layer._mask, l1["KB"])
+    h1 = gemm(a0, l1, N, 1, False, "gemm_ws_l1")
+    h2 = gemm(h1, l2, N, 1, False, "gemm_ws_l2")
+    out = torch.empty((N, 64), dtype=torch.float32, device=dev)
+    accumulate = logdet is not None
+    if not accumulate:
+        logdet = torch.empty((N,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        tm = _ops.KERNEL_TIMER
+        ev = tm.start("gemm_ws_rqs", dev) if tm is not None else None
+        call("nfk_gemm_ws_rqs", ptr(h2), ptr(l3["w"]), ptr(l3["b"]), ptr(x), ptr(out), ptr(logdet), N, l3["KB"],
+             l3["kmma_last"], layer._mask[0], float(layer.B), int(bool(inverse)), int(accumulate),
+             _ops._arith(layer.arith), stream_ptr(dev))
+        if ev is not None:
+            tm.stop(ev, dev)
+    return out, logdet
 
 
 def image_to_rows(img, n_rows, n_cols):

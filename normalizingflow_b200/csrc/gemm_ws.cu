@@ -20,22 +20,46 @@
 //               swizzled 16 KB output block in shared memory, one thread bulk-stores it.
 // The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of tile i runs
 // under the MMAs of tile i+1.  Four 48 KB operand stages + 32 KB of output staging = 224 KB.
+//
+// EPI_RQS (size = 32, dim = 2, K = 8 layers): the last GEMM's epilogue IS the spline transform
+// (reference nf/flows.py:232-239 + nf/utils.py:20-152).  W3's 23 rows per feature are padded to
+// 24, an N tile holds 8 features (192 accumulator columns), 16 epilogue warps: thread
+// (row, feature) pulls its 24 raw parameters out of TMEM, evaluates bin search + spline +
+// log|det| in registers (rqs_math.cuh) and writes the (conditioning, transformed) output pair;
+// the [N, 32, 23] parameter tensor never exists in HBM.
+#include "rqs_math.cuh"
 #include "tc05.cuh"
 
 namespace nfk {
 
+enum { EPI_BF16_IMG = 0, EPI_F32_ROWS = 1, EPI_RQS = 2 };
+
 constexpr int WS_M = 128;
-constexpr int WS_STAGES = 4;
-constexpr int WS_EPI_WARPS = 8;
-constexpr int WS_THREADS = (2 + WS_EPI_WARPS) * 32;
 constexpr int WS_MAX_TILES = 8;
 constexpr uint32_t WS_BLK = 128 * 128;                 // one 128 x 64 bf16 block
 constexpr uint32_t WS_A_BYTES = WS_BLK;
-constexpr uint32_t WS_B_BYTES = 256 * 128;
-constexpr uint32_t WS_STAGE_BYTES = WS_A_BYTES + WS_B_BYTES;
-constexpr uint32_t WS_STG_BYTES = 2 * WS_BLK;          // output staging
-constexpr size_t WS_SMEM = (size_t)WS_STAGES * WS_STAGE_BYTES + WS_STG_BYTES + 16 * 8 + 1024;
-static_assert(WS_SMEM <= 227 * 1024, "gemm_ws exceeds the 227 KB shared-memory limit");
+constexpr int WS_NF = 32, WS_PC = 24, WS_TF = 8;       // EPI_RQS: features, columns per feature, features per tile
+
+template <int EPI>
+struct WsCfg {                                         // plain GEMM epilogues
+  static constexpr int STAGES = 4;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr uint32_t B_BYTES = 256 * 128;
+  static constexpr uint32_t STG_BYTES = 2 * WS_BLK;    // output staging
+};
+template <>
+struct WsCfg<EPI_RQS> {
+  static constexpr int STAGES = 5;
+  static constexpr int EPI_WARPS = 16;
+  static constexpr uint32_t B_BYTES = WS_TF * WS_PC * 128;                       // 192 rows
+  static constexpr uint32_t STG_BYTES = WS_NF * WS_PC * 4 + 2 * WS_M * 4 * 4;    // b3 + log-det partials
+};
+template <int EPI>
+constexpr size_t ws_smem() {
+  return (size_t)WsCfg<EPI>::STAGES * (WS_A_BYTES + WsCfg<EPI>::B_BYTES) + WsCfg<EPI>::STG_BYTES + 16 * 8 + 1024;
+}
+static_assert(ws_smem<EPI_BF16_IMG>() <= 227 * 1024 && ws_smem<EPI_RQS>() <= 227 * 1024,
+              "gemm_ws exceeds the 227 KB shared-memory limit");
 
 struct WsArgs {
   const unsigned char* a_img;
@@ -51,6 +75,12 @@ struct WsArgs {
   int nb[WS_MAX_TILES];    // 64-column blocks per N tile (1..4)
   int n_out;               // real output columns (fp32 row output)
   int act;                 // 0 identity, 1 tanh
+  // EPI_RQS only
+  const float* x;          // [M, 64]
+  float* logdet;           // [M]
+  int cond_first;          // 1: conditioning column is column 0 of each pair (mask = [0])
+  int accumulate;
+  RqsConsts c;
 };
 
 __device__ __forceinline__ bool ws_elect_one() {
@@ -63,16 +93,22 @@ __device__ __forceinline__ bool ws_elect_one() {
   return pred != 0;
 }
 
-template <bool OUT_F32>
-__global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(const __grid_constant__ WsArgs a) {
+template <int EPI, int MODE, bool INVERSE>
+__global__ void __launch_bounds__((2 + WsCfg<EPI>::EPI_WARPS) * 32, 1)
+gemm_ws_kernel(const __grid_constant__ WsArgs a) {
+  constexpr int WS_STAGES = WsCfg<EPI>::STAGES;
+  constexpr int WS_EPI_WARPS = WsCfg<EPI>::EPI_WARPS;
+  constexpr uint32_t WS_STAGE_BYTES = WS_A_BYTES + WsCfg<EPI>::B_BYTES;
+  constexpr uint32_t WS_STG_BYTES = WsCfg<EPI>::STG_BYTES;
+  constexpr bool OUT_F32 = (EPI == EPI_F32_ROWS);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   unsigned char* stg = sm + WS_STAGES * WS_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + WS_STG_BYTES);
-  uint64_t* full = bars;                    // [4] operands landed           (1 + tx)
-  uint64_t* empty = bars + WS_STAGES;       // [4] stage consumed            (1, tcgen05.commit)
+  uint64_t* full = bars;                    // [STAGES] operands landed      (1 + tx)
+  uint64_t* empty = bars + WS_STAGES;       // [STAGES] stage consumed       (1, tcgen05.commit)
   uint64_t* tfull = bars + 2 * WS_STAGES;   // [2] accumulator complete      (1, tcgen05.commit)
-  uint64_t* tempty = tfull + 2;             // [2] accumulator drained       (8 epilogue warps)
+  uint64_t* tempty = tfull + 2;             // [2] accumulator drained       (epilogue warps)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -149,6 +185,66 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(const __grid_con
             ph ^= 1;
           }
         }
+      }
+    }
+  } else if constexpr (EPI == EPI_RQS) {
+    // ===================== epilogue: spline transform out of TMEM =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;              // TMEM lane quadrant this warp may read
+    const int slice = ew >> 2;           // features slice and slice + 4 of every 8-feature tile
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    float* sB3 = reinterpret_cast<float*>(stg);
+    float* sLd = sB3 + WS_NF * WS_PC;                    // [2][128][4]
+    for (int i = tid - 64; i < WS_NF * WS_PC; i += WS_EPI_WARPS * 32) sB3[i] = a.bias[i];
+    asm volatile("bar.sync 5, %0;" ::"n"(WS_EPI_WARPS * 32) : "memory");
+    uint32_t tl = 0, it = 0;
+    for (long long mt = first; mt < a.m_tiles; mt += stride, ++it) {
+      const long long grow = mt * WS_M + row;
+      const bool live = grow < a.M;
+      const float* xr = a.x + grow * 64;
+      float* orow = reinterpret_cast<float*>(a.out) + grow * 64;
+      float ld_old = 0.f;
+      if (slice == 0 && live && a.accumulate) ld_old = __ldg(a.logdet + grow);
+      float lad_acc = 0.f;
+      for (int t = 0; t < WS_NF / WS_TF; ++t, ++tl) {
+        const uint32_t acc = tl & 1;
+        float2 xin[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          xin[e] = live ? __ldg(reinterpret_cast<const float2*>(xr + 2 * (t * WS_TF + slice + 4 * e)))
+                        : make_float2(0.f, 0.f);
+        mbar_wait(&tfull[acc], (tl >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int f = t * WS_TF + slice + 4 * e;
+          uint32_t v[24];
+          const uint32_t ta = tmem + acc * 256 + lane_sel + (uint32_t)((slice + 4 * e) * WS_PC);
+          tmem_ld16(ta, v);
+          tmem_ld8(ta + 16, v + 16);
+          tmem_ld_wait();
+          if (e == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);      // the accumulator may be overwritten
+          }
+          const float2 xc = xin[e];
+          const RqsOut o = rqs_element<MODE, 8, INVERSE, true>(RegParams{v, sB3 + f * WS_PC},
+                                                                a.cond_first ? xc.y : xc.x, a.c);
+          if (live)                                          // (conditioning, transformed): quirk Q5
+            *reinterpret_cast<float2*>(orow + 2 * f) = make_float2(a.cond_first ? xc.x : xc.y, o.y);
+          lad_acc += o.lad;
+        }
+      }
+      // row log-det = sum over the 32 features (flows.py:238): 4 partial sums per row
+      float* sl = sLd + (it & 1) * (WS_M * 4);
+      sl[row * 4 + slice] = lad_acc;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+      if (slice == 0 && live) {
+        const float4 p = *reinterpret_cast<const float4*>(sl + row * 4);
+        const float tsum = (p.x + p.y) + (p.z + p.w);
+        a.logdet[grow] = a.accumulate ? ld_old + tsum : tsum;
       }
     }
   } else {
@@ -306,6 +402,24 @@ pack_a_img_kernel(const float* __restrict__ x, unsigned char* __restrict__ img, 
   }
 }
 
+RqsConsts make_rqs_consts(int K, float B);   // rqs_coupling.cu
+
+template <int EPI, int MODE, bool INVERSE>
+static int launch_ws(const WsArgs& a, cudaStream_t st) {
+  auto kern = gemm_ws_kernel<EPI, MODE, INVERSE>;
+  constexpr size_t smem = ws_smem<EPI>();
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("gemm_ws: cannot set %zu B dynamic shared memory: %s", smem, cudaGetErrorString(e));
+    return NFK_ECUDA;
+  }
+  const long long cap = sm_count();
+  const unsigned grid = (unsigned)(a.m_tiles < cap ? a.m_tiles : cap);
+  kern<<<grid, (2 + WsCfg<EPI>::EPI_WARPS) * 32, smem, st>>>(a);
+  count_launch();
+  return check_launch("gemm_ws");
+}
+
 }  // namespace nfk
 
 using namespace nfk;
@@ -373,22 +487,48 @@ int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* o
   a.n_out = n_out;
   a.act = act;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long cap = sm_count();
-  const unsigned grid = (unsigned)(a.m_tiles < cap ? a.m_tiles : cap);
-  cudaError_t e;
-  if (out_f32) {
-    e = cudaFuncSetAttribute(gemm_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
-    if (e == cudaSuccess) gemm_ws_kernel<true><<<grid, WS_THREADS, WS_SMEM, st>>>(a);
-  } else {
-    e = cudaFuncSetAttribute(gemm_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
-    if (e == cudaSuccess) gemm_ws_kernel<false><<<grid, WS_THREADS, WS_SMEM, st>>>(a);
-  }
-  if (e != cudaSuccess) {
-    set_error("gemm_ws: cannot set %zu B dynamic shared memory: %s", WS_SMEM, cudaGetErrorString(e));
-    return NFK_ECUDA;
-  }
-  count_launch();
-  return check_launch("gemm_ws");
+  return out_f32 ? launch_ws<EPI_F32_ROWS, 0, false>(a, st) : launch_ws<EPI_BF16_IMG, 0, false>(a, st);
+}
+
+int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, const float* x, float* out,
+                    float* logdet, int64_t M, int KB, int kmma_last, int mask_col, float B, int inverse,
+                    int accumulate, int arith, void* stream) {
+  NFK_REQUIRE(M >= 0 && KB > 0, "gemm_ws_rqs: bad shape M=%lld KB=%d", (long long)M, KB);
+  NFK_REQUIRE(kmma_last >= 1 && kmma_last <= 4, "gemm_ws_rqs: kmma_last must be 1..4");
+  NFK_REQUIRE(mask_col == 0 || mask_col == 1, "gemm_ws_rqs: mask column must be 0 or 1");
+  NFK_REQUIRE(arith >= NFK_ARITH_EXACT && arith <= NFK_ARITH_FAST, "gemm_ws_rqs: bad arith %d", arith);
+  NFK_REQUIRE(B > 0.f, "gemm_ws_rqs: tail bound must be positive");
+  if (M == 0) return NFK_OK;
+  NFK_REQUIRE(a_img && w_img && bias && x && out && logdet, "gemm_ws_rqs: null device pointer");
+  NFK_REQUIRE(x != out, "gemm_ws_rqs: out must not alias x");
+  NFK_REQUIRE(((reinterpret_cast<uintptr_t>(a_img) | reinterpret_cast<uintptr_t>(w_img) |
+                reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(x) |
+                reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              "gemm_ws_rqs: pointers must be 16-byte aligned");
+  WsArgs a{};
+  a.a_img = reinterpret_cast<const unsigned char*>(a_img);
+  a.w_img = reinterpret_cast<const unsigned char*>(w_img);
+  a.bias = bias;
+  a.out = out;
+  a.m_tiles = (M + WS_M - 1) / WS_M;
+  a.M = M;
+  a.KB = KB;
+  a.kmma_last = kmma_last;
+  a.n_tiles = WS_NF / WS_TF;
+  for (int t = 0; t < a.n_tiles; ++t) a.nb[t] = WS_TF * WS_PC / 64;
+  a.x = x;
+  a.logdet = logdet;
+  a.cond_first = (mask_col == 0);
+  a.accumulate = accumulate;
+  a.c = make_rqs_consts(8, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool inv = inverse != 0;
+  if (arith == NFK_ARITH_EXACT)
+    return inv ? launch_ws<EPI_RQS, NFK_ARITH_EXACT, true>(a, st) : launch_ws<EPI_RQS, NFK_ARITH_EXACT, false>(a, st);
+  if (arith == NFK_ARITH_HYBRID)
+    return inv ? launch_ws<EPI_RQS, NFK_ARITH_HYBRID, true>(a, st)
+               : launch_ws<EPI_RQS, NFK_ARITH_HYBRID, false>(a, st);
+  return inv ? launch_ws<EPI_RQS, NFK_ARITH_FAST, true>(a, st) : launch_ws<EPI_RQS, NFK_ARITH_FAST, false>(a, st);
 }
 
 }  // extern "C"

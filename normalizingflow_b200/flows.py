@@ -131,6 +131,9 @@ class NSF_CL(nn.Module):
         n_t = self.size * (self.dim - len(self._mask))
         if no_grad and x.dtype == torch.float32:
             from . import _wide
+            if self.fused and _wide.rqs_eligible(self):
+                # wide conditioner with the spline transform as the epilogue of its last GEMM
+                return _wide.run_layer(self, x, inverse, logdet)
             if _wide.usable(self.psi):
                 # wide conditioner: gather + 3 persistent tcgen05 GEMMs over image-layout operands
                 params = _wide.mlp3(self.psi, x, self.size, self.dim, self._mask).reshape(-1, n_t, 3 * self.K - 1)

@@ -76,6 +76,32 @@ def test_wide_mlp3_matches_bf16_chain():
 
 
 @pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("mask", [[0], [1]])
+@pytest.mark.parametrize("arith", ["fast", "hybrid", "exact"])
+def test_rqs_epilogue_matches_unfused(inverse, mask, arith):
+    """GEMM-with-spline-epilogue vs the same bf16 conditioner followed by the stand-alone spline
+    kernel: same parameters up to accumulation order, so outputs agree far inside the 1e-2 class;
+    also checks the tail tile (N not a multiple of 128) and log-det accumulation."""
+    from normalizingflow_b200 import flows
+    torch.manual_seed(2)
+    lay = flows.NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=200, mask=mask, arith=arith)
+    lay.psi.precision = "bf16"
+    lay = lay.cuda()
+    with torch.no_grad():
+        lay.psi.network[4].weight.mul_(4.0)          # non-uniform bins
+    x = torch.randn(1000, 64, generator=torch.Generator().manual_seed(4)).cuda()
+    x[0, :4] = torch.tensor([3.0, -3.0, 3.5, -7.0])  # tail bound and identity tails
+    ld0 = torch.randn(1000, generator=torch.Generator().manual_seed(5)).cuda()
+    with torch.no_grad():
+        lay.fused = True
+        o1, l1 = lay._transform(x, inverse, ld0.clone())
+        lay.fused = False
+        o2, l2 = lay._transform(x, inverse, ld0.clone())
+    assert rel_err(o1.cpu(), o2.cpu().double()) <= 2e-4
+    assert rel_err(l1.cpu(), l2.cpu().double()) <= 1e-3
+
+
+@pytest.mark.parametrize("inverse", [False, True])
 def test_nsf_layer_h800_vs_oracle(inverse):
     """Whole NSF_CL layer at the class-default hidden width: wide bf16 conditioner + spline kernel
     vs the fp32 oracle (1e-2 class of the bf16 conditioner path)."""
