@@ -191,14 +191,17 @@ int nfk_gemm_ws_rows_per_tile(void);
 int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* out, int64_t M,
                 int KB, int kmma_last, const int32_t* tile_blocks /*host*/, int n_tiles, int act,
                 int out_f32, int n_out, int64_t ldy, void* stream);
-/* last conditioner GEMM with the RQS transform as its epilogue (size = 32, dim = 2, one masked
- * column, K = 8): replaces the third nn.Linear of psi + nf/flows.py:232-239 / :246-253 +
- * nf/utils.py:20-152; the [N, 32, 23] parameter tensor never reaches HBM.  w_img: each feature's
- * 23 weight rows padded to 24, 4 N tiles of 8 features (192 rows), layout as nfk_gemm_ws; bias
- * [32*24] padded the same way.  x, out [M, 64] fp32; logdet [M] (+= when accumulate). */
+/* last conditioner GEMM with the RQS transform as its epilogue (any size, 2 <= dim <= 4, K = 8,
+ * at most 128 transformed features): replaces the third nn.Linear of psi + nf/flows.py:232-239 /
+ * :246-253 + nf/utils.py:20-152; the [N, F_t, 23] parameter tensor never reaches HBM.  w_img: each
+ * feature's 23 weight rows padded to 24, N tiles of 8 features (192 rows; the last tile zero
+ * padded), layout as nfk_gemm_ws; bias [ceil(F_t/8)*8*24] padded the same way.  x, out
+ * [M, size*dim] fp32 (out in the reference's column order, quirk Q5); logdet [M] (+= when
+ * accumulate); mask is a HOST array of n_mask conditioning columns. */
 int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, const float* x,
-                    float* out, float* logdet, int64_t M, int KB, int kmma_last, int mask_col,
-                    float B, int inverse, int accumulate, int arith, void* stream);
+                    float* out, float* logdet, int64_t M, int KB, int kmma_last, int size, int dim,
+                    const int32_t* mask, int n_mask, float B, int inverse, int accumulate,
+                    int arith, void* stream);
 /* x[:, :, cols].flatten(1) (nf/flows.py:230) -> bf16 a_img [ceil(N/128)][KB][128][64], zero padded */
 int nfk_pack_a_img(const float* x, void* img, int64_t N, int size, int dim, const int32_t* cols /*host*/,
                    int n_cols, int KB, void* stream);

@@ -133,13 +133,16 @@ def mlp3(fcnn, x, size=None, dim=1, cols=(0,)):
 
 def rqs_eligible(layer) -> bool:
     """Layers whose last GEMM can carry the spline transform as its epilogue (nfk_gemm_ws_rqs)."""
-    return (_lib.have("nfk_gemm_ws_rqs") and layer.size == 32 and layer.dim == 2 and len(layer._mask) == 1
-            and layer.K == 8 and usable(layer.psi) and layer.psi.network[0].in_features == 32)
+    n_t = layer.size * (layer.dim - len(layer._mask))
+    return (_lib.have("nfk_gemm_ws_rqs") and layer.K == 8 and 2 <= layer.dim <= 4 and n_t <= 128
+            and 1 <= len(layer._mask) < layer.dim and usable(layer.psi)
+            and layer.psi.network[0].in_features == layer.size * len(layer._mask)
+            and layer.psi.network[4].out_features == 23 * n_t)
 
 
 def packed_rqs(layer):
     """(l1, l2, l3) of the layer's conditioner with l3 in the per-feature padded (23 -> 24 rows)
-    layout of the fused spline epilogue."""
+    layout of the fused spline epilogue: N tiles of 8 features."""
     fcnn = layer.psi
     l1, l2, _ = packed(fcnn)
     last = fcnn.network[4]
@@ -148,12 +151,14 @@ def packed_rqs(layer):
     if cache is None or cache[0] != key:
         H = last.in_features
         dev = last.weight.device
-        w3 = torch.zeros((32, 24, H), dtype=torch.float32, device=dev)
-        w3[:, :23] = last.weight.detach().float().reshape(32, 23, H)
-        b3 = torch.zeros((32, 24), dtype=torch.float32, device=dev)
-        b3[:, :23] = last.bias.detach().float().reshape(32, 23)
+        n_t = last.out_features // 23
+        n_tiles = (n_t + 7) // 8
+        w3 = torch.zeros((n_tiles * 8, 24, H), dtype=torch.float32, device=dev)
+        w3[:n_t, :23] = last.weight.detach().float().reshape(n_t, 23, H)
+        b3 = torch.zeros((n_tiles * 8, 24), dtype=torch.float32, device=dev)
+        b3[:n_t, :23] = last.bias.detach().float().reshape(n_t, 23)
         kb = sum(l2["tiles"])
-        w_img, bp = weight_image(w3.reshape(768, H), b3.reshape(-1), kb, [3, 3, 3, 3])
+        w_img, bp = weight_image(w3.reshape(-1, H), b3.reshape(-1), kb, [3] * n_tiles)
         l3 = dict(w=w_img, b=bp, KB=kb, kmma_last=(H - 64 * (kb - 1) + 15) // 16)
         layer._wide_rqs_cache = cache = (key, l3)
     return l1, l2, cache[1]
@@ -165,10 +170,10 @@ def run_layer(layer, x, inverse, logdet=None):
     x = f32c(x)
     N = x.shape[0]
     l1, l2, l3 = packed_rqs(layer)
-    a0 = pack_input(x, 32, 2, layer._mask, l1["KB"])
+    a0 = pack_input(x, layer.size, layer.dim, layer._mask, l1["KB"])
     h1 = gemm(a0, l1, N, 1, False, "gemm_ws_l1")
     h2 = gemm(h1, l2, N, 1, False, "gemm_ws_l2")
-    out = torch.empty((N, 64), dtype=torch.float32, device=dev)
+    out = torch.empty((N, layer.size * layer.dim), dtype=torch.float32, device=dev)
     accumulate = logdet is not None
     if not accumulate:
         logdet = torch.empty((N,), dtype=torch.float32, device=dev)
@@ -176,8 +181,8 @@ def run_layer(layer, x, inverse, logdet=None):
         tm = _ops.KERNEL_TIMER
         ev = tm.start("gemm_ws_rqs", dev) if tm is not None else None
         call("nfk_gemm_ws_rqs", ptr(h2), ptr(l3["w"]), ptr(l3["b"]), ptr(x), ptr(out), ptr(logdet), N, l3["KB"],
-             l3["kmma_last"], layer._mask[0], float(layer.B), int(bool(inverse)), int(accumulate),
-             _ops._arith(layer.arith), stream_ptr(dev))
+             l3["kmma_last"], layer.size, layer.dim, i32_array(layer._mask), len(layer._mask), float(layer.B),
+             int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), stream_ptr(dev))
         if ev is not None:
             tm.stop(ev, dev)
     return out, logdet

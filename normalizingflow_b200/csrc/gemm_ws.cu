@@ -35,10 +35,10 @@ namespace nfk {
 enum { EPI_BF16_IMG = 0, EPI_F32_ROWS = 1, EPI_RQS = 2 };
 
 constexpr int WS_M = 128;
-constexpr int WS_MAX_TILES = 8;
+constexpr int WS_MAX_TILES = 16;
 constexpr uint32_t WS_BLK = 128 * 128;                 // one 128 x 64 bf16 block
 constexpr uint32_t WS_A_BYTES = WS_BLK;
-constexpr int WS_NF = 32, WS_PC = 24, WS_TF = 8;       // EPI_RQS: features, columns per feature, features per tile
+constexpr int WS_PC = 24, WS_TF = 8;    // EPI_RQS: accumulator columns per feature, features per N tile
 
 template <int EPI>
 struct WsCfg {                                         // plain GEMM epilogues
@@ -48,11 +48,18 @@ struct WsCfg {                                         // plain GEMM epilogues
   static constexpr uint32_t STG_BYTES = 2 * WS_BLK;    // output staging
 };
 template <>
+struct WsCfg<EPI_BF16_IMG> {                           // two teams of 8 epilogue warps, one staging block each
+  static constexpr int STAGES = 4;
+  static constexpr int EPI_WARPS = 16;
+  static constexpr uint32_t B_BYTES = 256 * 128;
+  static constexpr uint32_t STG_BYTES = 2 * WS_BLK;
+};
+template <>
 struct WsCfg<EPI_RQS> {
   static constexpr int STAGES = 5;
   static constexpr int EPI_WARPS = 16;
   static constexpr uint32_t B_BYTES = WS_TF * WS_PC * 128;                       // 192 rows
-  static constexpr uint32_t STG_BYTES = WS_NF * WS_PC * 4 + 2 * WS_M * 4 * 4;    // b3 + log-det partials
+  static constexpr uint32_t STG_BYTES = WS_MAX_TILES * WS_TF * WS_PC * 4 + 2 * WS_M * 4 * 4;   // b3 + log-det partials
 };
 template <int EPI>
 constexpr size_t ws_smem() {
@@ -76,9 +83,10 @@ struct WsArgs {
   int n_out;               // real output columns (fp32 row output)
   int act;                 // 0 identity, 1 tanh
   // EPI_RQS only
-  const float* x;          // [M, 64]
+  const float* x;          // [M, size*dim]
   float* logdet;           // [M]
-  int cond_first;          // 1: conditioning column is column 0 of each pair (mask = [0])
+  int dim, n_mask, n_feat; // columns per group, conditioning columns per group, transformed features
+  int mask[4], unm[4];     // conditioning / transformed column indices inside a group
   int accumulate;
   RqsConsts c;
 };
@@ -93,7 +101,7 @@ __device__ __forceinline__ bool ws_elect_one() {
   return pred != 0;
 }
 
-template <int EPI, int MODE, bool INVERSE>
+template <int EPI, int MODE, bool INVERSE, bool PAIRS>
 __global__ void __launch_bounds__((2 + WsCfg<EPI>::EPI_WARPS) * 32, 1)
 gemm_ws_kernel(const __grid_constant__ WsArgs a) {
   constexpr int WS_STAGES = WsCfg<EPI>::STAGES;
@@ -195,25 +203,44 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
     const int row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     float* sB3 = reinterpret_cast<float*>(stg);
-    float* sLd = sB3 + WS_NF * WS_PC;                    // [2][128][4]
-    for (int i = tid - 64; i < WS_NF * WS_PC; i += WS_EPI_WARPS * 32) sB3[i] = a.bias[i];
+    float* sLd = sB3 + WS_MAX_TILES * WS_TF * WS_PC;     // [2][128][4]
+    for (int i = tid - 64; i < a.n_tiles * WS_TF * WS_PC; i += WS_EPI_WARPS * 32) sB3[i] = a.bias[i];
     asm volatile("bar.sync 5, %0;" ::"n"(WS_EPI_WARPS * 32) : "memory");
+    const int D = a.dim, n_un = a.dim - a.n_mask, d = a.dim * (a.n_feat / n_un);
+    const int unm0 = a.unm[0], unm1 = a.unm[1], unm2 = a.unm[2];
+    const int mask0 = a.mask[0], mask1 = a.mask[1], mask2 = a.mask[2];
     uint32_t tl = 0, it = 0;
     for (long long mt = first; mt < a.m_tiles; mt += stride, ++it) {
       const long long grow = mt * WS_M + row;
       const bool live = grow < a.M;
-      const float* xr = a.x + grow * 64;
-      float* orow = reinterpret_cast<float*>(a.out) + grow * 64;
+      const float* xr = a.x + grow * d;
+      float* orow = reinterpret_cast<float*>(a.out) + grow * d;
       float ld_old = 0.f;
       if (slice == 0 && live && a.accumulate) ld_old = __ldg(a.logdet + grow);
       float lad_acc = 0.f;
-      for (int t = 0; t < WS_NF / WS_TF; ++t, ++tl) {
+      for (int t = 0; t < a.n_tiles; ++t, ++tl) {
         const uint32_t acc = tl & 1;
-        float2 xin[2];
+        // feature f = (group s, transformed column u): reads x[s*D + unm[u]], writes out[s*D + n_mask + u]
+        float xin[2], xcond[2];
+        int gbase[2], uu[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
-          xin[e] = live ? __ldg(reinterpret_cast<const float2*>(xr + 2 * (t * WS_TF + slice + 4 * e)))
-                        : make_float2(0.f, 0.f);
+        for (int e = 0; e < 2; ++e) {
+          const int f = t * WS_TF + slice + 4 * e;
+          if (PAIRS) {                                   // dim 2, one conditioning column: one 8-byte access
+            gbase[e] = live ? 2 * f : -1;
+            uu[e] = 0;
+            const float2 xc = live ? __ldg(reinterpret_cast<const float2*>(xr + 2 * f)) : make_float2(0.f, 0.f);
+            xin[e] = unm0 ? xc.y : xc.x;
+            xcond[e] = unm0 ? xc.x : xc.y;
+          } else {
+            const int sgrp = n_un == 1 ? f : (n_un == 2 ? (f >> 1) : f / 3);
+            uu[e] = f - sgrp * n_un;
+            gbase[e] = (live && f < a.n_feat) ? sgrp * D : -1;
+            const int col = uu[e] == 0 ? unm0 : (uu[e] == 1 ? unm1 : unm2);
+            xin[e] = gbase[e] >= 0 ? __ldg(xr + gbase[e] + col) : 0.f;
+            xcond[e] = 0.f;
+          }
+        }
         mbar_wait(&tfull[acc], (tl >> 1) & 1);
         tc_fence_after();
 #pragma unroll
@@ -229,15 +256,24 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);      // the accumulator may be overwritten
           }
-          const float2 xc = xin[e];
-          const RqsOut o = rqs_element<MODE, 8, INVERSE, true>(RegParams{v, sB3 + f * WS_PC},
-                                                                a.cond_first ? xc.y : xc.x, a.c);
-          if (live)                                          // (conditioning, transformed): quirk Q5
-            *reinterpret_cast<float2*>(orow + 2 * f) = make_float2(a.cond_first ? xc.x : xc.y, o.y);
-          lad_acc += o.lad;
+          const RqsOut o = rqs_element<MODE, 8, INVERSE, true>(RegParams{v, sB3 + f * WS_PC}, xin[e], a.c);
+          if (gbase[e] >= 0) {
+            // transformed columns follow the conditioning ones inside a group: quirk Q5
+            if (PAIRS) {
+              *reinterpret_cast<float2*>(orow + gbase[e]) = make_float2(xcond[e], o.y);
+            } else {
+              orow[gbase[e] + a.n_mask + uu[e]] = o.y;
+              if (uu[e] == 0) {
+                orow[gbase[e]] = __ldg(xr + gbase[e] + mask0);
+                if (a.n_mask > 1) orow[gbase[e] + 1] = __ldg(xr + gbase[e] + mask1);
+                if (a.n_mask > 2) orow[gbase[e] + 2] = __ldg(xr + gbase[e] + mask2);
+              }
+            }
+            lad_acc += o.lad;
+          }
         }
       }
-      // row log-det = sum over the 32 features (flows.py:238): 4 partial sums per row
+      // row log-det = sum over the features (flows.py:238): 4 partial sums per row
       float* sl = sLd + (it & 1) * (WS_M * 4);
       sl[row * 4 + slice] = lad_acc;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
@@ -247,6 +283,89 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
         a.logdet[grow] = a.accumulate ? ld_old + tsum : tsum;
       }
     }
+  } else if constexpr (EPI == EPI_BF16_IMG) {
+    // ============== epilogue: bias + tanh -> bf16 image block -> TMA bulk store ==============
+    // Two teams of 8 warps take alternate 64-column blocks; a team owns one 16 KB staging block.
+    const int ew = warp - 2;
+    const int team = ew >> 3;
+    const int q = warp & 3;              // TMEM lane quadrant this warp may read
+    const int h = (ew >> 2) & 1;         // 32-column half of the block
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const bool issuer = ((ew & 7) == 0 && lane == 0);
+    unsigned char* sb = stg + team * WS_BLK;
+    uint32_t tl = 0, bc = 0;
+    int ob_total = 0;
+    for (int t = 0; t < a.n_tiles; ++t) ob_total += a.nb[t];
+    for (long long mt = first; mt < a.m_tiles; mt += stride) {
+      int ob0 = 0;
+      for (int t = 0; t < a.n_tiles; ++t, ++tl) {
+        const uint32_t acc = tl & 1;
+        const int nb = a.nb[t];
+        mbar_wait(&tfull[acc], (tl >> 1) & 1);
+        tc_fence_after();
+        const int b_first = ((bc & 1) == (uint32_t)team) ? 0 : 1;      // this team's blocks: b_first, +2, ...
+        if (b_first >= nb) {                                           // nothing of this tile is ours
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        for (int b = b_first; b < nb; b += 2) {
+          uint32_t v[32];
+          tmem_ld32(tmem + acc * 256 + lane_sel + (uint32_t)(b * 64 + h * 32), v);
+          tmem_ld_wait();
+          if (b + 2 >= nb) {
+            // this warp's last columns of the accumulator are in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          const int colb = (ob0 + b) * 64 + h * 32;        // first padded output column of v[]
+          const float4* bp = reinterpret_cast<const float4*>(a.bias + colb);
+          uint4 u[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b0 = __ldg(bp + 2 * j), b1 = __ldg(bp + 2 * j + 1);
+            float f[8];
+            f[0] = __uint_as_float(v[8 * j + 0]) + b0.x;
+            f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
+            f[2] = __uint_as_float(v[8 * j + 2]) + b0.z;
+            f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
+            f[4] = __uint_as_float(v[8 * j + 4]) + b1.x;
+            f[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
+            f[6] = __uint_as_float(v[8 * j + 6]) + b1.z;
+            f[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+            if (a.act == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = tanh_approx(f[e]);
+            }
+            u[j].x = pack_bf16x2(f[0], f[1]);
+            u[j].y = pack_bf16x2(f[2], f[3]);
+            u[j].z = pack_bf16x2(f[4], f[5]);
+            u[j].w = pack_bf16x2(f[6], f[7]);
+          }
+          // the team's previous bulk store must have finished reading the staging block
+          if (issuer) bulk_wait_read<0>();
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = h * 4 + j;
+            *reinterpret_cast<uint4*>(sb + row * 128 + ((ch ^ (row & 7)) << 4)) = u[j];
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
+          if (issuer) {
+            unsigned char* og = reinterpret_cast<unsigned char*>(a.out) +
+                                ((size_t)mt * ob_total + (ob0 + b)) * WS_BLK;
+            bulk_s2g(og, sb, WS_BLK);
+            bulk_commit();
+          }
+        }
+        bc += nb;
+        ob0 += nb;
+      }
+    }
+    if (issuer) bulk_wait_all<0>();
   } else {
     // ================================ epilogue ================================
     const int ew = warp - 2;
@@ -404,9 +523,9 @@ pack_a_img_kernel(const float* __restrict__ x, unsigned char* __restrict__ img, 
 
 RqsConsts make_rqs_consts(int K, float B);   // rqs_coupling.cu
 
-template <int EPI, int MODE, bool INVERSE>
+template <int EPI, int MODE, bool INVERSE, bool PAIRS = false>
 static int launch_ws(const WsArgs& a, cudaStream_t st) {
-  auto kern = gemm_ws_kernel<EPI, MODE, INVERSE>;
+  auto kern = gemm_ws_kernel<EPI, MODE, INVERSE, PAIRS>;
   constexpr size_t smem = ws_smem<EPI>();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
@@ -491,21 +610,35 @@ int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* o
 }
 
 int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, const float* x, float* out,
-                    float* logdet, int64_t M, int KB, int kmma_last, int mask_col, float B, int inverse,
-                    int accumulate, int arith, void* stream) {
+                    float* logdet, int64_t M, int KB, int kmma_last, int size, int dim, const int32_t* mask,
+                    int n_mask, float B, int inverse, int accumulate, int arith, void* stream) {
   NFK_REQUIRE(M >= 0 && KB > 0, "gemm_ws_rqs: bad shape M=%lld KB=%d", (long long)M, KB);
   NFK_REQUIRE(kmma_last >= 1 && kmma_last <= 4, "gemm_ws_rqs: kmma_last must be 1..4");
-  NFK_REQUIRE(mask_col == 0 || mask_col == 1, "gemm_ws_rqs: mask column must be 0 or 1");
+  NFK_REQUIRE(size >= 1 && dim >= 2 && dim <= 4 && mask && n_mask >= 1 && n_mask < dim,
+              "gemm_ws_rqs: need 2 <= dim <= 4 and 1 <= n_mask < dim");
   NFK_REQUIRE(arith >= NFK_ARITH_EXACT && arith <= NFK_ARITH_FAST, "gemm_ws_rqs: bad arith %d", arith);
   NFK_REQUIRE(B > 0.f, "gemm_ws_rqs: tail bound must be positive");
+  WsArgs a{};
+  a.dim = dim;
+  a.n_mask = n_mask;
+  bool used[4] = {false, false, false, false};
+  for (int j = 0; j < n_mask; ++j) {
+    NFK_REQUIRE(mask[j] >= 0 && mask[j] < dim && !used[mask[j]], "gemm_ws_rqs: bad mask column %d", mask[j]);
+    used[mask[j]] = true;
+    a.mask[j] = mask[j];
+  }
+  for (int c = 0, u = 0; c < dim; ++c)
+    if (!used[c]) a.unm[u++] = c;
+  a.n_feat = size * (dim - n_mask);
+  a.n_tiles = (a.n_feat + WS_TF - 1) / WS_TF;
+  NFK_REQUIRE(a.n_tiles <= WS_MAX_TILES, "gemm_ws_rqs: %d transformed features exceed %d", a.n_feat,
+              WS_MAX_TILES * WS_TF);
   if (M == 0) return NFK_OK;
   NFK_REQUIRE(a_img && w_img && bias && x && out && logdet, "gemm_ws_rqs: null device pointer");
   NFK_REQUIRE(x != out, "gemm_ws_rqs: out must not alias x");
   NFK_REQUIRE(((reinterpret_cast<uintptr_t>(a_img) | reinterpret_cast<uintptr_t>(w_img) |
-                reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(x) |
-                reinterpret_cast<uintptr_t>(out)) & 15) == 0,
-              "gemm_ws_rqs: pointers must be 16-byte aligned");
-  WsArgs a{};
+                reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
+              "gemm_ws_rqs: operand images must be 16-byte aligned");
   a.a_img = reinterpret_cast<const unsigned char*>(a_img);
   a.w_img = reinterpret_cast<const unsigned char*>(w_img);
   a.bias = bias;
@@ -514,21 +647,24 @@ int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, con
   a.M = M;
   a.KB = KB;
   a.kmma_last = kmma_last;
-  a.n_tiles = WS_NF / WS_TF;
   for (int t = 0; t < a.n_tiles; ++t) a.nb[t] = WS_TF * WS_PC / 64;
   a.x = x;
   a.logdet = logdet;
-  a.cond_first = (mask_col == 0);
   a.accumulate = accumulate;
   a.c = make_rqs_consts(8, B);
   cudaStream_t st = (cudaStream_t)stream;
   const bool inv = inverse != 0;
-  if (arith == NFK_ARITH_EXACT)
-    return inv ? launch_ws<EPI_RQS, NFK_ARITH_EXACT, true>(a, st) : launch_ws<EPI_RQS, NFK_ARITH_EXACT, false>(a, st);
-  if (arith == NFK_ARITH_HYBRID)
-    return inv ? launch_ws<EPI_RQS, NFK_ARITH_HYBRID, true>(a, st)
-               : launch_ws<EPI_RQS, NFK_ARITH_HYBRID, false>(a, st);
-  return inv ? launch_ws<EPI_RQS, NFK_ARITH_FAST, true>(a, st) : launch_ws<EPI_RQS, NFK_ARITH_FAST, false>(a, st);
+  const bool pairs = (dim == 2);
+#define NFK_WS_RQS(MODE)                                                                             \
+  do {                                                                                               \
+    if (pairs)                                                                                       \
+      return inv ? launch_ws<EPI_RQS, MODE, true, true>(a, st) : launch_ws<EPI_RQS, MODE, false, true>(a, st);   \
+    return inv ? launch_ws<EPI_RQS, MODE, true, false>(a, st) : launch_ws<EPI_RQS, MODE, false, false>(a, st);   \
+  } while (0)
+  if (arith == NFK_ARITH_EXACT) NFK_WS_RQS(NFK_ARITH_EXACT);
+  if (arith == NFK_ARITH_HYBRID) NFK_WS_RQS(NFK_ARITH_HYBRID);
+  NFK_WS_RQS(NFK_ARITH_FAST);
+#undef NFK_WS_RQS
 }
 
 }  // extern "C"

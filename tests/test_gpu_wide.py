@@ -102,6 +102,28 @@ def test_rqs_epilogue_matches_unfused(inverse, mask, arith):
 
 
 @pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("mask", [[0], [1], [2], [0, 1], [1, 2], [0, 2]])
+def test_rqs_epilogue_lj38_geometry(inverse, mask):
+    """LJ-38 geometry (size 38, dim 3, all six masks of applications/src/setup.py:60-61): the
+    spline epilogue's column bookkeeping (quirk Q5 output order) vs the stand-alone kernel."""
+    from normalizingflow_b200 import flows
+    torch.manual_seed(3)
+    lay = flows.NSF_CL(38, dim=3, K=8, B=4.0, hidden_dim=160, mask=mask, arith="hybrid")
+    lay.psi.precision = "bf16"
+    lay = lay.cuda()
+    with torch.no_grad():
+        lay.psi.network[4].weight.mul_(4.0)
+    x = (1.5 * torch.randn(700, 114, generator=torch.Generator().manual_seed(6))).cuda()
+    with torch.no_grad():
+        lay.fused = True
+        o1, l1 = lay._transform(x, inverse)
+        lay.fused = False
+        o2, l2 = lay._transform(x, inverse)
+    assert rel_err(o1.cpu(), o2.cpu().double()) <= 2e-4
+    assert rel_err(l1.cpu(), l2.cpu().double()) <= 1e-3
+
+
+@pytest.mark.parametrize("inverse", [False, True])
 def test_nsf_layer_h800_vs_oracle(inverse):
     """Whole NSF_CL layer at the class-default hidden width: wide bf16 conditioner + spline kernel
     vs the fp32 oracle (1e-2 class of the bf16 conditioner path)."""
