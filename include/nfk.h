@@ -186,11 +186,14 @@ int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w
  *   out   out_f32 == 0: bf16 image [ceil(M/128)][sum(tile_blocks)][128][64] (next layer's a_img)
  *         out_f32 != 0: fp32 rows [M, ldy], first n_out columns written
  * kmma_last = ceil((K - 64*(KB-1)) / 16): tcgen05.mma count in the last K block.
- * Replaces one nn.Linear(+Tanh) of FCNN (nf/flows.py:26-35). */
+ * act: 0 identity, 1 tanh, 2 tanh BACKWARD: out = (A W^T) * (1 - h^2) with h read from the bf16
+ * image `aux` laid out like `out` (the saved forward activation) -- the dgrad step of the
+ * conditioner.  `aux` may be NULL otherwise.
+ * Replaces one nn.Linear(+Tanh) of FCNN (nf/flows.py:26-35), and autograd through it. */
 int nfk_gemm_ws_rows_per_tile(void);
 int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* out, int64_t M,
                 int KB, int kmma_last, const int32_t* tile_blocks /*host*/, int n_tiles, int act,
-                int out_f32, int n_out, int64_t ldy, void* stream);
+                int out_f32, int n_out, int64_t ldy, const void* aux, void* stream);
 /* last conditioner GEMM with the RQS transform as its epilogue (any size, 2 <= dim <= 4, K = 8,
  * at most 128 transformed features): replaces the third nn.Linear of psi + nf/flows.py:232-239 /
  * :246-253 + nf/utils.py:20-152; the [N, F_t, 23] parameter tensor never reaches HBM.  w_img: each
@@ -202,6 +205,24 @@ int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, con
                     float* out, float* logdet, int64_t M, int KB, int kmma_last, int size, int dim,
                     const int32_t* mask, int n_mask, float B, int inverse, int accumulate,
                     int arith, void* stream);
+/* BACKWARD twin of nfk_gemm_ws_rqs: recomputes the spline parameters with the same GEMM
+ * (a_img = saved last hidden activation, w_img / bias as the forward) and runs the spline's
+ * adjoint as the epilogue: grad_x [M, size*dim] receives the direct path (transformed columns
+ * through the spline, conditioning columns copied from grad_out in input order) and
+ * grad_params_img receives dL/dparams as a bf16 image [ceil(M/128)][3*ceil(F_t/8)][128][64]
+ * (per-feature 24-column padding, like w_img's rows) -- the A operand of the dgrad GEMM
+ * nfk_gemm_ws(grad_params_img, W3^T image, ..., act = 2, aux = h2 image).  grad_logdet [M] may be
+ * NULL: grad_logdet_const is then used for every row (1 for log-prob gradients).
+ * Replaces autograd through nf/flows.py:232-239 / :246-253 + nf/utils.py:27-152. */
+int nfk_gemm_ws_rqs_bwd(const void* a_img, const void* w_img, const float* bias, const float* x,
+                        const float* grad_out, const float* grad_logdet, float grad_logdet_const,
+                        float* grad_x, void* grad_params_img, int64_t M, int KB, int kmma_last,
+                        int size, int dim, const int32_t* mask, int n_mask, float B, int inverse,
+                        void* stream);
+/* g[:, s*dim + cols[j]] += dxc[:, s*n_cols + j]: adds the conditioner-input gradient [N, size*n_cols]
+ * to the conditioning columns of grad_x (adjoint of the gather at nf/flows.py:230) */
+int nfk_scatter_add_cols(float* g, const float* dxc, int64_t N, int size, int dim,
+                         const int32_t* cols /*host*/, int n_cols, void* stream);
 /* x[:, :, cols].flatten(1) (nf/flows.py:230) -> bf16 a_img [ceil(N/128)][KB][128][64], zero padded */
 int nfk_pack_a_img(const float* x, void* img, int64_t N, int size, int dim, const int32_t* cols /*host*/,
                    int n_cols, int KB, void* stream);

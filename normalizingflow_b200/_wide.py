@@ -97,7 +97,7 @@ def pack_input(x, size, dim, cols, kb):
     return img
 
 
-def gemm(a_img, layer, M, act, out_f32, tag="gemm_ws"):
+def gemm(a_img, layer, M, act, out_f32, tag="gemm_ws", aux=None):
     dev = a_img.device
     m_tiles = (M + ROWS - 1) // ROWS
     ob = sum(layer["tiles"])
@@ -112,7 +112,7 @@ def gemm(a_img, layer, M, act, out_f32, tag="gemm_ws"):
         ev = tm.start(tag, dev) if tm is not None else None
         call("nfk_gemm_ws", ptr(a_img), ptr(layer["w"]), ptr(layer["b"]), ptr(out), M, layer["KB"],
              layer["kmma_last"], layer["tiles_c"], len(layer["tiles"]), act, int(out_f32), layer["n_out"], ldy,
-             stream_ptr(dev))
+             ptr(aux), stream_ptr(dev))
         if ev is not None:
             tm.stop(ev, dev)
     return out
@@ -186,6 +186,124 @@ def run_layer(layer, x, inverse, logdet=None):
         if ev is not None:
             tm.stop(ev, dev)
     return out, logdet
+
+
+# ---------------------------------------------------------------------------------------------
+# log-prob gradient path (flow-preconditioned HMC, nf/hmc.py + SURVEY 8(a) row H): forward that
+# keeps the hidden-activation images, backward = spline adjoint as a GEMM epilogue + 3 dgrad GEMMs
+# ---------------------------------------------------------------------------------------------
+def grad_eligible(layer) -> bool:
+    """Layers whose d(out, logdet)/dx runs on the tensor-core path (any hidden width)."""
+    psi = layer.psi
+    net = getattr(psi, "network", None)
+    n_t = layer.size * (layer.dim - len(layer._mask))
+    return (_lib.have("nfk_gemm_ws_rqs_bwd") and available() and getattr(psi, "precision", None) == "bf16"
+            and net is not None and len(net) == 5 and layer.K == 8 and 2 <= layer.dim <= 4 and n_t <= 128
+            and 1 <= len(layer._mask) < layer.dim and net[0].in_features == layer.size * len(layer._mask)
+            and net[4].out_features == 23 * n_t)
+
+
+def _transposed(w, kb):
+    """Layer dict for out = A @ w (w [k_in, n_out]): the dgrad GEMM of y = x w^T.  No bias."""
+    wt = w.detach().float().t().contiguous()            # [n_out, k_in] in nn.Linear orientation
+    n_out, k_in = wt.shape
+    tiles = plan_tiles(blocks(n_out))
+    w_img, b = weight_image(wt, None, kb, tiles)
+    return dict(w=w_img, b=b, KB=kb, kmma_last=min(4, (k_in - 64 * (kb - 1) + 15) // 16), tiles=tiles,
+                tiles_c=i32_array(tiles), n_out=n_out)
+
+
+def packed_bwd(layer):
+    """dgrad operands (W3p^T, W2^T, W1^T images), cached per parameter version."""
+    net = layer.psi.network
+    l0, l2, l4 = net[0], net[2], net[4]
+    key = tuple((l.weight._version, l.weight.data_ptr()) for l in (l0, l2, l4))
+    cache = getattr(layer, "_wide_bwd_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    H = l4.in_features
+    dev = l4.weight.device
+    n_t = l4.out_features // 23
+    n_tiles = (n_t + 7) // 8
+    w3 = torch.zeros((n_tiles * 8, 24, H), dtype=torch.float32, device=dev)
+    w3[:n_t, :23] = l4.weight.detach().float().reshape(n_t, 23, H)
+    t3 = _transposed(w3.reshape(-1, H), 3 * n_tiles)          # dH2 = G @ W3p
+    t2 = _transposed(l2.weight, blocks(l2.out_features))      # dH1 = dZ2 @ W2
+    t1 = _transposed(l0.weight, blocks(l0.out_features))      # dXc = dZ1 @ W1
+    layer._wide_bwd_cache = (key, (t3, t2, t1))
+    return t3, t2, t1
+
+
+def layer_forward_saving(layer, x, inverse, logdet=None):
+    """run_layer that also returns what the backward needs: (out, logdet, (x, h1, h2))."""
+    dev = require_cuda(x, logdet)
+    x = f32c(x)
+    N = x.shape[0]
+    l1, l2, l3 = packed_rqs(layer)
+    a0 = pack_input(x, layer.size, layer.dim, layer._mask, l1["KB"])
+    h1 = gemm(a0, l1, N, 1, False, "gemm_ws_l1")
+    h2 = gemm(h1, l2, N, 1, False, "gemm_ws_l2")
+    out = torch.empty((N, layer.size * layer.dim), dtype=torch.float32, device=dev)
+    accumulate = logdet is not None
+    if not accumulate:
+        logdet = torch.empty((N,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("nfk_gemm_ws_rqs", ptr(h2), ptr(l3["w"]), ptr(l3["b"]), ptr(x), ptr(out), ptr(logdet), N, l3["KB"],
+             l3["kmma_last"], layer.size, layer.dim, i32_array(layer._mask), len(layer._mask), float(layer.B),
+             int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), stream_ptr(dev))
+    return out, logdet, (x, h1, h2, bool(inverse))
+
+
+def layer_backward(layer, ctx, g_out, g_logdet=None, g_logdet_const=1.0):
+    """dL/dx of one layer from dL/dout [N, d] and dL/dlogdet ([N] tensor, or a constant for all rows)."""
+    x, h1, h2, inverse = ctx
+    dev = require_cuda(x, g_out, g_logdet)
+    g_out = f32c(g_out)
+    N, d = x.shape
+    _, _, l3 = packed_rqs(layer)
+    t3, t2, t1 = packed_bwd(layer)
+    m_tiles = (N + ROWS - 1) // ROWS
+    g_in = torch.empty((N, d), dtype=torch.float32, device=dev)
+    g_img = torch.empty((m_tiles, t3["KB"], ROWS, 64), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        call("nfk_gemm_ws_rqs_bwd", ptr(h2), ptr(l3["w"]), ptr(l3["b"]), ptr(x), ptr(g_out),
+             ptr(f32c(g_logdet)) if g_logdet is not None else ptr(None), float(g_logdet_const), ptr(g_in),
+             ptr(g_img), N, l3["KB"], l3["kmma_last"], layer.size, layer.dim, i32_array(layer._mask),
+             len(layer._mask), float(layer.B), int(inverse), stream_ptr(dev))
+    dz2 = gemm(g_img, t3, N, 2, False, "gemm_ws_d3", aux=h2)        # (G W3p) * (1 - h2^2)
+    dz1 = gemm(dz2, t2, N, 2, False, "gemm_ws_d2", aux=h1)          # (dZ2 W2) * (1 - h1^2)
+    dxc = gemm(dz1, t1, N, 0, True, "gemm_ws_d1")                   # dZ1 W1  [N, size*n_mask] fp32
+    with torch.cuda.device(dev):
+        call("nfk_scatter_add_cols", ptr(g_in), ptr(dxc), N, layer.size, layer.dim, i32_array(layer._mask),
+             len(layer._mask), stream_ptr(dev))
+    return g_in
+
+
+def flow_grad_eligible(model) -> bool:
+    """All layers are grad_eligible NSF_CL layers under a GaussianPrior."""
+    from .flows import NSF_CL
+    prior = model.prior
+    return (hasattr(prior, "var") and hasattr(prior, "dim") and len(model.flows) > 0
+            and all(isinstance(f, NSF_CL) and grad_eligible(f) for f in model.flows))
+
+
+def flow_logp_and_grad(model, x):
+    """log p(x) [N] and d log p / dx [N, d] for a NormalizingFlowModel whose layers are all
+    grad_eligible NSF_CL layers under a GaussianPrior; None when the model does not qualify."""
+    if not flow_grad_eligible(model):
+        return None
+    prior = model.prior
+    h = f32c(x.detach())
+    logdet = torch.zeros(h.shape[0], dtype=torch.float32, device=h.device)
+    ctxs = []
+    for f in model.flows:
+        h, logdet, ctx = layer_forward_saving(f, h, False, logdet)
+        ctxs.append(ctx)
+    logp = _ops.gauss_logprob(h, prior.var) + logdet
+    g = h * (-1.0 / prior.var)                                      # d log N(z; 0, var I) / dz
+    for f, ctx in zip(reversed(model.flows), reversed(ctxs)):
+        g = layer_backward(f, ctx, g, None, 1.0)
+    return logp, g
 
 
 def image_to_rows(img, n_rows, n_cols):

@@ -27,12 +27,12 @@
 // (row, feature) pulls its 24 raw parameters out of TMEM, evaluates bin search + spline +
 // log|det| in registers (rqs_math.cuh) and writes the (conditioning, transformed) output pair;
 // the [N, 32, 23] parameter tensor never exists in HBM.
-#include "rqs_math.cuh"
+#include "rqs_bwd_math.cuh"
 #include "tc05.cuh"
 
 namespace nfk {
 
-enum { EPI_BF16_IMG = 0, EPI_F32_ROWS = 1, EPI_RQS = 2 };
+enum { EPI_BF16_IMG = 0, EPI_F32_ROWS = 1, EPI_RQS = 2, EPI_RQS_BWD = 3 };
 
 constexpr int WS_M = 128;
 constexpr int WS_MAX_TILES = 16;
@@ -61,11 +61,19 @@ struct WsCfg<EPI_RQS> {
   static constexpr uint32_t B_BYTES = WS_TF * WS_PC * 128;                       // 192 rows
   static constexpr uint32_t STG_BYTES = WS_MAX_TILES * WS_TF * WS_PC * 4 + 2 * WS_M * 4 * 4;   // b3 + log-det partials
 };
+template <>
+struct WsCfg<EPI_RQS_BWD> {                            // spline backward as the epilogue: grad_params image out
+  static constexpr int STAGES = 4;
+  static constexpr int EPI_WARPS = 16;
+  static constexpr uint32_t B_BYTES = WS_TF * WS_PC * 128;
+  static constexpr uint32_t STG_BYTES = 3 * WS_BLK + WS_MAX_TILES * WS_TF * WS_PC * 4;   // G tile + b3
+};
 template <int EPI>
 constexpr size_t ws_smem() {
   return (size_t)WsCfg<EPI>::STAGES * (WS_A_BYTES + WsCfg<EPI>::B_BYTES) + WsCfg<EPI>::STG_BYTES + 16 * 8 + 1024;
 }
-static_assert(ws_smem<EPI_BF16_IMG>() <= 227 * 1024 && ws_smem<EPI_RQS>() <= 227 * 1024,
+static_assert(ws_smem<EPI_BF16_IMG>() <= 227 * 1024 && ws_smem<EPI_RQS>() <= 227 * 1024 &&
+                  ws_smem<EPI_RQS_BWD>() <= 227 * 1024,
               "gemm_ws exceeds the 227 KB shared-memory limit");
 
 struct WsArgs {
@@ -89,6 +97,13 @@ struct WsArgs {
   int mask[4], unm[4];     // conditioning / transformed column indices inside a group
   int accumulate;
   RqsConsts c;
+  // act == 2 (bf16 image epilogue): out = acc * (1 - h^2), h = aux image laid out like out
+  const unsigned char* aux;
+  // EPI_RQS_BWD only
+  const float* gout;       // [M, size*dim] dL/d(layer output)
+  float* gin;              // [M, size*dim] dL/d(layer input), direct path
+  const float* gld;        // [M] dL/dlogdet, or null: gld_const for every row
+  float gld_const;
 };
 
 __device__ __forceinline__ bool ws_elect_one() {
@@ -283,6 +298,99 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
         a.logdet[grow] = a.accumulate ? ld_old + tsum : tsum;
       }
     }
+  } else if constexpr (EPI == EPI_RQS_BWD) {
+    // ============ epilogue: spline BACKWARD out of TMEM -> grad_params image + direct grad_x ============
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    constexpr int FPT = WS_TF / (WS_EPI_WARPS / 4);   // features per thread and tile
+    const int slice = ew >> 2;           // features FPT*slice .. FPT*slice+FPT-1 of every 8-feature tile
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const bool issuer = (ew == 0 && lane == 0);
+    unsigned char* sG = stg;                                             // [3][128][128 B] staged G tile
+    float* sB3 = reinterpret_cast<float*>(stg + 3 * WS_BLK);
+    for (int i = tid - 64; i < a.n_tiles * WS_TF * WS_PC; i += WS_EPI_WARPS * 32) sB3[i] = a.bias[i];
+    asm volatile("bar.sync 5, %0;" ::"n"(WS_EPI_WARPS * 32) : "memory");
+    const int D = a.dim, n_un = a.dim - a.n_mask, d = a.dim * (a.n_feat / n_un);
+    const int unm0 = a.unm[0], unm1 = a.unm[1], unm2 = a.unm[2];
+    const int mask0 = a.mask[0], mask1 = a.mask[1], mask2 = a.mask[2];
+    const int ob_total = 3 * a.n_tiles;
+    uint32_t tl = 0;
+    for (long long mt = first; mt < a.m_tiles; mt += stride) {
+      const long long grow = mt * WS_M + row;
+      const bool live = grow < a.M;
+      const float* xr = a.x + grow * d;
+      const float* gor = a.gout + grow * d;
+      float* gir = a.gin + grow * d;
+      const float gl = live ? (a.gld ? __ldg(a.gld + grow) : a.gld_const) : 0.f;
+      for (int t = 0; t < a.n_tiles; ++t, ++tl) {
+        const uint32_t acc = tl & 1;
+        float xin[FPT], gyv[FPT];
+        int gbase[FPT], uu[FPT], tcol[FPT];
+#pragma unroll
+        for (int e = 0; e < FPT; ++e) {
+          const int f = t * WS_TF + slice * FPT + e;
+          const int sgrp = n_un == 1 ? f : (n_un == 2 ? (f >> 1) : f / 3);
+          uu[e] = f - sgrp * n_un;
+          gbase[e] = (live && f < a.n_feat) ? sgrp * D : -1;
+          tcol[e] = uu[e] == 0 ? unm0 : (uu[e] == 1 ? unm1 : unm2);
+          xin[e] = gbase[e] >= 0 ? __ldg(xr + gbase[e] + tcol[e]) : 0.f;
+          gyv[e] = gbase[e] >= 0 ? __ldg(gor + gbase[e] + a.n_mask + uu[e]) : 0.f;
+        }
+        mbar_wait(&tfull[acc], (tl >> 1) & 1);
+        tc_fence_after();
+        // the previous tile's bulk store must have finished reading the staging tile
+        if (issuer) bulk_wait_read<0>();
+        asm volatile("bar.sync 1, %0;" ::"n"(WS_EPI_WARPS * 32) : "memory");
+#pragma unroll
+        for (int e = 0; e < FPT; ++e) {
+          const int fs = slice * FPT + e;                      // feature slot inside the tile
+          const int f = t * WS_TF + fs;
+          uint32_t v[24];
+          const uint32_t ta = tmem + acc * 256 + lane_sel + (uint32_t)(fs * WS_PC);
+          tmem_ld16(ta, v);
+          tmem_ld8(ta + 16, v + 16);
+          tmem_ld_wait();
+          if (e == FPT - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          float gxv, gp[24];
+          rqs_element_bwd<8, true>(RegParams{v, sB3 + f * WS_PC}, xin[e], gyv[e], gl, INVERSE, a.c, gxv, gp);
+          gp[23] = 0.f;
+          if (gbase[e] >= 0) {
+            gir[gbase[e] + tcol[e]] = gxv;
+            if (uu[e] == 0) {                                // conditioning columns: out[:, s, j] = x[:, s, mask[j]]
+              gir[gbase[e] + mask0] = __ldg(gor + gbase[e]);
+              if (a.n_mask > 1) gir[gbase[e] + mask1] = __ldg(gor + gbase[e] + 1);
+              if (a.n_mask > 2) gir[gbase[e] + mask2] = __ldg(gor + gbase[e] + 2);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 23; ++i) gp[i] = 0.f;        // padded rows / features: keep the image finite
+          }
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(gp[8 * j + 0], gp[8 * j + 1]);
+            u.y = pack_bf16x2(gp[8 * j + 2], gp[8 * j + 3]);
+            u.z = pack_bf16x2(gp[8 * j + 4], gp[8 * j + 5]);
+            u.w = pack_bf16x2(gp[8 * j + 6], gp[8 * j + 7]);
+            const int ch = 3 * fs + j;                       // 16-byte chunk of the 192-column tile
+            *reinterpret_cast<uint4*>(sG + (ch >> 3) * WS_BLK + row * 128 + (((ch & 7) ^ (row & 7)) << 4)) = u;
+          }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(WS_EPI_WARPS * 32) : "memory");
+        if (issuer) {
+          unsigned char* og = reinterpret_cast<unsigned char*>(a.out) + ((size_t)mt * ob_total + 3 * t) * WS_BLK;
+          bulk_s2g(og, sG, 3 * WS_BLK);
+          bulk_commit();
+        }
+      }
+    }
+    if (issuer) bulk_wait_all<0>();
   } else if constexpr (EPI == EPI_BF16_IMG) {
     // ============== epilogue: bias + tanh -> bf16 image block -> TMA bulk store ==============
     // Two teams of 8 warps take alternate 64-column blocks; a team owns one 16 KB staging block.
@@ -338,6 +446,17 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
             if (a.act == 1) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = tanh_approx(f[e]);
+            } else if (a.act == 2) {
+              // tanh backward: multiply by 1 - h^2, h from the saved activation image (same block, same chunk)
+              const uint4 hv = __ldg(reinterpret_cast<const uint4*>(
+                  a.aux + ((size_t)mt * ob_total + (ob0 + b)) * WS_BLK + row * 128 + (((h * 4 + j) ^ (row & 7)) << 4)));
+              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float h0 = __uint_as_float(hw[e] << 16), h1 = __uint_as_float(hw[e] & 0xffff0000u);
+                f[2 * e] *= fmaf(-h0, h0, 1.f);
+                f[2 * e + 1] *= fmaf(-h1, h1, 1.f);
+              }
             }
             u[j].x = pack_bf16x2(f[0], f[1]);
             u[j].y = pack_bf16x2(f[2], f[3]);
@@ -521,7 +640,44 @@ pack_a_img_kernel(const float* __restrict__ x, unsigned char* __restrict__ img, 
   }
 }
 
+// g[:, s*dim + mask[j]] += dxc[:, s*n_mask + j]: the conditioner-input gradient joins the direct path
+__global__ void __launch_bounds__(256)
+scatter_add_cols_kernel(float* __restrict__ g, const float* __restrict__ dxc, long long N, int size, int dim,
+                        int n_mask, int m0, int m1, int m2, int m3) {
+  const int per_row = size * n_mask;
+  const long long total = N * per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / per_row;
+    const int rem = (int)(i - row * per_row);
+    const int sgrp = rem / n_mask, j = rem - sgrp * n_mask;
+    const int col = j == 0 ? m0 : j == 1 ? m1 : j == 2 ? m2 : m3;
+    g[row * (long long)(size * dim) + sgrp * dim + col] += dxc[i];
+  }
+}
+
 RqsConsts make_rqs_consts(int K, float B);   // rqs_coupling.cu
+
+static int fill_rqs_geometry(WsArgs& a, int size, int dim, const int32_t* mask, int n_mask, const char* who) {
+  NFK_REQUIRE(size >= 1 && dim >= 2 && dim <= 4 && mask && n_mask >= 1 && n_mask < dim,
+              "%s: need 2 <= dim <= 4 and 1 <= n_mask < dim", who);
+  a.dim = dim;
+  a.n_mask = n_mask;
+  bool used[4] = {false, false, false, false};
+  for (int j = 0; j < n_mask; ++j) {
+    NFK_REQUIRE(mask[j] >= 0 && mask[j] < dim && !used[mask[j]], "%s: bad mask column %d", who, mask[j]);
+    used[mask[j]] = true;
+    a.mask[j] = mask[j];
+  }
+  for (int c = 0, u = 0; c < dim; ++c)
+    if (!used[c]) a.unm[u++] = c;
+  a.n_feat = size * (dim - n_mask);
+  a.n_tiles = (a.n_feat + WS_TF - 1) / WS_TF;
+  NFK_REQUIRE(a.n_tiles <= WS_MAX_TILES, "%s: %d transformed features exceed %d", who, a.n_feat,
+              WS_MAX_TILES * WS_TF);
+  for (int t = 0; t < a.n_tiles; ++t) a.nb[t] = WS_TF * WS_PC / 64;
+  return NFK_OK;
+}
 
 template <int EPI, int MODE, bool INVERSE, bool PAIRS = false>
 static int launch_ws(const WsArgs& a, cudaStream_t st) {
@@ -574,11 +730,13 @@ int nfk_pack_a_img(const float* x, void* img, int64_t N, int size, int dim, cons
 
 int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* out, int64_t M, int KB,
                 int kmma_last, const int32_t* tile_blocks, int n_tiles, int act, int out_f32, int n_out,
-                int64_t ldy, void* stream) {
+                int64_t ldy, const void* aux, void* stream) {
   NFK_REQUIRE(M >= 0 && KB > 0, "gemm_ws: bad shape M=%lld KB=%d", (long long)M, KB);
   NFK_REQUIRE(kmma_last >= 1 && kmma_last <= 4, "gemm_ws: kmma_last must be 1..4");
   NFK_REQUIRE(tile_blocks && n_tiles >= 1 && n_tiles <= WS_MAX_TILES, "gemm_ws: 1..%d N tiles", WS_MAX_TILES);
-  NFK_REQUIRE(act == 0 || act == 1, "gemm_ws: act must be 0 (identity) or 1 (tanh)");
+  NFK_REQUIRE(act >= 0 && act <= 2, "gemm_ws: act must be 0 (identity), 1 (tanh) or 2 (tanh backward)");
+  NFK_REQUIRE(act != 2 || (aux && !out_f32 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0),
+              "gemm_ws: act 2 needs the 16-byte aligned activation image `aux` and a bf16 image output");
   WsArgs a{};
   int ob = 0;
   for (int t = 0; t < n_tiles; ++t) {
@@ -605,6 +763,7 @@ int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* o
   a.n_tiles = n_tiles;
   a.n_out = n_out;
   a.act = act;
+  a.aux = reinterpret_cast<const unsigned char*>(aux);
   cudaStream_t st = (cudaStream_t)stream;
   return out_f32 ? launch_ws<EPI_F32_ROWS, 0, false>(a, st) : launch_ws<EPI_BF16_IMG, 0, false>(a, st);
 }
@@ -614,25 +773,10 @@ int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, con
                     int n_mask, float B, int inverse, int accumulate, int arith, void* stream) {
   NFK_REQUIRE(M >= 0 && KB > 0, "gemm_ws_rqs: bad shape M=%lld KB=%d", (long long)M, KB);
   NFK_REQUIRE(kmma_last >= 1 && kmma_last <= 4, "gemm_ws_rqs: kmma_last must be 1..4");
-  NFK_REQUIRE(size >= 1 && dim >= 2 && dim <= 4 && mask && n_mask >= 1 && n_mask < dim,
-              "gemm_ws_rqs: need 2 <= dim <= 4 and 1 <= n_mask < dim");
   NFK_REQUIRE(arith >= NFK_ARITH_EXACT && arith <= NFK_ARITH_FAST, "gemm_ws_rqs: bad arith %d", arith);
   NFK_REQUIRE(B > 0.f, "gemm_ws_rqs: tail bound must be positive");
   WsArgs a{};
-  a.dim = dim;
-  a.n_mask = n_mask;
-  bool used[4] = {false, false, false, false};
-  for (int j = 0; j < n_mask; ++j) {
-    NFK_REQUIRE(mask[j] >= 0 && mask[j] < dim && !used[mask[j]], "gemm_ws_rqs: bad mask column %d", mask[j]);
-    used[mask[j]] = true;
-    a.mask[j] = mask[j];
-  }
-  for (int c = 0, u = 0; c < dim; ++c)
-    if (!used[c]) a.unm[u++] = c;
-  a.n_feat = size * (dim - n_mask);
-  a.n_tiles = (a.n_feat + WS_TF - 1) / WS_TF;
-  NFK_REQUIRE(a.n_tiles <= WS_MAX_TILES, "gemm_ws_rqs: %d transformed features exceed %d", a.n_feat,
-              WS_MAX_TILES * WS_TF);
+  if (int rc = fill_rqs_geometry(a, size, dim, mask, n_mask, "gemm_ws_rqs")) return rc;
   if (M == 0) return NFK_OK;
   NFK_REQUIRE(a_img && w_img && bias && x && out && logdet, "gemm_ws_rqs: null device pointer");
   NFK_REQUIRE(x != out, "gemm_ws_rqs: out must not alias x");
@@ -647,7 +791,6 @@ int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, con
   a.M = M;
   a.KB = KB;
   a.kmma_last = kmma_last;
-  for (int t = 0; t < a.n_tiles; ++t) a.nb[t] = WS_TF * WS_PC / 64;
   a.x = x;
   a.logdet = logdet;
   a.accumulate = accumulate;
@@ -665,6 +808,60 @@ int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, con
   if (arith == NFK_ARITH_HYBRID) NFK_WS_RQS(NFK_ARITH_HYBRID);
   NFK_WS_RQS(NFK_ARITH_FAST);
 #undef NFK_WS_RQS
+}
+
+int nfk_gemm_ws_rqs_bwd(const void* a_img, const void* w_img, const float* bias, const float* x,
+                        const float* grad_out, const float* grad_logdet, float grad_logdet_const, float* grad_x,
+                        void* grad_params_img, int64_t M, int KB, int kmma_last, int size, int dim,
+                        const int32_t* mask, int n_mask, float B, int inverse, void* stream) {
+  NFK_REQUIRE(M >= 0 && KB > 0, "gemm_ws_rqs_bwd: bad shape M=%lld KB=%d", (long long)M, KB);
+  NFK_REQUIRE(kmma_last >= 1 && kmma_last <= 4, "gemm_ws_rqs_bwd: kmma_last must be 1..4");
+  NFK_REQUIRE(B > 0.f, "gemm_ws_rqs_bwd: tail bound must be positive");
+  WsArgs a{};
+  if (int rc = fill_rqs_geometry(a, size, dim, mask, n_mask, "gemm_ws_rqs_bwd")) return rc;
+  if (M == 0) return NFK_OK;
+  NFK_REQUIRE(a_img && w_img && bias && x && grad_out && grad_x && grad_params_img,
+              "gemm_ws_rqs_bwd: null device pointer");
+  NFK_REQUIRE(((reinterpret_cast<uintptr_t>(a_img) | reinterpret_cast<uintptr_t>(w_img) |
+                reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(grad_params_img)) & 15) == 0,
+              "gemm_ws_rqs_bwd: operand images must be 16-byte aligned");
+  a.a_img = reinterpret_cast<const unsigned char*>(a_img);
+  a.w_img = reinterpret_cast<const unsigned char*>(w_img);
+  a.bias = bias;
+  a.out = grad_params_img;
+  a.m_tiles = (M + WS_M - 1) / WS_M;
+  a.M = M;
+  a.KB = KB;
+  a.kmma_last = kmma_last;
+  a.x = x;
+  a.gout = grad_out;
+  a.gin = grad_x;
+  a.gld = grad_logdet;
+  a.gld_const = grad_logdet_const;
+  a.c = make_rqs_consts(8, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  return inverse ? launch_ws<EPI_RQS_BWD, 0, true>(a, st) : launch_ws<EPI_RQS_BWD, 0, false>(a, st);
+}
+
+int nfk_scatter_add_cols(float* g, const float* dxc, int64_t N, int size, int dim, const int32_t* cols, int n_cols,
+                         void* stream) {
+  NFK_REQUIRE(N >= 0 && size > 0 && dim > 0, "scatter_add_cols: bad shape");
+  NFK_REQUIRE(cols && n_cols >= 1 && n_cols <= 4, "scatter_add_cols: 1..4 columns supported");
+  int c[4] = {0, 0, 0, 0};
+  for (int i = 0; i < n_cols; ++i) {
+    NFK_REQUIRE(cols[i] >= 0 && cols[i] < dim, "scatter_add_cols: column %d outside [0,%d)", cols[i], dim);
+    c[i] = cols[i];
+  }
+  if (N == 0) return NFK_OK;
+  NFK_REQUIRE(g && dxc, "scatter_add_cols: null device pointer");
+  const long long total = (long long)N * size * n_cols;
+  long long grid = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  scatter_add_cols_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(g, dxc, N, size, dim, n_cols, c[0], c[1],
+                                                                          c[2], c[3]);
+  count_launch();
+  return check_launch("scatter_add_cols");
 }
 
 }  // extern "C"

@@ -131,6 +131,9 @@ class FlowSimulation:
         self.inv_mass = 1.0 / float(mass)
         self.velocity = torch.zeros_like(self.position)
         self.grad_evals = 0
+        self.tensor_core_grad = True      # bf16-conditioner models: hand-written forward+backward path
+        self.use_graph = True             # replay whole trajectories as one CUDA graph on that path
+        self._graphs = {}
 
     # duck type ---------------------------------------------------------------------------
     def get_position(self):
@@ -150,6 +153,14 @@ class FlowSimulation:
 
     def potential_and_force(self, q):
         """U(q) [C] and F(q) = -grad U = grad log p [C, d] — one forward + one backward through the flow."""
+        from . import _wide
+        fast = _wide.flow_logp_and_grad(self.model, q) if self.tensor_core_grad else None
+        if fast is not None:
+            # forward keeps the hidden activations, backward = spline adjoint as a GEMM epilogue +
+            # dgrad GEMMs on the tensor cores (csrc/gemm_ws.cu); no autograd graph
+            logp, force = fast
+            self.grad_evals += 1
+            return -logp, force
         params = [p for p in self.model.parameters() if p.requires_grad]
         for p in params:
             p.requires_grad_(False)              # dgrad only: no weight gradients in the leapfrog
@@ -165,6 +176,48 @@ class FlowSimulation:
         self.grad_evals += 1
         return -logp.detach(), force.contiguous()
 
+    # ---- whole trajectory as one CUDA graph -------------------------------------------------
+    def _trajectory(self, q, p, path_len, dt):
+        pot, force = self.potential_and_force(q)
+        for _ in range(path_len):
+            _ops.leapfrog_kick_drift(q, p, force, dt, self.inv_mass)
+            pot, force = self.potential_and_force(q)
+            _ops.leapfrog_kick(p, force, dt)
+        return pot
+
+    def _graph_trajectory(self, path_len, dt):
+        """The leapfrog trajectory (path_len + 1 log-prob+grad evaluations, ~75 launches each) is a
+        fixed launch sequence on fixed buffers: capture it once per (path_len, dt, parameter
+        version) and replay it, so the GPU is never waiting on the host."""
+        from . import _wide
+        if not _wide.flow_grad_eligible(self.model):
+            return None
+        key = (path_len, dt, self.n_chains, tuple(p._version for p in self.model.parameters()))
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs.clear()
+            q = self.position.clone()
+            p = self.velocity.clone()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                       # warm-up: weight images, kernel attributes
+                self._trajectory(q.clone(), p.clone(), 1, dt)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            evals = self.grad_evals
+            with torch.cuda.graph(graph):
+                pot = self._trajectory(q, p, path_len, dt)
+            self.grad_evals = evals
+            entry = self._graphs[key] = (graph, q, p, pot)
+        graph, q, p, pot = entry
+        q.copy_(self.position)
+        p.copy_(self.velocity)
+        graph.replay()
+        self.grad_evals += path_len + 1
+        self.position = q.clone()
+        self.velocity = p.clone()
+        return self.position, pot.clone()
+
     def integration_step(self, path_len=1, dt=0.005, init_pos=None, init_velocity=None):
         if init_pos is not None:
             self.set_position(init_pos)
@@ -172,6 +225,10 @@ class FlowSimulation:
             self.set_velocity(init_velocity)
         if dt is None:
             dt = 0.005
+        if self.tensor_core_grad and self.use_graph:
+            out = self._graph_trajectory(int(path_len), float(dt))
+            if out is not None:
+                return out
         q, p = self.position, self.velocity       # unit-mass convention: p is the velocity
         pot, force = self.potential_and_force(q)
         for _ in range(path_len):

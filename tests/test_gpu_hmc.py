@@ -74,3 +74,66 @@ def test_batched_hmc_through_reference_driver_interface():
     # the reference's acceptance rule ignores the kinetic energy (Q12), so chains can only keep or
     # lower their potential on average: the batch mean must not increase
     assert float(pot[-1].mean()) <= float(pot[0].mean()) + 1e-3
+
+
+def test_tensor_core_force_matches_autograd_and_oracle():
+    """bf16-conditioner model: the hand-written forward+backward path (spline adjoint as a GEMM
+    epilogue + dgrad GEMMs, csrc/gemm_ws.cu) vs autograd through the same model, and vs torch
+    autograd through the fp32 oracle (1e-2 class of the bf16 conditioner)."""
+    from normalizingflow_b200 import _wide
+    from normalizingflow_b200.hmc import FlowSimulation
+    from oracle import nf_oracle as O
+    m = _model(precision="bf16")
+    g = golden("models.npz")
+    x = T(g["nsf.x"])
+    assert _wide.flow_logp_and_grad(m, x.cuda()) is not None
+    sim = FlowSimulation(m, n_chains=x.shape[0], init_pos=x)
+    U, F = sim.potential_and_force(sim.get_position())
+    sim.tensor_core_grad = False
+    U2, F2 = sim.potential_and_force(sim.get_position())
+    scale = float(F2.abs().max())
+    assert rel_err(U, U2.double().cpu()) <= 2e-3
+    assert float((F - F2).abs().max()) <= 2e-2 * scale
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    specs = [dict(type="NSF_CL", size=32, dim=2, K=8, B=3.0, mask=[i % 2]) for i in range(8)]
+    xr = x.clone().requires_grad_()
+    z, plp, ld = O.flow_forward(specs, sd, xr)
+    (gref,) = torch.autograd.grad((plp + ld).sum(), xr)
+    assert rel_err(-U, (plp + ld).detach()) <= 1e-2
+    # d logdet / dx is discontinuous across knots (the spline is C1): the bf16 conditioner moves the
+    # knots by ~1e-3, so a few elements next to a knot see another bin's second derivative -- gate
+    # the bulk, not the maximum
+    err = (F.cpu() - gref).abs() / (1.0 + gref.abs())
+    assert float(err.median()) <= 5e-3, float(err.median())
+    assert float((err > 3e-2).float().mean()) <= 8e-2, float((err > 3e-2).float().mean())
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("size,dim,mask,H", [(32, 2, [1], 200), (38, 3, [0, 2], 160), (38, 3, [1], 96)])
+def test_layer_backward_matches_autograd(inverse, size, dim, mask, H):
+    """One layer: dL/dx from the tensor-core backward vs autograd through the unfused kernels of
+    the SAME bf16-conditioner layer (same hidden activations, fp32 dgrad), for
+    L = sum(out * r) + sum(logdet * s) with random r, s."""
+    from normalizingflow_b200 import _wide, flows
+    torch.manual_seed(7)
+    lay = flows.NSF_CL(size, dim=dim, K=8, B=3.0, hidden_dim=H, mask=mask).cuda()
+    with torch.no_grad():
+        lay.psi.network[4].weight.mul_(3.0)
+    lay.psi.precision = "bf16"
+    N, d = 900, size * dim
+    gen = torch.Generator().manual_seed(11)
+    x = (1.2 * torch.randn(N, d, generator=gen)).cuda()
+    r = torch.randn(N, d, generator=gen).cuda()
+    s = torch.randn(N, generator=gen).cuda()
+    xg = x.clone().requires_grad_()
+    out, ld = (lay.inverse if inverse else lay.forward)(xg)          # autograd Functions (unfused)
+    (gref,) = torch.autograd.grad((out * r).sum() + (ld * s).sum(), xg)
+    assert _wide.grad_eligible(lay)
+    with torch.no_grad():
+        o2, l2, ctx = _wide.layer_forward_saving(lay, x, inverse)
+        gin = _wide.layer_backward(lay, ctx, r, s)
+    assert rel_err(o2.cpu(), out.detach().double().cpu()) <= 2e-3
+    assert rel_err(l2.cpu(), ld.detach().double().cpu()) <= 5e-3
+    err = (gin - gref).abs() / (1.0 + gref.abs())
+    assert float(err.median()) <= 2e-3, float(err.median())
+    assert float((err > 3e-2).float().mean()) <= 5e-3, float((err > 3e-2).float().mean())

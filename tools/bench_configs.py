@@ -101,7 +101,7 @@ def cfg5(C, H, precision):
     torch.cuda.synchronize()
     n0 = sim.grad_evals
     t0 = time.perf_counter()
-    pos, pot, logp, acc = h.hmc(epochs=3)
+    pos, pot, logp, acc = h.hmc(epochs=5)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     evals = sim.grad_evals - n0
