@@ -378,6 +378,9 @@ radial_dot_kernel(const float* __restrict__ x, const float* __restrict__ x0, con
   }
 }
 
+// Persistent over rows (grid-stride): a thread keeps its columns' share of grad_x0 in registers
+// (d <= 8 G) or in shared-memory atomics (wider rows), the block folds them in shared memory and
+// issues ONE global atomic per column -- not one per element.
 template <int G>
 __global__ void __launch_bounds__(256)
 radial_bwd_kernel(const float* __restrict__ x, const float* __restrict__ x0,
@@ -386,64 +389,97 @@ radial_bwd_kernel(const float* __restrict__ x, const float* __restrict__ x0,
                   const float* __restrict__ gz, const float* __restrict__ gld, float* __restrict__ gx,
                   float* __restrict__ gx0, float* __restrict__ gla, float* __restrict__ gbeta,
                   long long N, int d, int per_sample) {
-  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x);
-  const long long row = gid / G;
-  const int g = (int)(gid % G);
-  const bool live = row < N;
+  extern __shared__ float s_gx0[];                           // [d]
+  for (int i = threadIdx.x; i < d; i += blockDim.x) s_gx0[i] = 0.f;
+  __syncthreads();
+  constexpr int RPB = 256 / G;                               // rows per block and pass
+  const int g = threadIdx.x % G, lr = threadIdx.x / G;
+  const bool in_regs = d <= 8 * G;
+  float acc0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float a_acc = 0.f, b_acc = 0.f;
   const float alpha = expf(log_alpha[0]);
   const float braw = beta_raw[0];
   const float beta = -alpha + logf(1.f + expf(braw));
-  float r, S1, gl;
-  if (per_sample) {
-    float a2 = 0.f, a1 = 0.f;
-    if (live)
-      for (int j = g; j < d; j += G) {
-        const float df = x[row * d + j] - x0[j];
-        a2 = fmaf(df, df, a2);
-        a1 = fmaf(gz[row * d + j], df, a1);
-      }
-    r = sqrtf(group_sum<G>(a2));
-    S1 = group_sum<G>(a1);
-    gl = (live && gld) ? gld[row] : 0.f;
-  } else {
-    r = sqrtf(sumsq[0]);
-    S1 = dot[0];
-    gl = gld ? gld[0] : 0.f;
-  }
-  const float A = alpha + r, h = 1.f / A;
-  const float p = 1.f + beta * h, qv = 1.f + beta * h - beta * r * h * h;
   const float n1 = (float)(d - 1);
-  // ld = (n-1) log p + log q  (flows_1.py:94-95)
-  float g_h = beta * S1 + gl * (n1 * beta / p + (beta - 2.f * beta * r * h) / qv);
-  float g_b = h * S1 + gl * (n1 * h / p + (h - r * h * h) / qv);
-  float g_r = gl * (-beta * h * h) / qv;
-  const float g_A = -g_h * h * h;
-  g_r += g_A;
-  float g_alpha = g_A - g_b;                                 // beta = -alpha + softplus(braw)
-  const float g_braw = g_b / (1.f + expf(-braw));
-  const float scale = 1.f + beta * h;
-  const float rinv = r > 0.f ? 1.f / r : 0.f;
-  if (live) {
-    for (int j = g; j < d; j += G) {
-      const float df = x[row * d + j] - x0[j];
-      const float v = gz[row * d + j] * scale + g_r * df * rinv;
-      gx[row * d + j] = v;
-      // z = x + beta h (x - x0): d/dx0 = -(beta h gz) - g_r df / r
-      atomicAdd(gx0 + j, -(gz[row * d + j] * beta * h) - g_r * df * rinv);
+  for (long long row0 = (long long)blockIdx.x * RPB; row0 < N; row0 += (long long)gridDim.x * RPB) {
+    const long long row = row0 + lr;
+    const bool live = row < N;
+    float r, S1, gl;
+    if (per_sample) {
+      float a2 = 0.f, a1 = 0.f;
+      if (live)
+        for (int j = g; j < d; j += G) {
+          const float df = x[row * d + j] - x0[j];
+          a2 = fmaf(df, df, a2);
+          a1 = fmaf(gz[row * d + j], df, a1);
+        }
+      r = sqrtf(group_sum<G>(a2));
+      S1 = group_sum<G>(a1);
+      gl = (live && gld) ? gld[row] : 0.f;
+    } else {
+      r = sqrtf(sumsq[0]);
+      S1 = dot[0];
+      gl = gld ? gld[0] : 0.f;
+    }
+    const float A = alpha + r, h = 1.f / A;
+    const float p = 1.f + beta * h, qv = 1.f + beta * h - beta * r * h * h;
+    // ld = (n-1) log p + log q  (flows_1.py:94-95)
+    float g_h = beta * S1 + gl * (n1 * beta / p + (beta - 2.f * beta * r * h) / qv);
+    float g_b = h * S1 + gl * (n1 * h / p + (h - r * h * h) / qv);
+    float g_r = gl * (-beta * h * h) / qv;
+    const float g_A = -g_h * h * h;
+    g_r += g_A;
+    const float g_alpha = g_A - g_b;                           // beta = -alpha + softplus(braw)
+    const float g_braw = g_b / (1.f + expf(-braw));
+    const float scale = 1.f + beta * h;
+    const float rinv = r > 0.f ? 1.f / r : 0.f;
+    if (live) {
+      if (in_regs) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int j = g + c * G;
+          if (j < d) {
+            const float df = x[row * d + j] - x0[j];
+            const float gzv = gz[row * d + j];
+            gx[row * d + j] = gzv * scale + g_r * df * rinv;
+            // z = x + beta h (x - x0): d/dx0 = -(beta h gz) - g_r df / r
+            acc0[c] += -(gzv * beta * h) - g_r * df * rinv;
+          }
+        }
+      } else {
+        for (int j = g; j < d; j += G) {
+          const float df = x[row * d + j] - x0[j];
+          const float gzv = gz[row * d + j];
+          gx[row * d + j] = gzv * scale + g_r * df * rinv;
+          atomicAdd(&s_gx0[j], -(gzv * beta * h) - g_r * df * rinv);
+        }
+      }
+    }
+    if (per_sample) {
+      if (live && g == 0) {
+        a_acc += g_alpha * alpha;
+        b_acc += g_braw;
+      }
+    } else if (row0 == 0 && threadIdx.x == 0) {              // batch-global: one value for the whole batch
+      a_acc = g_alpha * alpha;
+      b_acc = g_braw;
     }
   }
-  if (per_sample) {
-    float a = (live && g == 0) ? g_alpha * alpha : 0.f, b = (live && g == 0) ? g_braw : 0.f;
-    a = warp_sum(a);
-    b = warp_sum(b);
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(gla, a);
-      atomicAdd(gbeta, b);
+  if (in_regs) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = g + c * G;
+      if (j < d) atomicAdd(&s_gx0[j], acc0[c]);
     }
-  } else if (gid == 0) {
-    atomicAdd(gla, g_alpha * alpha);
-    atomicAdd(gbeta, g_braw);
   }
+  a_acc = warp_sum(a_acc);
+  b_acc = warp_sum(b_acc);
+  if ((threadIdx.x & 31) == 0 && (a_acc != 0.f || b_acc != 0.f)) {
+    atomicAdd(gla, a_acc);
+    atomicAdd(gbeta, b_acc);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) atomicAdd(gx0 + i, s_gx0[i]);
 }
 
 // ---- log-prob reduction (nf/models.py:19-20, :34, :39) --------------------------------------
@@ -727,10 +763,12 @@ int nfk_radial_bwd(const float* x, const float* x0, const float* log_alpha, cons
               "radial_bwd: null device pointer");
   NFK_REQUIRE(per_sample || (sumsq && dot), "radial_bwd: batch-global mode needs sumsq and dot");
   const int G = pick_group(d);
-  const long long threads = (long long)N * G;
-  const unsigned grid = (unsigned)((threads + 255) / 256);
+  NFK_REQUIRE((size_t)d * sizeof(float) <= 48 * 1024, "radial_bwd: d = %d exceeds the shared-memory accumulator", d);
+  const long long blocks_needed = ((long long)N * G + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);
   cudaStream_t st = (cudaStream_t)stream;
-  NFK_GROUP_SWITCH(G, (radial_bwd_kernel<GG><<<grid, 256, 0, st>>>(x, x0, log_alpha, beta, sumsq, dot, grad_out,
+  NFK_GROUP_SWITCH(G, (radial_bwd_kernel<GG><<<grid, 256, d * sizeof(float), st>>>(x, x0, log_alpha, beta, sumsq, dot, grad_out,
                                                                     grad_logdet, grad_x, grad_x0, grad_log_alpha,
                                                                     grad_beta, N, d, per_sample)));
   count_launch();
