@@ -149,6 +149,57 @@ def test_fused_weight_image_is_the_sw128_layout():
                 assert torch.equal(src, dst)
 
 
+def test_wide_path_tile_plan_and_operand_images():
+    """Host logic of the wide conditioner path (_wide.py): N-tile plan, weight / activation images
+    (the SWIZZLE_128B shared-memory layout stored in HBM) and argument checks of its entry points."""
+    import ctypes
+    from normalizingflow_b200 import _lib, _wide
+    for nblk in range(1, 40):
+        tiles = _wide.plan_tiles(nblk)
+        assert sum(tiles) == nblk and max(tiles) <= 4 and min(tiles) >= 1
+        assert len(tiles) == (nblk + 3) // 4 and max(tiles) - min(tiles) <= 1
+    assert _wide.plan_tiles(13) == [4, 3, 3, 3]                       # hidden 800 -> 832 padded columns
+    # weight image: tile t, K block kb, row r, chunk slot j holds W[row0_t + r, kb*64 + (j ^ r%8)*8 ...]
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(100, 70, generator=g)
+    b = torch.randn(100, generator=g)
+    tiles = _wide.plan_tiles(_wide.blocks(100))                        # 2 blocks -> one tile
+    img, bp = _wide.weight_image(w, b, _wide.blocks(70), tiles)
+    assert img.numel() == 128 * 128 and bp.shape == (128,)
+    assert torch.equal(bp[:100], b) and float(bp[100:].abs().sum()) == 0.0
+    im = img.reshape(2, 128, 8, 8)
+    wb = torch.zeros(128, 128, dtype=torch.bfloat16)
+    wb[:100, :70] = w.to(torch.bfloat16)
+    for kb in range(2):
+        for r in (0, 5, 63, 99, 127):
+            for j in range(8):
+                c = j ^ (r & 7)
+                assert torch.equal(im[kb, r, j], wb[r, kb * 64 + c * 8: kb * 64 + c * 8 + 8])
+    # image_to_rows inverts the activation image layout
+    rows = torch.randn(300, 192, generator=g).to(torch.bfloat16)
+    pad = torch.zeros(384, 192, dtype=torch.bfloat16)
+    pad[:300] = rows
+    a_img = torch.stack([_wide._swizzle_image(pad[m * 128:(m + 1) * 128]) for m in range(3)]).reshape(3, 3, 128, 64)
+    assert torch.equal(_wide.image_to_rows(a_img, 300, 192), rows)
+    # argument errors are caught on the host (NFK_EINVAL), before any launch
+    L = _lib.lib
+    tiles_c = (ctypes.c_int32 * 1)(5)
+    assert L.nfk_gemm_ws(None, None, None, None, 128, 1, 4, tiles_c, 1, 1, 0, 0, 0, None, None) == _lib.NFK_EINVAL
+    tiles_c = (ctypes.c_int32 * 1)(4)
+    assert L.nfk_gemm_ws(None, None, None, None, 128, 1, 7, tiles_c, 1, 1, 0, 0, 0, None, None) == _lib.NFK_EINVAL
+    assert L.nfk_gemm_ws(None, None, None, None, 128, 1, 4, tiles_c, 1, 2, 0, 0, 0, None, None) == _lib.NFK_EINVAL
+    assert L.nfk_gemm_ws(None, None, None, None, 0, 1, 4, tiles_c, 1, 1, 0, 0, 0, None, None) == 0
+    mask = (ctypes.c_int32 * 1)(3)
+    rc = L.nfk_gemm_ws_rqs(None, None, None, None, None, None, 128, 13, 2, 32, 2, mask, 1, 3.0, 0, 0, 2, None)
+    assert rc == _lib.NFK_EINVAL and b"mask" in L.nfk_last_error()
+    mask = (ctypes.c_int32 * 1)(1)
+    rc = L.nfk_gemm_ws_rqs(None, None, None, None, None, None, 128, 13, 2, 200, 2, mask, 1, 3.0, 0, 0, 2, None)
+    assert rc == _lib.NFK_EINVAL and b"exceed" in L.nfk_last_error()
+    assert L.nfk_gemm_ws_rqs_bwd(None, None, None, None, None, None, 1.0, None, None, 0, 13, 2, 32, 2, mask, 1, 3.0,
+                                 0, None) == 0
+    assert L.nfk_gemm_ws_rows_per_tile() == 128
+
+
 def test_shard_rows_partitions_the_batch():
     from normalizingflow_b200.dist import shard_rows
     for n, w in ((1 << 20, 8), (10, 3), (7, 8), (0, 2)):
