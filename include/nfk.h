@@ -83,6 +83,18 @@ int nfk_unconstrained_rqs(const float* inputs, const float* W, const float* H, c
                           float* out, float* lad, int8_t* bins, int64_t M, int K, float B,
                           int inverse, int arith, void* stream);
 
+/* ---- element-wise spline with the layer-side normalisation: the transform step of the
+ * autoregressive spline flow NSF_AR (nf/flows.py:178-190 forward, :196-208 inverse): softmax x 2B on
+ * W,H and softplus on D (flows.py:183-185), then unconstrained_RQS (nf/utils.py:27-152).
+ * inputs [M], params [M, 3K-1] raw conditioner outputs -> out [M], lad [M], bins [M] (nullable). */
+int nfk_rqs_elementwise(const float* inputs, const float* params, float* out, float* lad,
+                        int8_t* bins, int64_t M, int K, float B, int inverse, int arith,
+                        void* stream);
+/* backward: grad_out [M], grad_lad [M] (nullable = 0) -> grad_in [M], grad_params [M, 3K-1] */
+int nfk_rqs_elementwise_bwd(const float* inputs, const float* params, const float* grad_out,
+                            const float* grad_lad, float* grad_in, float* grad_params, int64_t M,
+                            int K, float B, int inverse, void* stream);
+
 /* ---- affine half-coupling: y = t + v*exp(s) (forward) or (v - t)*exp(-s) (inverse),
  * logdet (+)= +-sum_j s.  Replaces nf/flows.py:56, :59, :61-62 and :69, :72, :74-75.
  * v is read from x[:, v_off : v_off+h] (row stride ld_x), s,t are [N,h] contiguous, y is

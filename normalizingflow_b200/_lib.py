@@ -38,6 +38,8 @@ SIGNATURES = {
     "nfk_rqs_coupling": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_float,
                                  c_int, c_int, c_int, _P]),
     "nfk_unconstrained_rqs": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int, _P]),
+    "nfk_rqs_elementwise": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int, _P]),
+    "nfk_rqs_elementwise_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, _P]),
     "nfk_affine_halfcoupling": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int64, c_int, _P, c_int64, c_int,
                                         c_int, c_int, _P]),
     "nfk_affine_halfcoupling_bwd": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int64, c_int, _P, _P, c_int64,

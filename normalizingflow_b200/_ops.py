@@ -118,6 +118,49 @@ class RqsCouplingFn(torch.autograd.Function):
         return gx.view_as(x), gp.view_as(params), None, None, None, None, None, None, None
 
 
+def rqs_elementwise(inputs, params, K: int, B: float, inverse: bool, arith=DEFAULT_ARITH, want_bins=False):
+    """Element-wise spline on raw conditioner outputs (NSF_AR, nf/flows.py:178-190 / :196-208):
+    inputs [...], params [..., 3K-1] -> (out [...], lad [...], bins | None)."""
+    dev = require_cuda(inputs, params)
+    P = 3 * K - 1
+    M = inputs.numel()
+    if params.numel() != M * P:
+        raise ValueError(f"params has {params.numel()} elements, expected {M}*{P}")
+    shape = inputs.shape
+    inputs, params = f32c(inputs), f32c(params)
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
+    lad = torch.empty(shape, dtype=torch.float32, device=dev)
+    bins = torch.empty(shape, dtype=torch.int8, device=dev) if want_bins else None
+    with torch.cuda.device(dev):
+        call("nfk_rqs_elementwise", ptr(inputs), ptr(params), ptr(out), ptr(lad), ptr(bins), M, K, float(B),
+             int(bool(inverse)), _arith(arith), stream_ptr(dev))
+    return out, lad, bins
+
+
+class RqsElementwiseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, params, K, B, inverse, arith):
+        out, lad, _ = rqs_elementwise(inputs, params, K, B, inverse, arith)
+        ctx.save_for_backward(inputs, params)
+        ctx.cfg = (K, B, inverse)
+        return out, lad
+
+    @staticmethod
+    def backward(ctx, g_out, g_lad):
+        inputs, params = ctx.saved_tensors
+        K, B, inverse = ctx.cfg
+        dev = inputs.device
+        xi, pp = f32c(inputs), f32c(params)
+        g_out = f32c(g_out) if g_out is not None else torch.zeros_like(xi)
+        g_lad = f32c(g_lad) if g_lad is not None else None
+        gi = torch.empty_like(xi)
+        gp = torch.empty_like(pp)
+        with torch.cuda.device(dev):
+            call("nfk_rqs_elementwise_bwd", ptr(xi), ptr(pp), ptr(g_out), ptr(g_lad), ptr(gi), ptr(gp), xi.numel(), K,
+                 float(B), int(bool(inverse)), stream_ptr(dev))
+        return gi.view_as(inputs), gp.view_as(params), None, None, None, None
+
+
 def unconstrained_rqs(inputs, W, H, D, inverse: bool, B: float, arith=DEFAULT_ARITH, want_bins=False):
     """nf/utils.py:27-56 on tensors inputs [...], W,H [...,K], D [...,K-1]."""
     dev = require_cuda(inputs, W, H, D)

@@ -64,6 +64,28 @@ __global__ void __launch_bounds__(128) rqs_coupling_bwd_kernel(const __grid_cons
   }
 }
 
+// backward of rqs_elementwise_kernel: one thread per scalar
+template <int KT>
+__global__ void __launch_bounds__(128)
+rqs_elementwise_bwd_kernel(const float* __restrict__ inputs, const float* __restrict__ params,
+                           const float* __restrict__ gout, const float* __restrict__ glad,
+                           float* __restrict__ gin, float* __restrict__ gparams, long long M, int inverse,
+                           RqsConsts c) {
+  constexpr int KK = KT ? KT : KMAX;
+  const int K = KT ? KT : c.K;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M) return;
+  const int P = 3 * K - 1;
+  float gxv;
+  float gpl[3 * KK - 1];
+  rqs_element_bwd<KT>(PtrParams{params + e * P}, inputs[e], gout[e], glad ? glad[e] : 0.f, inverse != 0, c, gxv,
+                      gpl);
+  gin[e] = gxv;
+#pragma unroll
+  for (int i = 0; i < 3 * KK - 1; ++i)
+    if (i < P) gparams[e * P + i] = gpl[i];
+}
+
 int fill_coupling_geometry_bwd(BwdArgs& a, int size, int dim, const int32_t* mask, int n_mask, int K) {
   NFK_REQUIRE(size > 0 && dim > 1 && dim <= BW_MAXDIM, "rqs_coupling_bwd: need size > 0 and 2 <= dim <= %d",
               BW_MAXDIM);
@@ -123,4 +145,25 @@ extern "C" int nfk_rqs_coupling_bwd(const float* x, const float* params, const f
     rqs_coupling_bwd_kernel<0><<<(unsigned)grid, 128, 0, st>>>(a);
   count_launch();
   return check_launch("rqs_coupling_bwd");
+}
+
+extern "C" int nfk_rqs_elementwise_bwd(const float* inputs, const float* params, const float* grad_out,
+                                       const float* grad_lad, float* grad_in, float* grad_params, int64_t M,
+                                       int K, float B, int inverse, void* stream) {
+  NFK_REQUIRE(M >= 0, "rqs_elementwise_bwd: negative size");
+  NFK_REQUIRE(K >= 2 && K <= KMAX, "rqs_elementwise_bwd: 2 <= K <= %d supported", KMAX);
+  NFK_REQUIRE(B > 0.f, "rqs_elementwise_bwd: tail bound must be positive");
+  if (M == 0) return NFK_OK;
+  NFK_REQUIRE(inputs && params && grad_out && grad_in && grad_params, "rqs_elementwise_bwd: null device pointer");
+  const RqsConsts c = make_rqs_consts(K, B);
+  const unsigned grid = (unsigned)((M + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K == 8)
+    rqs_elementwise_bwd_kernel<8><<<grid, 128, 0, st>>>(inputs, params, grad_out, grad_lad, grad_in, grad_params, M,
+                                                        inverse, c);
+  else
+    rqs_elementwise_bwd_kernel<0><<<grid, 128, 0, st>>>(inputs, params, grad_out, grad_lad, grad_in, grad_params, M,
+                                                        inverse, c);
+  count_launch();
+  return check_launch("rqs_elementwise_bwd");
 }

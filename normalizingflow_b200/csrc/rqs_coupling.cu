@@ -284,6 +284,29 @@ unconstrained_rqs_kernel(const float* __restrict__ inputs, const float* __restri
   if (bins) bins[e] = (int8_t)o.bin;
 }
 
+// Element-wise spline with the LAYER-side normalisation (softmax x 2B, softplus) applied to packed raw
+// parameters [M, 3K-1]: the transform step of the autoregressive spline flow NSF_AR (reference
+// nf/flows.py:178-190, :196-208), one thread per scalar.
+struct PackedPtr {
+  const float* p;
+  __device__ __forceinline__ float operator()(int i) const { return __ldg(p + i); }
+  __device__ __forceinline__ float dyn(int base, int i) const { return __ldg(p + base + i); }
+};
+
+template <int MODE, int KT, bool INVERSE>
+__global__ void __launch_bounds__(128)
+rqs_elementwise_kernel(const float* __restrict__ inputs, const float* __restrict__ params,
+                       float* __restrict__ out, float* __restrict__ lad, int8_t* __restrict__ bins,
+                       long long M, RqsConsts c) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M) return;
+  const int K = KT ? KT : c.K;
+  const RqsOut o = rqs_element<MODE, KT, INVERSE, true>(PackedPtr{params + e * (3 * K - 1)}, inputs[e], c);
+  out[e] = o.y;
+  lad[e] = o.lad;
+  if (bins) bins[e] = (int8_t)o.bin;
+}
+
 template <bool EXACT, int KT, bool LAYER_NORM>
 __global__ void __launch_bounds__(128)
 debug_knots_kernel(const float* __restrict__ logits, float* __restrict__ knots, long long M,
@@ -451,6 +474,15 @@ static int launch_free(const float* inputs, const float* W, const float* H, cons
   return check_launch("unconstrained_rqs");
 }
 
+template <int MODE, int KT, bool INVERSE>
+static int launch_elementwise(const float* inputs, const float* params, float* out, float* lad, int8_t* bins,
+                              long long M, RqsConsts c, cudaStream_t st) {
+  const long long grid = (M + 127) / 128;
+  rqs_elementwise_kernel<MODE, KT, INVERSE><<<(unsigned)grid, 128, 0, st>>>(inputs, params, out, lad, bins, M, c);
+  count_launch();
+  return check_launch("rqs_elementwise");
+}
+
 static int dispatch_coupling(int mode, int K, int inverse, CouplingArgs& a, long long N,
                              cudaStream_t st) {
   NFK_DISPATCH_MODE_K_INV(launch_coupling, mode, K, inverse, a, N, st);
@@ -459,6 +491,11 @@ static int dispatch_free(int mode, int K, int inverse, const float* inputs, cons
                          const float* H, const float* D, float* out, float* lad, int8_t* bins,
                          long long M, RqsConsts c, cudaStream_t st) {
   NFK_DISPATCH_MODE_K_INV(launch_free, mode, K, inverse, inputs, W, H, D, out, lad, bins, M, c, st);
+}
+
+static int dispatch_elementwise(int mode, int K, int inverse, const float* inputs, const float* params, float* out,
+                                float* lad, int8_t* bins, long long M, RqsConsts c, cudaStream_t st) {
+  NFK_DISPATCH_MODE_K_INV(launch_elementwise, mode, K, inverse, inputs, params, out, lad, bins, M, c, st);
 }
 
 int fill_coupling_geometry(CouplingArgs& a, int size, int dim, const int32_t* mask, int n_mask,
@@ -541,6 +578,20 @@ int nfk_unconstrained_rqs(const float* inputs, const float* W, const float* H, c
   NFK_REQUIRE(inputs && W && H && D && out && lad, "unconstrained_rqs: null device pointer");
   return dispatch_free(arith, K, inverse, inputs, W, H, D, out, lad, bins, M, make_consts(K, B),
                        (cudaStream_t)stream);
+}
+
+int nfk_rqs_elementwise(const float* inputs, const float* params, float* out, float* lad, int8_t* bins,
+                        int64_t M, int K, float B, int inverse, int arith, void* stream) {
+  NFK_REQUIRE(M >= 0, "rqs_elementwise: negative size");
+  NFK_REQUIRE(K >= 2 && K <= KMAX, "rqs_elementwise: 2 <= K <= %d supported (got %d)", KMAX, K);
+  NFK_REQUIRE(1e-3 * K <= 1.0, "Minimal bin width too large for the number of bins");
+  NFK_REQUIRE(arith >= NFK_ARITH_EXACT && arith <= NFK_ARITH_FAST, "rqs_elementwise: bad arith");
+  NFK_REQUIRE(B > 0.f, "rqs_elementwise: tail bound must be positive");
+  if (M == 0) return NFK_OK;
+  NFK_REQUIRE(inputs && params && out && lad, "rqs_elementwise: null device pointer");
+  NFK_REQUIRE(M < (1LL << 31) * 128, "rqs_elementwise: too many elements");
+  return dispatch_elementwise(arith, K, inverse, inputs, params, out, lad, bins, M, make_consts(K, B),
+                              (cudaStream_t)stream);
 }
 
 int nfk_debug_knots(const float* logits, float* knots, int64_t M, int K, float B, int layer_norm,

@@ -4,6 +4,7 @@ Constructor signatures, attribute names and state-dict keys follow the reference
 checkpoints load with ``load_state_dict``:
   FCNN      network.{0,2,4}.{weight,bias}          nf/flows.py:20-35
   RealNVP   {t1,s1,t2,s2}.network.*                nf/flows.py:38-76
+  NSF_AR    init_param, layers.{i}.network.*       nf/flows.py:152-209
   NSF_CL    psi.network.*                          nf/flows.py:210-253
   Planar    w, u, b                                nf/flows_1.py:21-63
   Radial    x0, log_alpha, beta                    nf/flows_1.py:66-97
@@ -19,7 +20,7 @@ import torch.nn.init as init
 
 from . import _ops
 
-__all__ = ["FCNN", "RealNVP", "NSF_CL", "Planar", "Radial", "PlanarStack"]
+__all__ = ["FCNN", "RealNVP", "NSF_AR", "NSF_CL", "Planar", "Radial", "PlanarStack"]
 
 
 class FCNN(nn.Module):
@@ -83,6 +84,71 @@ class RealNVP(nn.Module):
         t1, s1 = self.t1(lower), self.s1(lower)
         upper, ld1 = _ops.AffineHalfFn.apply(upper, s1, t1, True)        # flows.py:72
         return torch.cat([lower, upper], dim=1), ld1 + ld2               # flows.py:73-75
+
+
+class NSF_AR(nn.Module):
+    """Autoregressive neural spline flow (nf/flows.py:152-209): dimension i is transformed by an RQS
+    whose 3K-1 parameters come from ``layers[i-1]`` applied to [cos, sin](pi x[:, :i] / B)
+    (``trig_transform``, flows.py:172-173); dimension 0 uses the learned ``init_param``.
+
+    forward (x -> z) needs only known inputs, so all dim conditioners run back to back and ONE
+    element-wise spline launch transforms every column; inverse (z -> x) is inherently sequential
+    (flows.py:196-208): dim conditioner + spline steps.
+    """
+
+    def __init__(self, dim, K=32, B=3, hidden_dim=800, base_network=FCNN, device="cpu", arith=_ops.DEFAULT_ARITH):
+        super().__init__()
+        self.dim = dim
+        self.K = K
+        self.B = B
+        self.device = device
+        self.arith = arith
+        self.layers = nn.ModuleList()
+        self.init_param = nn.Parameter(torch.Tensor(3 * K - 1))
+        for i in range(1, dim):
+            self.layers += [base_network(2 * i, 3 * K - 1, hidden_dim)]
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        init.uniform_(self.init_param, -1 / 2, 1 / 2)
+
+    def trig_transform(self, x):
+        pi = torch.tensor(math.pi, dtype=torch.float32, device=x.device)
+        return torch.cat((torch.cos(pi * x / self.B), torch.sin(pi * x / self.B)), dim=-1)
+
+    def _spline(self, v, params, inverse):
+        if torch.is_grad_enabled() and (v.requires_grad or params.requires_grad):
+            return _ops.RqsElementwiseFn.apply(v, params, self.K, float(self.B), inverse, self.arith)
+        out, lad, _ = _ops.rqs_elementwise(v, params, self.K, float(self.B), inverse, self.arith)
+        return out, lad
+
+    def forward(self, x):
+        N = x.shape[0]
+        P = 3 * self.K - 1
+        pi = torch.tensor(math.pi, dtype=torch.float32, device=x.device)
+        ang = pi * x / self.B
+        c, s = torch.cos(ang), torch.sin(ang)
+        cols = [self.init_param.to(x.device).expand(N, P)]
+        for i in range(1, self.dim):
+            cols.append(self.layers[i - 1](torch.cat((c[:, :i], s[:, :i]), dim=-1)))      # flows.py:186
+        params = torch.stack(cols, dim=1)                                                # [N, dim, 3K-1]
+        z, lad = self._spline(x, params, False)
+        return z, lad.sum(dim=1)
+
+    def inverse(self, z):
+        N = z.shape[0]
+        P = 3 * self.K - 1
+        xs = []
+        log_det = torch.zeros(N, dtype=torch.float32, device=z.device)
+        for i in range(self.dim):
+            if i == 0:
+                params = self.init_param.to(z.device).expand(N, P)
+            else:
+                params = self.layers[i - 1](self.trig_transform(torch.stack(xs, dim=1)))  # flows.py:203
+            xi, ld = self._spline(z[:, i].contiguous(), params.contiguous(), True)
+            xs.append(xi)
+            log_det = log_det + ld
+        return torch.stack(xs, dim=1), log_det
 
 
 class NSF_CL(nn.Module):

@@ -163,6 +163,80 @@ def fix_realnvp(out_dir):
     np.savez_compressed(os.path.join(out_dir, "realnvp.npz"), **rec)
 
 
+def fix_nsf_ar(out_dir):
+    """NSF_AR (nf/flows.py:152-209), the flow type of the shipped experiment YAMLs: forward, inverse,
+    bins per dimension, and autograd gradients of sum(z*r) + sum(ld*s) w.r.t. x and every parameter."""
+    rec = {}
+    for tag, dim, K, B, H, N in (("d6k8", 6, 8, 3.0, 16, 96), ("d4k32", 4, 32, 3, 12, 64), ("d12k8", 12, 8, 4.0, 24, 40)):
+        torch.manual_seed(77 + dim)
+        layer = ref_flows.NSF_AR(dim, K=K, B=B, hidden_dim=H)
+        with torch.no_grad():
+            for l in layer.layers:                       # non-uniform bins
+                l.network[4].weight.mul_(3.0)
+        x = edge_inputs(1.5 * torch.randn(N, dim, generator=gen(500 + dim)), float(B))
+        zin = edge_inputs(1.5 * torch.randn(N, dim, generator=gen(600 + dim)), float(B))
+        _captured.clear()
+        with torch.no_grad():
+            z, ld = layer.forward(x)
+        fb = [c.clone() for c in _captured]
+        _captured.clear()
+        with torch.no_grad():
+            xi, ldi = layer.inverse(zin)
+        ib = [c.clone() for c in _captured]
+        _captured.clear()
+        rec.update(sd_np(layer, tag + ".sd."))
+        rec.update({tag + ".x": npy(x), tag + ".z": npy(z), tag + ".ld": npy(ld), tag + ".zin": npy(zin),
+                    tag + ".x_inv": npy(xi), tag + ".ld_inv": npy(ldi), tag + ".dim": dim, tag + ".K": K,
+                    tag + ".B": float(B), tag + ".H": H})
+        # bins of the inside elements, one capture per dimension (searchsorted sees only inside inputs)
+        for name, caps, inp in (("bins", fb, x), ("bins_inv", ib, zin)):
+            full = torch.full((N, dim), -1, dtype=torch.int64)
+            for i in range(dim):
+                inside = (inp[:, i] >= -B) & (inp[:, i] <= B)
+                full[inside, i] = caps[i].reshape(-1)
+            rec[tag + "." + name] = npy(full)
+        # gradients
+        r = torch.randn(N, dim, generator=gen(700 + dim))
+        s = torch.randn(N, generator=gen(800 + dim))
+        xg = x.clone().requires_grad_()
+        zz, ll = layer.forward(xg)
+        loss = (zz * r).sum() + (ll * s).sum()
+        grads = torch.autograd.grad(loss, [xg] + list(layer.parameters()))
+        rec[tag + ".r"] = npy(r)
+        rec[tag + ".s"] = npy(s)
+        rec[tag + ".gx"] = npy(grads[0])
+        for (n, _), gv in zip(layer.named_parameters(), grads[1:]):
+            rec[tag + ".g." + n] = npy(gv)
+    np.savez_compressed(os.path.join(out_dir, "nsf_ar.npz"), **rec)
+
+
+def fix_checkpoint(out_dir):
+    """A checkpoint exactly as applications/src/train.py:39-40 writes it
+    ({"model", "optim", "scheduler", "epoch", "loss"}), plus the model's outputs on a seeded batch."""
+    torch.manual_seed(5)
+    flows = [ref_flows.NSF_CL(4, dim=2, K=8, B=3.0, hidden_dim=8, mask=[i % 2]) for i in range(2)] + \
+            [ref_flows.RealNVP(8, hidden_dim=8)]
+    prior = MultivariateNormal(torch.zeros(8), torch.eye(8))
+    model = ref_models.NormalizingFlowModel(prior, flows)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=10, gamma=0.5)
+    x = torch.randn(32, 8, generator=gen(900))
+    losses = []
+    for _ in range(3):                                   # a few steps of train.py:22-29
+        opt.zero_grad()
+        z, plp, ld = model(x)
+        loss = -torch.mean(plp + ld)
+        losses.append(loss.mean().data)
+        loss.backward()
+        opt.step()
+        sched.step()
+    torch.save({"model": model.state_dict(), "optim": opt.state_dict(), "scheduler": sched.state_dict(), "epoch": 3,
+                "loss": losses}, os.path.join(out_dir, "ref_checkpoint.pth"))
+    with torch.no_grad():
+        z, plp, ld = model(x)
+    np.savez_compressed(os.path.join(out_dir, "ref_checkpoint_out.npz"), x=npy(x), z=npy(z), plp=npy(plp), ld=npy(ld))
+
+
 def init_radial(layer, d, seed):
     with torch.no_grad():
         b = math.sqrt(1 / d)
@@ -374,6 +448,8 @@ def main():
     fix_models(a.out)
     fix_grads(a.out)
     fix_hmc(a.out)
+    fix_nsf_ar(a.out)
+    fix_checkpoint(a.out)
     tot = sum(os.path.getsize(os.path.join(a.out, f)) for f in os.listdir(a.out))
     print("wrote", sorted(os.listdir(a.out)), "total bytes", tot)
 

@@ -195,6 +195,46 @@ def nsf_cl(x, net, size, dim, mask, K, B, inverse, prefix="psi."):
 
 
 # --------------------------------------------------------------------------------------
+# NSF_AR autoregressive spline flow
+# --------------------------------------------------------------------------------------
+def _nsf_ar_spline(v, raw, K, B, inverse):
+    """flows.py:182-188 / :204-206: split, softmax x 2B, softplus, unconstrained_RQS."""
+    W, H, D = torch.split(raw, K, dim=1)
+    W, H = torch.softmax(W, dim=1), torch.softmax(H, dim=1)
+    W, H = 2 * B * W, 2 * B * H
+    D = F.softplus(D)
+    out, lad, bins = rqs_elementwise(v, W, H, D, inverse, B)
+    return out, lad, bins
+
+
+def nsf_ar_trig(x: torch.Tensor, B: float) -> torch.Tensor:
+    """trig_transform (flows.py:172-173): cat(cos(pi x / B), sin(pi x / B)) with pi as an fp32 tensor."""
+    pi = torch.tensor(math.pi, dtype=torch.float32).to(x.dtype)
+    return torch.cat((torch.cos(pi * x / B), torch.sin(pi * x / B)), dim=-1)
+
+
+def nsf_ar(x: torch.Tensor, net: Dict[str, torch.Tensor], dim: int, K: int, B: float, inverse: bool,
+           prefix: str = ""):
+    """Whole NSF_AR layer (flows.py:175-208).  Returns (out, log_det, bins [N, dim])."""
+    N = x.shape[0]
+    out = torch.zeros_like(x)
+    log_det = torch.zeros(N, dtype=x.dtype)
+    bins = []
+    for i in range(dim):
+        src = out if inverse else x                                    # conditioner sees x[:, :i] either way
+        if i == 0:
+            raw = net[prefix + "init_param"].to(x.dtype).expand(N, 3 * K - 1)
+        else:
+            raw = fcnn(nsf_ar_trig(src[:, :i], B), net, prefix + f"layers.{i - 1}.")
+        col, ld, b = _nsf_ar_spline(x[:, i], raw, K, B, inverse)
+        out = out.clone()
+        out[:, i] = col
+        log_det = log_det + ld
+        bins.append(b)
+    return out, log_det, torch.stack(bins, dim=1)
+
+
+# --------------------------------------------------------------------------------------
 # RealNVP, Planar, Radial
 # --------------------------------------------------------------------------------------
 def realnvp(x: torch.Tensor, net: Dict[str, torch.Tensor], inverse: bool, prefix: str = ""):
@@ -267,6 +307,9 @@ def apply_layer(spec: dict, sd: Dict[str, torch.Tensor], i: int, x: torch.Tensor
     if kind == "NSF_CL":
         out, ld, _, _ = nsf_cl(x, sd, spec["size"], spec["dim"], spec["mask"], spec["K"],
                                spec["B"], inverse, prefix=pre + "psi.")
+        return out, ld
+    if kind == "NSF_AR":
+        out, ld, _ = nsf_ar(x, sd, spec["dim"], spec["K"], spec["B"], inverse, prefix=pre)
         return out, ld
     if kind == "RealNVP":
         return realnvp(x, sd, inverse, prefix=pre)

@@ -149,6 +149,30 @@ def test_fused_weight_image_is_the_sw128_layout():
                 assert torch.equal(src, dst)
 
 
+def test_reference_checkpoint_loads_unchanged(tmp_path):
+    """A .pth written by the reference's train.py:39-40 loads into the drop-in model with no missing
+    or unexpected keys; optimizer / scheduler state round-trips too."""
+    import os as _os
+    from normalizingflow_b200 import checkpoint, flows, models
+    fl = [flows.NSF_CL(4, dim=2, K=8, B=3.0, hidden_dim=8, mask=[i % 2]) for i in range(2)] + [flows.RealNVP(8, hidden_dim=8)]
+    m = models.NormalizingFlowModel(models.GaussianPrior(8, device="cpu"), fl)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=10, gamma=0.5)
+    path = _os.path.join(ROOT, "tests", "golden", "ref_checkpoint.pth")
+    epoch, losses, res = checkpoint.load_checkpoint(path, m, opt, sched)
+    assert epoch == 3 and len(losses) == 3
+    assert list(res.missing_keys) == [] and list(res.unexpected_keys) == []
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    for k, v in blob["model"].items():
+        assert torch.equal(m.state_dict()[k], v), k
+    assert opt.state_dict()["state"][0]["step"] == 3 and sched.last_epoch == 3
+    # and the writer produces the same container
+    out = tmp_path / "mine.pth"
+    checkpoint.save_checkpoint(out, m, opt, sched, epoch=4, losses=[1.0])
+    again = torch.load(out, map_location="cpu", weights_only=False)
+    assert set(again) == set(checkpoint.KEYS) and set(again["model"]) == set(blob["model"])
+
+
 def test_wide_path_tile_plan_and_operand_images():
     """Host logic of the wide conditioner path (_wide.py): N-tile plan, weight / activation images
     (the SWIZZLE_128B shared-memory layout stored in HBM) and argument checks of its entry points."""
