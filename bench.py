@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunk-rows", type=int, default=131072, help="row chunk of the host-buffer (e2e) pipeline")
+    ap.add_argument("--e2e-wait", type=int, default=0, help="1: order the current stream after every host-API call")
     ap.add_argument("--no-fused", action="store_true", help="run the layer as separate GEMM + spline kernels")
     return ap.parse_args()
 
@@ -272,8 +274,8 @@ def run_native(a):
 
         def e2e_step():
             # public host-buffer API: row chunks stream through the GPU, copies overlap kernels
-            model.evaluate_host(hx, out=out_lp)                        # log p(x): forward + prior
-            model.inverse_host(hz, out_x=out_x, out_log_px=out_lpx)    # sampling direction
+            model.evaluate_host(hx, out=out_lp, chunk_rows=a.chunk_rows, wait=bool(a.e2e_wait))                        # log p(x)
+            model.inverse_host(hz, out_x=out_x, out_log_px=out_lpx, chunk_rows=a.chunk_rows, wait=bool(a.e2e_wait))    # sampling
 
         for _ in range(2):
             e2e_step()
@@ -282,6 +284,7 @@ def run_native(a):
         e0.record()
         for _ in range(a.steps):
             e2e_step()
+        model.host_sync()                      # every result of every step is in host memory
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
@@ -292,7 +295,7 @@ def run_native(a):
         ems = float(t.item()) / a.steps
         e2e = {"value": world * N / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems,
                "h2d_bytes_per_step": 2 * N * D * 4, "d2h_bytes_per_step": N * D * 4 + 2 * N * 4,
-               "api": "NormalizingFlowModel.evaluate_host(x) + inverse_host(z): pinned host buffers, 131072-row chunks, "
+               "api": f"NormalizingFlowModel.evaluate_host(x) + inverse_host(z): pinned host buffers, {a.chunk_rows}-row chunks, "
                       "H2D / kernels / D2H on three streams"}
 
     if rank == 0:

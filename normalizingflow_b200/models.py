@@ -116,23 +116,33 @@ class NormalizingFlowModel(nn.Module):
     # chunk i-1 overlapping the kernels of chunk i (three CUDA streams, rotating device buffers).
     # Same results as evaluate()/inverse() on the whole batch: rows are independent.
     # ------------------------------------------------------------------------------------
-    def _stream_rows(self, host_in, fn, outs, chunk_rows):
+    def _host_pipe(self, dev, rows, d):
+        """Copy streams and rotating device buffers, kept across calls: the next call's first
+        host->device copy then overlaps the previous call's last kernels and device->host copy."""
+        key = (str(dev), rows, d)
+        pipe = getattr(self, "_pipe", None)
+        if pipe is None or pipe["key"] != key:
+            nbuf = 3
+            pipe = dict(key=key, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), nbuf=nbuf, it=0,
+                        bufs=[torch.empty((rows, d), dtype=torch.float32, device=dev) for _ in range(nbuf)],
+                        free=[None] * nbuf)
+            self._pipe = pipe
+        return pipe
+
+    def _stream_rows(self, host_in, fn, outs, chunk_rows, wait=True):
         dev = next(self.parameters()).device
         n, d = host_in.shape
         cur = torch.cuda.current_stream(dev)
-        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        s_in.wait_stream(cur)
-        s_out.wait_stream(cur)
-        nbuf = 3
-        bufs = [torch.empty((min(chunk_rows, n), d), dtype=torch.float32, device=dev) for _ in range(nbuf)]
-        free = [None] * nbuf
+        pipe = self._host_pipe(dev, min(chunk_rows, n), d)
+        s_in, s_out, nbuf, bufs, free = pipe["s_in"], pipe["s_out"], pipe["nbuf"], pipe["bufs"], pipe["free"]
         with torch.no_grad():
-            for i, a in enumerate(range(0, n, chunk_rows)):
+            for a in range(0, n, chunk_rows):
                 b = min(n, a + chunk_rows)
-                k = i % nbuf
+                k = pipe["it"] % nbuf
+                pipe["it"] += 1
                 with torch.cuda.stream(s_in):
                     if free[k] is not None:
-                        s_in.wait_event(free[k])
+                        s_in.wait_event(free[k])            # the kernels that read this buffer are done
                     xin = bufs[k][: b - a]
                     xin.copy_(host_in[a:b], non_blocking=True)
                     ready = torch.cuda.Event()
@@ -147,22 +157,32 @@ class NormalizingFlowModel(nn.Module):
                     for r, o in zip(res, outs):
                         o[a:b].copy_(r, non_blocking=True)
                         r.record_stream(s_out)
-        cur.wait_stream(s_out)
-        cur.wait_stream(s_in)
+        if wait:
+            # results are valid once the CURRENT stream is synchronised (as for any non_blocking copy)
+            cur.wait_stream(s_out)
         return outs
 
-    def evaluate_host(self, x_host, out=None, chunk_rows=131072):
-        """log p(x) for a batch in host memory -> host tensor [N] (pinned when allocated here)."""
+    def host_sync(self):
+        """Block the host until every evaluate_host / inverse_host result has landed (needed before
+        reading results of calls made with ``wait=False``)."""
+        pipe = getattr(self, "_pipe", None)
+        if pipe is not None:
+            pipe["s_out"].synchronize()
+
+    def evaluate_host(self, x_host, out=None, chunk_rows=131072, wait=True):
+        """log p(x) for a batch in host memory -> host tensor [N] (pinned when allocated here).
+        ``wait=False`` does not order the current stream after the device->host copies, so
+        back-to-back calls overlap completely; call ``host_sync()`` before reading the results."""
         if out is None:
             out = torch.empty(x_host.shape[0], dtype=torch.float32).pin_memory()
 
         def fn(x):
             z, prior_logprob, log_det = self.forward(x)
             return (prior_logprob + log_det,)
-        self._stream_rows(x_host, fn, (out,), chunk_rows)
+        self._stream_rows(x_host, fn, (out,), chunk_rows, wait)
         return out
 
-    def inverse_host(self, z_host, out_x=None, out_log_px=None, chunk_rows=131072):
+    def inverse_host(self, z_host, out_x=None, out_log_px=None, chunk_rows=131072, wait=True):
         """sampling direction for latents in host memory -> (x, log_px) host tensors, as sample()."""
         n, d = z_host.shape
         if out_x is None:
@@ -173,5 +193,5 @@ class NormalizingFlowModel(nn.Module):
         def fn(z):
             x, log_det = self.inverse(z)
             return x, self.prior.log_prob(z) - log_det
-        self._stream_rows(z_host, fn, (out_x, out_log_px), chunk_rows)
+        self._stream_rows(z_host, fn, (out_x, out_log_px), chunk_rows, wait)
         return out_x, out_log_px

@@ -217,3 +217,10 @@ def test_host_streaming_entry_points_equal_device_calls():
         rx, rld = m.inverse(x.cuda())
         rlpx = m.prior.log_prob(x.cuda()) - rld
     assert torch.equal(lp, ref.cpu()) and torch.equal(xs, rx.cpu()) and torch.equal(lpx, rlpx.cpu())
+    # wait=False: back-to-back calls overlap; host_sync() makes every result visible
+    lp2 = m.evaluate_host(x, chunk_rows=256, wait=False)
+    xs2, lpx2 = m.inverse_host(x, chunk_rows=256, wait=False)
+    lp3 = m.evaluate_host(xs2.clone().pin_memory() if False else x, chunk_rows=256, wait=False)
+    m.host_sync()
+    assert torch.equal(lp2, ref.cpu()) and torch.equal(xs2, rx.cpu()) and torch.equal(lpx2, rlpx.cpu())
+    assert torch.equal(lp3, ref.cpu())

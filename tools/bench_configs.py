@@ -8,7 +8,7 @@ import argparse, json, os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from normalizingflow_b200 import _lib
-from normalizingflow_b200.flows import NSF_CL, Planar, Radial, RealNVP
+from normalizingflow_b200.flows import NSF_AR, NSF_CL, Planar, Radial, RealNVP
 from normalizingflow_b200.hmc import HMC, FlowSimulation
 from normalizingflow_b200.models import GaussianPrior, NormalizingFlowModel
 
@@ -109,6 +109,23 @@ def cfg5(C, H, precision):
             "ms_per_logprob_grad_eval": dt / evals * 1e3, "chain_grad_evals_per_s": C * evals / dt, "accept_rate": acc}
 
 
+def cfg_nsf_ar(N, precision):
+    """the shipped LJ experiment (applications/input/LJ.yaml): 2 x NSF_AR(dim = 32*3,
+    K = 32 splines, hidden 354); B = 3."""
+    torch.manual_seed(0)
+    fl = [NSF_AR(96, K=32, B=3.0, hidden_dim=354) for _ in range(2)]
+    for f in fl:
+        for l in f.layers:
+            l.precision = precision
+    m = NormalizingFlowModel(GaussianPrior(96, device=dev), fl, device=dev).to(dev)
+    x = torch.randn(N, 96, device=dev)
+    t_eval = timeit(lambda: m.evaluate(x), iters=3, warm=1)
+    t_samp = timeit(lambda: m.sample(N), iters=2, warm=1)
+    return {"config": f"N1: LJ.yaml flow, 2 x NSF_AR(96, K=32, H=354, {precision} conditioners), batch {N}",
+            "evaluate_ms": t_eval, "sample_ms": t_samp, "evaluate_samples_per_s": N / t_eval * 1e3,
+            "sample_samples_per_s": N / t_samp * 1e3}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -116,7 +133,8 @@ def main():
     n3 = 131072 if a.quick else 1 << 19
     n4 = 1 << 18 if a.quick else 1 << 20
     for fn in (lambda: cfg1(100), lambda: cfg1(800), lambda: cfg3(n3), lambda: cfg4(n4),
-               lambda: cfg5(65536, 128, "fp32"), lambda: cfg5(65536, 128, "bf16")):
+               lambda: cfg5(65536, 128, "fp32"), lambda: cfg5(65536, 128, "bf16"),
+               lambda: cfg_nsf_ar(65536, "fp32"), lambda: cfg_nsf_ar(65536, "bf16")):
         l0 = _lib.launch_count()
         r = fn()
         r["libnfk_launches"] = _lib.launch_count() - l0
