@@ -203,6 +203,12 @@ int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w
  * conditioner.  `aux` may be NULL otherwise.
  * Replaces one nn.Linear(+Tanh) of FCNN (nf/flows.py:26-35), and autograd through it. */
 int nfk_gemm_ws_rows_per_tile(void);
+/* CTA-pair mode of the wide-path GEMMs (tcgen05 cta_group::2: two SMs share one 256-row MMA, each
+ * holding half of the B tile): -1 automatic (pairs once there are >= 2 M tiles per SM), 0 never,
+ * 1 always.  Process-global; for tuning and tests. */
+int nfk_set_gemm_ws_pair_mode(int mode);
+/* diagnostic: CTA pairs the last pair-mode launch could keep co-resident (cudaOccupancyMaxActiveClusters) */
+int nfk_gemm_ws_last_clusters(void);
 int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* out, int64_t M,
                 int KB, int kmma_last, const int32_t* tile_blocks /*host*/, int n_tiles, int act,
                 int out_f32, int n_out, int64_t ldy, const void* aux, void* stream);

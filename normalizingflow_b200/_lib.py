@@ -62,6 +62,8 @@ SIGNATURES = {
     "nfk_gemm_f32": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int64,
                              c_int, _P]),
     "nfk_gemm_ws_rows_per_tile": (c_int, []),
+    "nfk_set_gemm_ws_pair_mode": (c_int, [c_int]),
+    "nfk_gemm_ws_last_clusters": (c_int, []),
     "nfk_gemm_ws": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int64, _P, _P]),
     "nfk_gemm_ws_rqs_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P,
                                     c_int, c_float, c_int, _P]),

@@ -70,7 +70,7 @@ struct WsCfg<EPI_RQS_BWD> {                            // spline backward as the
 };
 template <int EPI>
 constexpr size_t ws_smem() {
-  return (size_t)WsCfg<EPI>::STAGES * (WS_A_BYTES + WsCfg<EPI>::B_BYTES) + WsCfg<EPI>::STG_BYTES + 16 * 8 + 1024;
+  return (size_t)WsCfg<EPI>::STAGES * (WS_A_BYTES + WsCfg<EPI>::B_BYTES) + WsCfg<EPI>::STG_BYTES + 32 * 8 + 1024;
 }
 static_assert(ws_smem<EPI_BF16_IMG>() <= 227 * 1024 && ws_smem<EPI_RQS>() <= 227 * 1024 &&
                   ws_smem<EPI_RQS_BWD>() <= 227 * 1024,
@@ -116,12 +116,70 @@ __device__ __forceinline__ bool ws_elect_one() {
   return pred != 0;
 }
 
-template <int EPI, int MODE, bool INVERSE, bool PAIRS>
+// ---- CTA-pair (cta_group::2) helpers: two SMs of one TPC run ONE 256-row MMA, each holding its own
+// 128 A rows and HALF of the B tile, so the shared-memory port sees half the B traffic per MMA.
+constexpr uint32_t WS_PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit: the even CTA's copy of an address
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs of the pair -> the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// arrive on the EVEN CTA's copy of a barrier (local when executed by the even CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  // default (cta-scope) semantics on purpose: what is handed over lives in TMEM / TMA-written shared memory
+  // and is ordered by the tcgen05 fences and the mbarrier itself; a cluster-scope release/acquire would make
+  // ptxas emit an L1 invalidate (CCTL.IVALL) inside the spin loops
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & WS_PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+template <int EPI, int MODE, bool INVERSE, bool PAIRS, bool TWO>
 __global__ void __launch_bounds__((2 + WsCfg<EPI>::EPI_WARPS) * 32, 1)
 gemm_ws_kernel(const __grid_constant__ WsArgs a) {
-  constexpr int WS_STAGES = WsCfg<EPI>::STAGES;
+  // pair mode: a CTA stages only half of the B tile, the saved shared memory buys deeper pipelining
+  constexpr uint32_t WS_STAGE_BYTES = WS_A_BYTES + (TWO ? WsCfg<EPI>::B_BYTES / 2 : WsCfg<EPI>::B_BYTES);
+  constexpr int WS_STAGES = (int)((WsCfg<EPI>::STAGES * (WS_A_BYTES + WsCfg<EPI>::B_BYTES)) / WS_STAGE_BYTES);
   constexpr int WS_EPI_WARPS = WsCfg<EPI>::EPI_WARPS;
-  constexpr uint32_t WS_STAGE_BYTES = WS_A_BYTES + WsCfg<EPI>::B_BYTES;
   constexpr uint32_t WS_STG_BYTES = WsCfg<EPI>::STG_BYTES;
   constexpr bool OUT_F32 = (EPI == EPI_F32_ROWS);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -131,43 +189,54 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
   uint64_t* full = bars;                    // [STAGES] operands landed      (1 + tx)
   uint64_t* empty = bars + WS_STAGES;       // [STAGES] stage consumed       (1, tcgen05.commit)
   uint64_t* tfull = bars + 2 * WS_STAGES;   // [2] accumulator complete      (1, tcgen05.commit)
-  uint64_t* tempty = tfull + 2;             // [2] accumulator drained       (epilogue warps)
+  uint64_t* tempty = tfull + 2;             // [2] accumulator drained       (epilogue warps; pair: of both CTAs)
+  uint64_t* pfull = tempty + 2;             // [STAGES] pair mode: the odd CTA's operands landed (1, remote arrive)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  const uint32_t crank = TWO ? cluster_ctarank() : 0u;
+  if (warp == 0) {
+    if (TWO) tmem_alloc2(&tmem_base_s, 512); else tmem_alloc(&tmem_base_s, 512);
+  }
   if (tid == 32) {
     for (int i = 0; i < WS_STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
+      mbar_init(&pfull[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], WS_EPI_WARPS);
+      mbar_init(&tempty[i], TWO ? 2 * WS_EPI_WARPS : WS_EPI_WARPS);
     }
     fence_barrier_init();
   }
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();              // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const long long first = blockIdx.x, stride = gridDim.x;
+  // work items: M tiles (pair mode: pairs of M tiles, CTA rank r owns tile 2*pt + r)
+  const long long first = TWO ? (blockIdx.x >> 1) : blockIdx.x, stride = TWO ? (gridDim.x >> 1) : gridDim.x;
+  const long long n_pt = TWO ? (a.m_tiles + 1) / 2 : a.m_tiles;
 
   if (warp == 0) {
     // ================================ producer ================================
     uint32_t s = 0, ph = 0;
-    for (long long mt = first; mt < a.m_tiles; mt += stride) {
-      const unsigned char* ag = a.a_img + (size_t)mt * a.KB * WS_BLK;
+    for (long long pt = first; pt < n_pt; pt += stride) {
+      const long long mt = TWO ? 2 * pt + crank : pt;
+      const long long mt_ld = mt < a.m_tiles ? mt : a.m_tiles - 1;      // odd tile count: the pair's spare half
+      const unsigned char* ag = a.a_img + (size_t)mt_ld * a.KB * WS_BLK;
       const unsigned char* wg = a.w_img;
       for (int t = 0; t < a.n_tiles; ++t) {
         const uint32_t bb = (uint32_t)a.nb[t] * 64u * 128u;
+        const uint32_t bl = TWO ? bb / 2 : bb;                           // pair mode: this CTA's half of the B rows
         for (int kb = 0; kb < a.KB; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           if (lane == 0) {
             unsigned char* st = sm + s * WS_STAGE_BYTES;
-            mbar_expect_tx(&full[s], WS_A_BYTES + bb);
+            mbar_expect_tx(&full[s], WS_A_BYTES + bl);
             bulk_g2s(st, ag + (size_t)kb * WS_BLK, WS_A_BYTES, &full[s]);
-            bulk_g2s(st + WS_A_BYTES, wg + (size_t)kb * bb, bb, &full[s]);
+            bulk_g2s(st + WS_A_BYTES, wg + (size_t)kb * bb + (size_t)crank * bl, bl, &full[s]);
           }
           __syncwarp();
           if (++s == WS_STAGES) {
@@ -181,31 +250,55 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     uint32_t s = 0, ph = 0, tl = 0;
-    for (long long mt = first; mt < a.m_tiles; mt += stride) {
-      for (int t = 0; t < a.n_tiles; ++t, ++tl) {
-        const uint32_t acc = tl & 1;
-        const uint32_t idesc = make_idesc_bf16(WS_M, a.nb[t] * 64);
-        mbar_wait(&tempty[acc], ((tl >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem + acc * 256;
-        for (int kb = 0; kb < a.KB; ++kb) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          if (ws_elect_one()) {
-            const uint32_t aa = smem_u32(sm + s * WS_STAGE_BYTES), ba = aa + WS_A_BYTES;
-            const int nm = (kb == a.KB - 1) ? a.kmma_last : 4;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < nm)
-                umma_bf16(d, make_desc_sw128(aa + k * 32), make_desc_sw128(ba + k * 32), idesc,
-                          (kb | k) ? 1u : 0u);
-            umma_commit(&empty[s]);
-            if (kb == a.KB - 1) umma_commit(&tfull[acc]);
+    if (TWO && crank == 1) {
+      // odd CTA of the pair: no MMA issue -- forward "my operands landed" to the even CTA
+      for (long long pt = first; pt < n_pt; pt += stride)
+        for (int t = 0; t < a.n_tiles; ++t)
+          for (int kb = 0; kb < a.KB; ++kb) {
+            mbar_wait(&full[s], ph);
+            if (lane == 0) mbar_arrive_leader(&pfull[s]);
+            __syncwarp();
+            if (++s == WS_STAGES) {
+              s = 0;
+              ph ^= 1;
+            }
           }
-          __syncwarp();
-          if (++s == WS_STAGES) {
-            s = 0;
-            ph ^= 1;
+    } else {
+      for (long long pt = first; pt < n_pt; pt += stride) {
+        for (int t = 0; t < a.n_tiles; ++t, ++tl) {
+          const uint32_t acc = tl & 1;
+          const uint32_t idesc = make_idesc_bf16(TWO ? 2 * WS_M : WS_M, a.nb[t] * 64);
+          mbar_wait(&tempty[acc], ((tl >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem + acc * 256;
+          for (int kb = 0; kb < a.KB; ++kb) {
+            mbar_wait(&full[s], ph);
+            if (TWO) mbar_wait(&pfull[s], ph);
+            tc_fence_after();
+            if (ws_elect_one()) {
+              const uint32_t aa = smem_u32(sm + s * WS_STAGE_BYTES), ba = aa + WS_A_BYTES;
+              const int nm = (kb == a.KB - 1) ? a.kmma_last : 4;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < nm) {
+                  if (TWO)
+                    umma2_bf16(d, make_desc_sw128(aa + k * 32), make_desc_sw128(ba + k * 32), idesc, (kb | k) ? 1u : 0u);
+                  else
+                    umma_bf16(d, make_desc_sw128(aa + k * 32), make_desc_sw128(ba + k * 32), idesc, (kb | k) ? 1u : 0u);
+                }
+              if (TWO) {
+                umma2_commit(&empty[s]);                     // frees the stage in both CTAs
+                if (kb == a.KB - 1) umma2_commit(&tfull[acc]);
+              } else {
+                umma_commit(&empty[s]);
+                if (kb == a.KB - 1) umma_commit(&tfull[acc]);
+              }
+            }
+            __syncwarp();
+            if (++s == WS_STAGES) {
+              s = 0;
+              ph ^= 1;
+            }
           }
         }
       }
@@ -225,7 +318,8 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
     const int unm0 = a.unm[0], unm1 = a.unm[1], unm2 = a.unm[2];
     const int mask0 = a.mask[0], mask1 = a.mask[1], mask2 = a.mask[2];
     uint32_t tl = 0, it = 0;
-    for (long long mt = first; mt < a.m_tiles; mt += stride, ++it) {
+    for (long long pt = first; pt < n_pt; pt += stride, ++it) {
+      const long long mt = TWO ? 2 * pt + crank : pt;
       const long long grow = mt * WS_M + row;
       const bool live = grow < a.M;
       const float* xr = a.x + grow * d;
@@ -269,7 +363,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
           if (e == 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);      // the accumulator may be overwritten
+            if (lane == 0) { if (TWO) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }      // the accumulator may be overwritten
           }
           const RqsOut o = rqs_element<MODE, 8, INVERSE, true>(RegParams{v, sB3 + f * WS_PC}, xin[e], a.c);
           if (gbase[e] >= 0) {
@@ -316,7 +410,8 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
     const int mask0 = a.mask[0], mask1 = a.mask[1], mask2 = a.mask[2];
     const int ob_total = 3 * a.n_tiles;
     uint32_t tl = 0;
-    for (long long mt = first; mt < a.m_tiles; mt += stride) {
+    for (long long pt = first; pt < n_pt; pt += stride) {
+      const long long mt = TWO ? 2 * pt + crank : pt;
       const long long grow = mt * WS_M + row;
       const bool live = grow < a.M;
       const float* xr = a.x + grow * d;
@@ -354,7 +449,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
           if (e == FPT - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) { if (TWO) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
           }
           float gxv, gp[24];
           rqs_element_bwd<8, true>(RegParams{v, sB3 + f * WS_PC}, xin[e], gyv[e], gl, INVERSE, a.c, gxv, gp);
@@ -383,7 +478,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, %0;" ::"n"(WS_EPI_WARPS * 32) : "memory");
-        if (issuer) {
+        if (issuer && mt < a.m_tiles) {
           unsigned char* og = reinterpret_cast<unsigned char*>(a.out) + ((size_t)mt * ob_total + 3 * t) * WS_BLK;
           bulk_s2g(og, sG, 3 * WS_BLK);
           bulk_commit();
@@ -405,7 +500,8 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
     uint32_t tl = 0, bc = 0;
     int ob_total = 0;
     for (int t = 0; t < a.n_tiles; ++t) ob_total += a.nb[t];
-    for (long long mt = first; mt < a.m_tiles; mt += stride) {
+    for (long long pt = first; pt < n_pt; pt += stride) {
+      const long long mt = TWO ? 2 * pt + crank : pt;
       int ob0 = 0;
       for (int t = 0; t < a.n_tiles; ++t, ++tl) {
         const uint32_t acc = tl & 1;
@@ -416,7 +512,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
         if (b_first >= nb) {                                           // nothing of this tile is ours
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) { if (TWO) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
         }
         for (int b = b_first; b < nb; b += 2) {
           uint32_t v[32];
@@ -426,7 +522,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
             // this warp's last columns of the accumulator are in registers
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) { if (TWO) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
           }
           const int colb = (ob0 + b) * 64 + h * 32;        // first padded output column of v[]
           const float4* bp = reinterpret_cast<const float4*>(a.bias + colb);
@@ -449,7 +545,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
             } else if (a.act == 2) {
               // tanh backward: multiply by 1 - h^2, h from the saved activation image (same block, same chunk)
               const uint4 hv = __ldg(reinterpret_cast<const uint4*>(
-                  a.aux + ((size_t)mt * ob_total + (ob0 + b)) * WS_BLK + row * 128 + (((h * 4 + j) ^ (row & 7)) << 4)));
+                  a.aux + ((size_t)(mt < a.m_tiles ? mt : a.m_tiles - 1) * ob_total + (ob0 + b)) * WS_BLK + row * 128 + (((h * 4 + j) ^ (row & 7)) << 4)));
               const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -473,7 +569,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
           }
           fence_proxy_async();
           asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
-          if (issuer) {
+          if (issuer && mt < a.m_tiles) {
             unsigned char* og = reinterpret_cast<unsigned char*>(a.out) +
                                 ((size_t)mt * ob_total + (ob0 + b)) * WS_BLK;
             bulk_s2g(og, sb, WS_BLK);
@@ -496,7 +592,8 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
     uint32_t tl = 0, bc = 0;
     int ob_total = 0;
     for (int t = 0; t < a.n_tiles; ++t) ob_total += a.nb[t];
-    for (long long mt = first; mt < a.m_tiles; mt += stride) {
+    for (long long pt = first; pt < n_pt; pt += stride) {
+      const long long mt = TWO ? 2 * pt + crank : pt;
       int ob0 = 0;
       for (int t = 0; t < a.n_tiles; ++t, ++tl) {
         const uint32_t acc = tl & 1;
@@ -511,7 +608,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
             // every column of this accumulator is in registers: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) { if (TWO) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
           }
           const int colb = (ob0 + b) * 64 + h * 32;        // first padded output column of v[]
           const float4* bp = reinterpret_cast<const float4*>(a.bias + colb);
@@ -599,7 +696,10 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (TWO) cluster_sync_all();              // the peer is done with this CTA's shared memory / barriers
+  if (warp == 0) {
+    if (TWO) tmem_dealloc2(tmem, 512); else tmem_dealloc(tmem, 512);
+  }
 }
 
 // fp32 x[:, :, cols] gather (nf/flows.py:230) -> bf16 A image [m_tiles][KB][128][64], zero padded.
@@ -679,18 +779,63 @@ static int fill_rqs_geometry(WsArgs& a, int size, int dim, const int32_t* mask, 
   return NFK_OK;
 }
 
+static int g_ws_last_clusters = 0;     // co-resident CTA pairs of the last pair-mode launch (diagnostic)
+static int g_ws_pair_mode = -1;          // -1 automatic, 0 never, 1 always (nfk_set_gemm_ws_pair_mode)
+
 template <int EPI, int MODE, bool INVERSE, bool PAIRS = false>
 static int launch_ws(const WsArgs& a, cudaStream_t st) {
-  auto kern = gemm_ws_kernel<EPI, MODE, INVERSE, PAIRS>;
   constexpr size_t smem = ws_smem<EPI>();
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  constexpr unsigned threads = (2 + WsCfg<EPI>::EPI_WARPS) * 32;
+  const long long cap = sm_count();
+  // CTA pairs (cta_group::2) once there are enough M tiles to keep every SM pair busy
+  const bool two = g_ws_pair_mode < 0 ? (a.m_tiles >= 2 * cap) : (g_ws_pair_mode != 0 && a.m_tiles >= 2);
+  cudaError_t e;
+  if (two) {
+    auto kern = gemm_ws_kernel<EPI, MODE, INVERSE, PAIRS, true>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      const long long pairs = (a.m_tiles + 1) / 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)cap);
+      cfg.blockDim = dim3(threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      // persistent kernel: launch exactly as many CTA pairs as can be co-resident (a pair needs both
+      // SMs of one TPC; not every SM of the chip has a free partner), never a second wave
+      static int max_clusters[4] = {0, 0, 0, 0};
+      if (max_clusters[EPI] == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = (int)(cap / 2);
+        max_clusters[EPI] = n;
+      }
+      g_ws_last_clusters = max_clusters[EPI];
+      const long long gp = pairs < max_clusters[EPI] ? pairs : max_clusters[EPI];
+      cfg.gridDim = dim3((unsigned)(2 * gp));
+      e = cudaLaunchKernelEx(&cfg, kern, a);
+      if (e != cudaSuccess) {
+        set_error("gemm_ws: cluster launch failed: %s", cudaGetErrorString(e));
+        return NFK_ECUDA;
+      }
+    }
+  } else {
+    auto kern = gemm_ws_kernel<EPI, MODE, INVERSE, PAIRS, false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      const unsigned grid = (unsigned)(a.m_tiles < cap ? a.m_tiles : cap);
+      kern<<<grid, threads, smem, st>>>(a);
+    }
+  }
   if (e != cudaSuccess) {
     set_error("gemm_ws: cannot set %zu B dynamic shared memory: %s", smem, cudaGetErrorString(e));
     return NFK_ECUDA;
   }
-  const long long cap = sm_count();
-  const unsigned grid = (unsigned)(a.m_tiles < cap ? a.m_tiles : cap);
-  kern<<<grid, (2 + WsCfg<EPI>::EPI_WARPS) * 32, smem, st>>>(a);
   count_launch();
   return check_launch("gemm_ws");
 }
@@ -702,6 +847,14 @@ using namespace nfk;
 extern "C" {
 
 int nfk_gemm_ws_rows_per_tile(void) { return WS_M; }
+
+int nfk_gemm_ws_last_clusters(void) { return g_ws_last_clusters; }
+
+int nfk_set_gemm_ws_pair_mode(int mode) {
+  NFK_REQUIRE(mode >= -1 && mode <= 1, "set_gemm_ws_pair_mode: -1 automatic, 0 single CTA, 1 CTA pairs");
+  g_ws_pair_mode = mode;
+  return NFK_OK;
+}
 
 int nfk_pack_a_img(const float* x, void* img, int64_t N, int size, int dim, const int32_t* cols, int n_cols,
                    int KB, void* stream) {

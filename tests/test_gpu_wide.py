@@ -15,6 +15,16 @@ def _wide():
     return _wide
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["single_cta", "cta_pair"])
+def pair_mode(request):
+    """Every test runs with the wide-path GEMMs forced to single-CTA tiles and to CTA pairs
+    (tcgen05 cta_group::2; needs >= 2 M tiles, smaller problems fall back to single)."""
+    from normalizingflow_b200 import _lib
+    _lib.lib.nfk_set_gemm_ws_pair_mode(request.param)
+    yield request.param
+    _lib.lib.nfk_set_gemm_ws_pair_mode(-1)
+
+
 def _layer(w, b, kb):
     W = _wide()
     n_out, k_in = w.shape

@@ -17,6 +17,9 @@ pp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "
 if os.path.exists(pp):
     peak = float(json.load(open(pp))["bf16_tflops"])
 M = int(os.environ.get("ROWS", 1 << 20))
+from normalizingflow_b200 import _lib
+_lib.lib.nfk_set_gemm_ws_pair_mode(int(os.environ.get("PAIR", -1)))
+print("pair mode", os.environ.get("PAIR", -1), flush=True)
 
 
 def timeit(fn, n=5):
@@ -49,6 +52,7 @@ for K, N, act, f32 in ((32, 800, 1, False), (800, 800, 1, False), (800, 736, 0, 
     del x
     fl = 2 * M * K * N
     byt = M * K * 2 + N * K * 2 + M * N * (4 if f32 else 2)
+    print("co-resident CTA pairs:", _lib.lib.nfk_gemm_ws_last_clusters(), end="  ")
     print(f"M={M} K={K:4d} N={N:4d} tiles={tiles} {'f32' if f32 else 'bf16'} out: {ms:7.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s "
           f"({fl / ms / 1e9 / peak:5.1%} of measured bf16 peak)  {byt / ms / 1e6:7.1f} GB/s algorithmic | "
           f"cuBLAS bf16 matmul (no bias/act, bf16 out) {ms_cublas:7.3f} ms", flush=True)
