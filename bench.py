@@ -195,6 +195,8 @@ def run_native(a):
         raise SystemExit("bench.py --impl native needs a CUDA device (there is no CPU path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from normalizingflow_b200.dist import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local)          # before any pinned allocation (first touch = local node)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -355,7 +357,7 @@ def run_native(a):
                 "config": {"workload": workload_name(a), "hidden": a.hidden, "arith": a.arith, "conditioner": cond,
                            "fused_layer_kernel": bool(not a.no_fused and cond == "bf16" and a.hidden <= 128),
                            "spline_epilogue_on_last_gemm": bool(not a.no_fused and cond == "bf16" and a.hidden > 128), "global_batch": world * N, "parallelism": f"batch-sharded x{world}",
-                           "l2": "inputs larger than L2 (x 268 MB, spline params 3.1 GB per layer)"},
+                           "l2": "inputs larger than L2 (x 268 MB, spline params 3.1 GB per layer)", "numa": numa},
                 "roofline": roofline, "clocks": clk, "gpu_launches": launches, "e2e": e2e}
         if not a.no_cpu_baseline and world == 1:       # reported at N=1 only
             line["cpu_baseline"] = cpu_baseline(a, sd)

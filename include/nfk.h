@@ -237,6 +237,10 @@ int nfk_gemm_ws_rqs_bwd(const void* a_img, const void* w_img, const float* bias,
                         float* grad_x, void* grad_params_img, int64_t M, int KB, int kmma_last,
                         int size, int dim, const int32_t* mask, int n_mask, float B, int inverse,
                         void* stream);
+/* bf16 image [ceil(M/128)][KB][128][64] -> row-major bf16 rows [M, ld], first ncols columns (ncols, ld
+ * multiples of 8): hands saved activations / gradient images to the weight-gradient GEMMs */
+int nfk_unpack_img_rows(const void* img, void* rows, int64_t M, int KB, int ncols, int64_t ld,
+                        void* stream);
 /* g[:, s*dim + cols[j]] += dxc[:, s*n_cols + j]: adds the conditioner-input gradient [N, size*n_cols]
  * to the conditioning columns of grad_x (adjoint of the gather at nf/flows.py:230) */
 int nfk_scatter_add_cols(float* g, const float* dxc, int64_t N, int size, int dim,

@@ -254,8 +254,9 @@ def layer_forward_saving(layer, x, inverse, logdet=None):
     return out, logdet, (x, h1, h2, bool(inverse))
 
 
-def layer_backward(layer, ctx, g_out, g_logdet=None, g_logdet_const=1.0):
-    """dL/dx of one layer from dL/dout [N, d] and dL/dlogdet ([N] tensor, or a constant for all rows)."""
+def layer_backward(layer, ctx, g_out, g_logdet=None, g_logdet_const=1.0, keep=False):
+    """dL/dx of one layer from dL/dout [N, d] and dL/dlogdet ([N] tensor, or a constant for all rows).
+    ``keep``: also return the gradient images (dL/dparams, dL/dz2, dL/dz1) the weight gradients need."""
     x, h1, h2, inverse = ctx
     dev = require_cuda(x, g_out, g_logdet)
     g_out = f32c(g_out)
@@ -276,7 +277,76 @@ def layer_backward(layer, ctx, g_out, g_logdet=None, g_logdet_const=1.0):
     with torch.cuda.device(dev):
         call("nfk_scatter_add_cols", ptr(g_in), ptr(dxc), N, layer.size, layer.dim, i32_array(layer._mask),
              len(layer._mask), stream_ptr(dev))
+    if keep:
+        return g_in, (g_img, dz2, dz1)
     return g_in
+
+
+def unpack_rows(img, M, ncols):
+    """bf16 image -> row-major bf16 [M, pad8(ncols)] (view of the first ncols columns returned)."""
+    dev = img.device
+    kb = img.shape[1]
+    ld = (ncols + 7) // 8 * 8
+    rows = torch.empty((M, ld), dtype=torch.bfloat16, device=dev)
+    if ld > (ncols // 8) * 8:
+        rows[:, (ncols // 8) * 8:] = 0
+    with torch.cuda.device(dev):
+        call("nfk_unpack_img_rows", ptr(img), ptr(rows), M, kb, min(ld, kb * 64), ld, stream_ptr(dev))
+    return rows[:, :ncols]
+
+
+def _mm_f32(a_t, b):
+    """a_t^T-contracted GEMM of two bf16 row-major operands with an fp32 result: [K, M]^T... i.e.
+    a_t [N, P], b [N, Q] -> a_t.T @ b [P, Q] (weight gradient: contraction over the batch).
+    Plain library GEMM (cuBLAS) — the batch-contraction GEMM is not on the inference hot path."""
+    try:
+        return torch.mm(a_t.t(), b, out_dtype=torch.float32)
+    except TypeError:
+        return torch.mm(a_t.t(), b).float()
+
+
+class NsfWideFn(torch.autograd.Function):
+    """One grad_eligible NSF_CL layer for training: forward = pack + 2 GEMMs + GEMM-with-spline
+    epilogue (hidden activations stay in HBM as bf16 images), backward = spline adjoint as a GEMM
+    epilogue + dgrad GEMMs with fused tanh backward on the tensor cores; weight gradients contract
+    the saved images over the batch with library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w2, b2, w4, b4, layer, inverse):
+        out, ld, saved = layer_forward_saving(layer, x.detach(), inverse)
+        xs, h1, h2, inv = saved
+        ctx.save_for_backward(xs, h1, h2)
+        ctx.layer, ctx.inv = layer, inv
+        return out, ld
+
+    @staticmethod
+    def backward(ctx, g_out, g_ld):
+        xs, h1, h2 = ctx.saved_tensors
+        layer = ctx.layer
+        N = xs.shape[0]
+        if g_out is None:
+            g_out = torch.zeros_like(xs)
+        if g_ld is None:
+            g_ld = torch.zeros(N, dtype=torch.float32, device=xs.device)
+        g_in, (g_img, dz2, dz1) = layer_backward(layer, (xs, h1, h2, ctx.inv), g_out, g_ld, keep=True)
+        need_w = any(ctx.needs_input_grad[1:7])
+        if not need_w:
+            return (g_in,) + (None,) * 8
+        net = layer.psi.network
+        H, n_t = net[4].in_features, net[4].out_features // 23
+        n_tiles = (n_t + 7) // 8
+        l1 = packed(layer.psi)[0]
+        G = unpack_rows(g_img, N, n_tiles * 192)                     # dL/dparams, 24 columns per feature
+        h2r, h1r = unpack_rows(h2, N, H), unpack_rows(h1, N, H)
+        dz2r, dz1r = unpack_rows(dz2, N, H), unpack_rows(dz1, N, H)
+        xc = unpack_rows(pack_input(xs, layer.size, layer.dim, layer._mask, l1["KB"]), N, net[0].in_features)
+        gw4 = _mm_f32(G, h2r).reshape(n_tiles * 8, 24, H)[:n_t, :23].reshape(n_t * 23, H)
+        gb4 = torch.sum(G, dim=0, dtype=torch.float32).reshape(n_tiles * 8, 24)[:n_t, :23].reshape(-1)
+        gw2 = _mm_f32(dz2r, h1r)
+        gb2 = torch.sum(dz2r, dim=0, dtype=torch.float32)
+        gw0 = _mm_f32(dz1r, xc)
+        gb0 = torch.sum(dz1r, dim=0, dtype=torch.float32)
+        return g_in, gw0, gb0, gw2, gb2, gw4, gb4, None, None
 
 
 def flow_grad_eligible(model) -> bool:

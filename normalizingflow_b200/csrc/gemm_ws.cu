@@ -740,6 +740,26 @@ pack_a_img_kernel(const float* __restrict__ x, unsigned char* __restrict__ img, 
   }
 }
 
+// bf16 image [m_tiles][KB][128][64] -> row-major bf16 [M, ld] (first ncols columns): hands the saved
+// activations / gradient images to the weight-gradient GEMMs.  One thread per 16-byte chunk.
+__global__ void __launch_bounds__(256)
+unpack_img_rows_kernel(const unsigned char* __restrict__ img, unsigned char* __restrict__ rows, long long M,
+                       int KB, int ncols, long long ld) {
+  const long long m_tiles = (M + 127) / 128;
+  const long long total = m_tiles * KB * 128 * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int slot = (int)(i & 7);
+    const int r = (int)((i >> 3) & 127);
+    const long long blk = i >> 10;
+    const int kb = (int)(blk % KB);
+    const long long row = (blk / KB) * 128 + r;
+    const int col = kb * 64 + (slot ^ (r & 7)) * 8;
+    if (row < M && col + 8 <= ncols)
+      *reinterpret_cast<uint4*>(rows + (row * ld + col) * 2) = *reinterpret_cast<const uint4*>(img + i * 16);
+  }
+}
+
 // g[:, s*dim + mask[j]] += dxc[:, s*n_mask + j]: the conditioner-input gradient joins the direct path
 __global__ void __launch_bounds__(256)
 scatter_add_cols_kernel(float* __restrict__ g, const float* __restrict__ dxc, long long N, int size, int dim,
@@ -994,6 +1014,23 @@ int nfk_gemm_ws_rqs_bwd(const void* a_img, const void* w_img, const float* bias,
   a.c = make_rqs_consts(8, B);
   cudaStream_t st = (cudaStream_t)stream;
   return inverse ? launch_ws<EPI_RQS_BWD, 0, true>(a, st) : launch_ws<EPI_RQS_BWD, 0, false>(a, st);
+}
+
+int nfk_unpack_img_rows(const void* img, void* rows, int64_t M, int KB, int ncols, int64_t ld, void* stream) {
+  NFK_REQUIRE(M >= 0 && KB > 0 && ncols > 0 && ncols <= KB * 64 && ncols % 8 == 0 && ld >= ncols && ld % 8 == 0,
+              "unpack_img_rows: need ncols, ld multiples of 8 with ncols <= 64*KB <= ... and ld >= ncols");
+  if (M == 0) return NFK_OK;
+  NFK_REQUIRE(img && rows, "unpack_img_rows: null device pointer");
+  NFK_REQUIRE(((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(rows)) & 15) == 0,
+              "unpack_img_rows: pointers must be 16-byte aligned");
+  const long long total = ((M + 127) / 128) * KB * 128 * 8;
+  long long grid = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  unpack_img_rows_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned char*>(img), reinterpret_cast<unsigned char*>(rows), M, KB, ncols, ld);
+  count_launch();
+  return check_launch("unpack_img_rows");
 }
 
 int nfk_scatter_add_cols(float* g, const float* dxc, int64_t N, int size, int dim, const int32_t* cols, int n_cols,

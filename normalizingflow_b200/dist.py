@@ -32,6 +32,55 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> Optional[str]:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that pinned host
+    buffers allocated afterwards (first touch) and the copy-issuing thread are local to the GPU's
+    PCIe root: with 8 ranks streaming host batches, cross-socket traffic is what caps the
+    end-to-end rate.  Best effort: returns a one-line description, or None when the topology
+    cannot be read (then nothing is changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(_physical_index(local_rank))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                                  # 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(set(cpus) & allowed)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"GPU {local_rank} ({bdf}) -> NUMA node {node}, {len(cpus)} CPUs"
+    except Exception:                                           # noqa: BLE001 - best effort by design
+        return None
+
+
+def _physical_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        if local_rank < len(ids) and ids[local_rank].strip().isdigit():
+            return int(ids[local_rank])
+    return local_rank
+
+
+def _parse_cpulist(text: str):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            out.extend(range(int(a), int(b) + 1))
+        else:
+            out.append(int(part))
+    return out
+
+
 def shard_rows(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous row range [start, stop) of ``rank``; sizes differ by at most one row."""
     base, rem = divmod(n_total, world)

@@ -206,6 +206,16 @@ class NSF_CL(nn.Module):
                 out, ld, _ = _ops.rqs_coupling(x, params, self.size, self.dim, self._mask, self.K, float(self.B),
                                                inverse, self.arith, logdet=logdet)
                 return out, ld
+        if not no_grad and self.fused and x.dtype == torch.float32:
+            from . import _wide
+            if _wide.grad_eligible(self):
+                # training / gradient path on the tensor cores (forward keeps the activation images)
+                net = self.psi.network
+                out, ld = _wide.NsfWideFn.apply(x, net[0].weight, net[0].bias, net[2].weight, net[2].bias,
+                                                net[4].weight, net[4].bias, self, bool(inverse))
+                if logdet is not None:
+                    ld = logdet + ld
+                return out, ld
         params = self.psi(self._lower(x)).reshape(-1, n_t, 3 * self.K - 1)   # flows.py:231
         if torch.is_grad_enabled() and (x.requires_grad or params.requires_grad):
             out, ld = _ops.RqsCouplingFn.apply(x, params, self.size, self.dim, tuple(self._mask), self.K,

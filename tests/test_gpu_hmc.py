@@ -90,6 +90,8 @@ def test_tensor_core_force_matches_autograd_and_oracle():
     sim = FlowSimulation(m, n_chains=x.shape[0], init_pos=x)
     U, F = sim.potential_and_force(sim.get_position())
     sim.tensor_core_grad = False
+    for f in m.flows:
+        f.fused = False                                   # reference: unfused autograd Functions
     U2, F2 = sim.potential_and_force(sim.get_position())
     scale = float(F2.abs().max())
     assert rel_err(U, U2.double().cpu()) <= 2e-3
@@ -126,9 +128,20 @@ def test_layer_backward_matches_autograd(inverse, size, dim, mask, H):
     r = torch.randn(N, d, generator=gen).cuda()
     s = torch.randn(N, generator=gen).cuda()
     xg = x.clone().requires_grad_()
+    lay.fused = False
     out, ld = (lay.inverse if inverse else lay.forward)(xg)          # autograd Functions (unfused)
-    (gref,) = torch.autograd.grad((out * r).sum() + (ld * s).sum(), xg)
+    names = [n for n, _ in lay.named_parameters()]
+    gall = torch.autograd.grad((out * r).sum() + (ld * s).sum(), [xg] + list(lay.parameters()))
+    gref = gall[0]
+    lay.fused = True
     assert _wide.grad_eligible(lay)
+    # training path: the same loss through NsfWideFn (tensor-core dgrad, batch-contraction wgrad)
+    xg2 = x.clone().requires_grad_()
+    out_t, ld_t = (lay.inverse if inverse else lay.forward)(xg2)
+    gtrain = torch.autograd.grad((out_t * r).sum() + (ld_t * s).sum(), [xg2] + list(lay.parameters()))
+    for n, ga, gb in zip(["x"] + names, gtrain, gall):
+        scale = max(1e-6, float(gb.abs().max()))
+        assert float((ga - gb).abs().max()) <= 4e-2 * scale, (n, float((ga - gb).abs().max()), scale)
     with torch.no_grad():
         o2, l2, ctx = _wide.layer_forward_saving(lay, x, inverse)
         gin = _wide.layer_backward(lay, ctx, r, s)

@@ -109,6 +109,28 @@ def cfg5(C, H, precision):
             "ms_per_logprob_grad_eval": dt / evals * 1e3, "chain_grad_evals_per_s": C * evals / dt, "accept_rate": acc}
 
 
+def cfg_train(N, H, precision):
+    """forward-KL training step (applications/src/train.py:22-29) of the cfg-2 flow:
+    loss = -mean(prior_logprob + log_det), backward through every layer, Adam."""
+    torch.manual_seed(0)
+    fl = [NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=H, mask=[i % 2]) for i in range(8)]
+    for f in fl:
+        f.psi.precision = precision
+    m = NormalizingFlowModel(GaussianPrior(64, device=dev), fl, device=dev).to(dev)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    x = torch.randn(N, 64, device=dev)
+
+    def step():
+        z, plp, ld = m(x)
+        loss = -torch.mean(plp + ld)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    t = timeit(step, iters=3, warm=2)
+    return {"config": f"A11: forward-KL train step, 8 x NSF_CL(32, dim 2, K 8, H={H}, {precision} conditioner), batch {N}",
+            "train_step_ms": t, "train_samples_per_s": N / t * 1e3}
+
+
 def cfg_nsf_ar(N, precision):
     """the shipped LJ experiment (applications/input/LJ.yaml): 2 x NSF_AR(dim = 32*3,
     K = 32 splines, hidden 354); B = 3."""
@@ -134,7 +156,9 @@ def main():
     n4 = 1 << 18 if a.quick else 1 << 20
     for fn in (lambda: cfg1(100), lambda: cfg1(800), lambda: cfg3(n3), lambda: cfg4(n4),
                lambda: cfg5(65536, 128, "fp32"), lambda: cfg5(65536, 128, "bf16"),
-               lambda: cfg_nsf_ar(65536, "fp32"), lambda: cfg_nsf_ar(65536, "bf16")):
+               lambda: cfg_nsf_ar(65536, "fp32"), lambda: cfg_nsf_ar(65536, "bf16"),
+               lambda: cfg_train(262144, 128, "fp32"), lambda: cfg_train(262144, 128, "bf16"),
+               lambda: cfg_train(262144, 800, "bf16")):
         l0 = _lib.launch_count()
         r = fn()
         r["libnfk_launches"] = _lib.launch_count() - l0
