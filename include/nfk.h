@@ -255,6 +255,21 @@ int nfk_gather_cols(const float* x, void* out, int64_t N, int size, int dim,
                     void* stream);
 int nfk_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
 
+/* ---- priors / targets evaluated next to the flow (applications/src/systems.py)
+ * EinsteinCrystal.log_prob (systems.py:360-366): x [N, natoms*dim], centers [natoms*dim] -> out [N];
+ * boxlength <= 0 = no minimum-image wrap; grad_x (nullable) receives d log_prob / dx. */
+int nfk_einstein_logprob(const float* x, const float* centers, float* out, float* grad_x, int64_t N,
+                         int natoms, int dim, float alpha, float boxlength, void* stream);
+/* LJ.potential (systems.py:154-189): pos [N, nparticles, dim] -> out [N]; minimum image when
+ * boxlength > 0, cutoff <= 0 = none, shift as in the reference; grad_pos (nullable) receives dU/dpos. */
+int nfk_lj_potential(const float* pos, float* out, float* grad_pos, int64_t N, int nparticles, int dim,
+                     float boxlength, float epsilon, float sigma, float cutoff, int shift,
+                     void* stream);
+/* GaussianMixture.log_prob (systems.py:287-292): x [N, npoints, dim], centers [nc, dim], vars [nc]
+ * -> out [N] = sum over points of log(mean_c N(x; mu_c, var_c I)). */
+int nfk_gmm_logprob(const float* x, const float* centers, const float* vars, float* out, int64_t N,
+                    int npoints, int dim, int ncenters, void* stream);
+
 /* ---- leapfrog pieces for flow-preconditioned HMC (hmc.py:34-41 drives
  * simulation.integration_step; the integrator pattern is applications/src/systems.py:331-336).
  * kick-drift: p += 0.5*dt*F ; q += dt*inv_mass*p.   kick: p += 0.5*dt*F. */

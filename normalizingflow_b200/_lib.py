@@ -74,6 +74,9 @@ SIGNATURES = {
     "nfk_pack_a_img": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, c_int, _P]),
     "nfk_gather_cols": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int64, _P]),
     "nfk_cast_f32_bf16": (c_int, [_P, _P, c_int64, _P]),
+    "nfk_einstein_logprob": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_float, c_float, _P]),
+    "nfk_lj_potential": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_float, c_float, c_float, c_float, c_int, _P]),
+    "nfk_gmm_logprob": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "nfk_leapfrog_kick_drift": (c_int, [_P, _P, _P, c_int64, c_float, c_float, _P]),
     "nfk_leapfrog_kick": (c_int, [_P, _P, c_int64, c_float, _P]),
 }

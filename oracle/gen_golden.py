@@ -237,6 +237,44 @@ def fix_checkpoint(out_dir):
     np.savez_compressed(os.path.join(out_dir, "ref_checkpoint_out.npz"), x=npy(x), z=npy(z), plp=npy(plp), ld=npy(ld))
 
 
+def fix_systems(out_dir):
+    """Priors / targets of applications/src/systems.py (EinsteinCrystal, LJ.potential, GaussianMixture) run
+    unmodified (stub modules for lammps / MDAnalysis / matplotlib, which these three never touch)."""
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.path.insert(0, os.path.join(REF, "applications"))
+    from src import systems as ref_sys
+    rec = {}
+    # Einstein crystal: lattice + displaced samples, with and without the periodic wrap
+    g0 = gen(1000)
+    centers = (torch.rand(12, 3, generator=g0) - 0.5) * 3.6
+    for tag, alpha, box in (("ec_free", 50, None), ("ec_box", 1000, 4.0)):
+        ec = ref_sys.EinsteinCrystal(centers.tolist(), dim=3, boxlength=box, alpha=alpha)
+        x = (centers + torch.randn(40, 12, 3, generator=g0) * (3.0 / alpha) ** 0.5).reshape(40, -1)
+        if box is not None:
+            x[:5] += box                                   # images one box length away: wrapped back
+        rec.update({tag + ".centers": npy(centers), tag + ".alpha": float(alpha), tag + ".box": float(box or 0.0),
+                    tag + ".x": npy(x), tag + ".lp": npy(ec.log_prob(x.clone()))})
+    # Lennard-Jones: jittered cubic lattice (no overlaps), all four cutoff/shift combinations
+    n_side, a0 = 3, 1.15
+    grid = torch.stack(torch.meshgrid(*[torch.arange(n_side) * a0] * 3, indexing="ij"), -1).reshape(-1, 3).float()
+    box = n_side * a0
+    pos = grid[None] + 0.08 * torch.randn(30, n_side ** 3, 3, generator=g0) - box / 2
+    rec.update({"lj.pos": npy(pos), "lj.box": float(box)})
+    for tag, cutoff, shift in (("lj_nocut", None, True), ("lj_cut_shift", 1.6, True), ("lj_cut", 1.6, False)):
+        lj = ref_sys.LJ(boxlength=box, epsilon=1.3, sigma=0.95, cutoff=cutoff, shift=shift)
+        rec.update({tag + ".cutoff": float(cutoff or 0.0), tag + ".shift": int(shift),
+                    tag + ".U": npy(lj.potential(pos.clone()))})
+    # Gaussian mixture
+    gm_c = [[-1.0, 0.5], [1.2, -0.3], [0.1, 1.4], [0.0, 0.0]]
+    gm_v = [0.5, 0.3, 0.8, 0.2]
+    gm = ref_sys.GaussianMixture(gm_c, gm_v, npoints=3, dim=2)
+    xg = torch.randn(50, 6, generator=g0) * 1.2
+    rec.update({"gm.centers": np.array(gm_c, dtype=np.float32), "gm.vars": np.array(gm_v, dtype=np.float32),
+                "gm.x": npy(xg), "gm.lp": npy(gm.log_prob(xg))})
+    np.savez_compressed(os.path.join(out_dir, "systems.npz"), **rec)
+
+
 def init_radial(layer, d, seed):
     with torch.no_grad():
         b = math.sqrt(1 / d)
@@ -450,6 +488,7 @@ def main():
     fix_hmc(a.out)
     fix_nsf_ar(a.out)
     fix_checkpoint(a.out)
+    fix_systems(a.out)
     tot = sum(os.path.getsize(os.path.join(a.out, f)) for f in os.listdir(a.out))
     print("wrote", sorted(os.listdir(a.out)), "total bytes", tot)
 

@@ -235,6 +235,54 @@ def nsf_ar(x: torch.Tensor, net: Dict[str, torch.Tensor], dim: int, K: int, B: f
 
 
 # --------------------------------------------------------------------------------------
+# priors / targets next to the flow (applications/src/systems.py)
+# --------------------------------------------------------------------------------------
+def einstein_logprob(x: torch.Tensor, centers: torch.Tensor, dim: int, alpha: float, boxlength=None):
+    """EinsteinCrystal.log_prob (systems.py:360-366) with noise = MultivariateNormal(0, I/alpha)."""
+    from torch.distributions import MultivariateNormal
+    natoms = centers.shape[0]
+    noise = MultivariateNormal(torch.zeros(dim, dtype=x.dtype), 1 / alpha * torch.eye(dim, dtype=x.dtype))
+    dev = x.reshape(-1, natoms, dim) - centers
+    if boxlength is not None:
+        dev = dev - (torch.abs(dev) > 0.5 * boxlength) * torch.sign(dev) * boxlength
+    return torch.sum(noise.log_prob(dev.reshape(-1, dim)).reshape(-1, natoms), dim=1)
+
+
+def lj_potential(pos: torch.Tensor, boxlength: float, epsilon=1.0, sigma=1.0, cutoff=None, shift=True):
+    """LJ.potential (systems.py:154-189) on pos [..., n, dim]."""
+    pair_dist = pos.unsqueeze(-2) - pos.unsqueeze(-3)
+    pair_dist = pair_dist - (torch.abs(pair_dist) > 0.5 * boxlength) * torch.sign(pair_dist) * boxlength
+    distances = torch.linalg.norm(pair_dist.float(), axis=-1)
+    scaled = distances + (distances == 0)
+    inv = 1 / scaled
+    if cutoff is not None:
+        inv = inv - (distances > cutoff) * inv
+        pow_6 = torch.pow(sigma * inv, 6)
+        if shift:
+            s = (sigma / cutoff) ** 6
+            pair = epsilon * 4 * (torch.pow(pow_6, 2) - pow_6 - s ** 2 + s)
+        else:
+            pair = epsilon * 4 * (torch.pow(pow_6, 2) - pow_6)
+    else:
+        pow_6 = torch.pow(sigma * inv, 6)
+        pair = epsilon * 4 * (torch.pow(pow_6, 2) - pow_6)
+    pair = pair * inv * distances
+    return torch.sum(pair, axis=(-1, -2)) / 2
+
+
+def gmm_logprob(x: torch.Tensor, centers: torch.Tensor, vars_: torch.Tensor, npoints: int, dim: int):
+    """GaussianMixture.log_prob (systems.py:287-292): plain exp-sum over the components."""
+    from torch.distributions import MultivariateNormal
+    pts = x.reshape(-1, dim)
+    prob = 0
+    nc = centers.shape[0]
+    for i in range(nc):
+        d = MultivariateNormal(centers[i], vars_[i] * torch.eye(dim, dtype=x.dtype))
+        prob = prob + 1 / nc * torch.exp(d.log_prob(pts))
+    return torch.sum(torch.log(prob).reshape(-1, npoints), axis=1)
+
+
+# --------------------------------------------------------------------------------------
 # RealNVP, Planar, Radial
 # --------------------------------------------------------------------------------------
 def realnvp(x: torch.Tensor, net: Dict[str, torch.Tensor], inverse: bool, prefix: str = ""):

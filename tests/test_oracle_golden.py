@@ -145,3 +145,20 @@ def test_nsf_ar(tag):
     back, ldb, _ = O.nsf_ar(z, sd, dim, K, B, True)
     assert rel_err(back, g[tag + ".x"]) <= 2e-4
     assert rel_err(ld + ldb, torch.zeros_like(ld)) <= 2e-4
+
+
+def test_systems_priors_and_targets():
+    """EinsteinCrystal.log_prob, LJ.potential, GaussianMixture.log_prob (applications/src/systems.py;
+    SURVEY 8(f) N2): oracle restatements vs the unmodified reference."""
+    g = golden("systems.npz")
+    for tag in ("ec_free", "ec_box"):
+        box = float(g[tag + ".box"]) or None
+        lp = O.einstein_logprob(T(g[tag + ".x"]), T(g[tag + ".centers"]), 3, float(g[tag + ".alpha"]), box)
+        assert rel_err(lp, g[tag + ".lp"]) <= 1e-6
+    pos, box = T(g["lj.pos"]), float(g["lj.box"])
+    for tag in ("lj_nocut", "lj_cut_shift", "lj_cut"):
+        cutoff = float(g[tag + ".cutoff"]) or None
+        U = O.lj_potential(pos, box, 1.3, 0.95, cutoff, bool(int(g[tag + ".shift"])))
+        assert rel_err(U, g[tag + ".U"]) <= 1e-6
+    lp = O.gmm_logprob(T(g["gm.x"]), T(g["gm.centers"]), T(g["gm.vars"]), 3, 2)
+    assert rel_err(lp, g["gm.lp"]) <= 1e-6

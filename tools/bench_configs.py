@@ -131,6 +131,22 @@ def cfg_train(N, H, precision):
             "train_step_ms": t, "train_samples_per_s": N / t * 1e3}
 
 
+def cfg_targets(N):
+    """the prior / target next to the flow in the shipped LJ experiment
+    (applications/input/LJ.yaml: 32 particles, Einstein-crystal prior alpha 1000, LJ target)."""
+    from normalizingflow_b200 import systems
+    torch.manual_seed(0)
+    centers = (torch.rand(32, 3) - 0.5) * 3.0
+    ec = systems.EinsteinCrystal(centers, dim=3, boxlength=3.4, alpha=1000)
+    lj = systems.LJ(boxlength=3.4, cutoff=1.6, shift=True)
+    x = ec.sample(N)
+    t_ec = timeit(lambda: ec.log_prob(x))
+    t_lj = timeit(lambda: lj.potential(x.reshape(N, 32, 3)))
+    return {"config": f"N2: EinsteinCrystal.log_prob + LJ.potential, 32 particles (d=96), batch {N}",
+            "einstein_logprob_ms": t_ec, "einstein_GBps": N * 96 * 4 / t_ec / 1e6, "lj_potential_ms": t_lj,
+            "lj_pairs_per_s": N * 32 * 32 / t_lj * 1e3}
+
+
 def cfg_nsf_ar(N, precision):
     """the shipped LJ experiment (applications/input/LJ.yaml): 2 x NSF_AR(dim = 32*3,
     K = 32 splines, hidden 354); B = 3."""
@@ -158,7 +174,7 @@ def main():
                lambda: cfg5(65536, 128, "fp32"), lambda: cfg5(65536, 128, "bf16"),
                lambda: cfg_nsf_ar(65536, "fp32"), lambda: cfg_nsf_ar(65536, "bf16"),
                lambda: cfg_train(262144, 128, "fp32"), lambda: cfg_train(262144, 128, "bf16"),
-               lambda: cfg_train(262144, 800, "bf16")):
+               lambda: cfg_train(262144, 800, "bf16"), lambda: cfg_targets(1 << 20)):
         l0 = _lib.launch_count()
         r = fn()
         r["libnfk_launches"] = _lib.launch_count() - l0
