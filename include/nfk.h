@@ -270,6 +270,16 @@ int nfk_lj_potential(const float* pos, float* out, float* grad_pos, int64_t N, i
 int nfk_gmm_logprob(const float* x, const float* centers, const float* vars, float* out, int64_t N,
                     int npoints, int dim, int ncenters, void* stream);
 
+/* ---- free-energy estimators on the device
+ * BAR fixed point (applications/src/bar.py:16-67): w_F [T_F], w_R [T_R] work values (fp32, or fp64 when
+ * is_f64), fp64 arithmetic, the whole iteration runs in one launch; out[0] = DeltaF, out[1] =
+ * iterations used (device doubles). */
+int nfk_bar(const void* w_F, const void* w_R, int64_t T_F, int64_t T_R, int is_f64, double DeltaF,
+            int max_iter, double rtol, double* out, void* stream);
+/* out[c] = logsumexp_r a[r, c] - log(rows): log-mean-exp reweighting (applications/src/test.py:66-68,
+ * dynamics.py:36) */
+int nfk_log_mean_exp(const float* a, float* out, int64_t rows, int64_t cols, void* stream);
+
 /* ---- leapfrog pieces for flow-preconditioned HMC (hmc.py:34-41 drives
  * simulation.integration_step; the integrator pattern is applications/src/systems.py:331-336).
  * kick-drift: p += 0.5*dt*F ; q += dt*inv_mass*p.   kick: p += 0.5*dt*F. */

@@ -77,6 +77,8 @@ SIGNATURES = {
     "nfk_einstein_logprob": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_float, c_float, _P]),
     "nfk_lj_potential": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_float, c_float, c_float, c_float, c_int, _P]),
     "nfk_gmm_logprob": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "nfk_bar": (c_int, [_P, _P, c_int64, c_int64, c_int, ctypes.c_double, c_int, ctypes.c_double, _P, _P]),
+    "nfk_log_mean_exp": (c_int, [_P, _P, c_int64, c_int64, _P]),
     "nfk_leapfrog_kick_drift": (c_int, [_P, _P, _P, c_int64, c_float, c_float, _P]),
     "nfk_leapfrog_kick": (c_int, [_P, _P, c_int64, c_float, _P]),
 }

@@ -275,6 +275,23 @@ def fix_systems(out_dir):
     np.savez_compressed(os.path.join(out_dir, "systems.npz"), **rec)
 
 
+def fix_bar(out_dir):
+    """BAR free-energy estimate of the UNMODIFIED applications/src/bar.py (pure numpy) on seeded work values:
+    forward works ~ N(2.0 + 0.5 s^2, s), reverse works ~ N(-2.0 + 0.5 s^2, s) (exact DeltaF = 2.0)."""
+    sys.path.insert(0, os.path.join(REF, "applications"))
+    from src import bar as ref_bar
+    rec = {}
+    rng = np.random.default_rng(7)
+    for tag, s, nF, nR in (("a", 1.0, 4000, 4000), ("b", 2.5, 6000, 1500), ("c", 0.3, 300, 900)):
+        wF = rng.normal(2.0 + 0.5 * s * s, s, nF)
+        wR = rng.normal(-2.0 + 0.5 * s * s, s, nR)
+        rec[tag + ".wF"], rec[tag + ".wR"] = wF, wR
+        rec[tag + ".dF64"] = ref_bar.BAR(wF, wR)
+        rec[tag + ".dF32"] = float(ref_bar.BAR(wF.astype(np.float32), wR.astype(np.float32)))
+        rec[tag + ".fzero_at_1"] = ref_bar.BARzero(wF, wR, 1.0)
+    np.savez_compressed(os.path.join(out_dir, "bar.npz"), **rec)
+
+
 def init_radial(layer, d, seed):
     with torch.no_grad():
         b = math.sqrt(1 / d)
@@ -489,6 +506,7 @@ def main():
     fix_nsf_ar(a.out)
     fix_checkpoint(a.out)
     fix_systems(a.out)
+    fix_bar(a.out)
     tot = sum(os.path.getsize(os.path.join(a.out, f)) for f in os.listdir(a.out))
     print("wrote", sorted(os.listdir(a.out)), "total bytes", tot)
 

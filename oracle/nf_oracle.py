@@ -283,6 +283,40 @@ def gmm_logprob(x: torch.Tensor, centers: torch.Tensor, vars_: torch.Tensor, npo
 
 
 # --------------------------------------------------------------------------------------
+# BAR free-energy estimator (applications/src/bar.py)
+# --------------------------------------------------------------------------------------
+def _logsum(a):
+    mx = torch.max(a)
+    return torch.log(torch.sum(torch.exp(a - mx))) + mx                 # bar.py:3-14
+
+
+def bar_zero(w_F: torch.Tensor, w_R: torch.Tensor, DeltaF: float) -> float:
+    """BARzero (bar.py:16-59) in the dtype of the inputs."""
+    T_F, T_R = float(w_F.numel()), float(w_R.numel())
+    M = math.log(T_F / T_R)
+    arg_F = M + w_F - DeltaF
+    max_F = torch.where(arg_F < 0.0, torch.zeros_like(arg_F), arg_F)
+    log_f_F = -max_F - torch.log(torch.exp(-max_F) + torch.exp(arg_F - max_F))
+    log_numer = _logsum(log_f_F) - math.log(T_F)
+    arg_R = M - w_R - DeltaF
+    max_R = torch.where(arg_R < 0.0, torch.zeros_like(arg_R), arg_R)
+    log_f_R = -max_R - torch.log(torch.exp(-max_R) + torch.exp(arg_R - max_R)) - w_R
+    log_denom = _logsum(log_f_R) - math.log(T_R)
+    return float(DeltaF - (log_denom - log_numer))
+
+
+def bar(w_F: torch.Tensor, w_R: torch.Tensor, DeltaF: float = 0.0, maximum_iterations: int = 1000,
+        relative_tolerance: float = 1.0e-5) -> float:
+    """BAR (bar.py:61-67)."""
+    for iteration in range(maximum_iterations):
+        old = DeltaF
+        DeltaF = -bar_zero(w_F, w_R, DeltaF) + DeltaF
+        if iteration > 0 and abs((DeltaF - old) / DeltaF) < relative_tolerance:
+            break
+    return DeltaF
+
+
+# --------------------------------------------------------------------------------------
 # RealNVP, Planar, Radial
 # --------------------------------------------------------------------------------------
 def realnvp(x: torch.Tensor, net: Dict[str, torch.Tensor], inverse: bool, prefix: str = ""):

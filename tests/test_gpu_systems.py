@@ -62,3 +62,29 @@ def test_gaussian_mixture_logprob_and_sample():
     assert rel_err(lp, g["gm.lp"]) <= 1e-5
     s = gm.sample(2000, flatten=False)
     assert s.shape == (2000, 3, 2) and torch.isfinite(gm.log_prob(s.reshape(2000, -1))).all()
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_bar_on_device_matches_reference(tag):
+    """nfk_bar (whole fixed point in one launch, fp64 accumulation) vs applications/src/bar.py."""
+    from normalizingflow_b200 import estimators
+    g = golden("bar.npz")
+    wF, wR = T(g[tag + ".wF"]).cuda(), T(g[tag + ".wR"]).cuda()
+    dF, iters = estimators.BAR(wF, wR, return_iterations=True)
+    assert abs(dF - float(g[tag + ".dF64"])) <= 1e-9 * max(1.0, abs(dF)) and 2 <= iters <= 1000
+    # fp32 work values (what the reference's test.py feeds it): fp64 accumulation agrees with the
+    # reference's fp32 numpy run to the iteration tolerance
+    dF32 = estimators.BAR(wF.float(), wR.float())
+    assert abs(dF32 - float(g[tag + ".dF32"])) <= 2e-4
+    assert abs(dF32 - float(g[tag + ".dF64"])) <= 1e-5
+    # one iteration from DeltaF = 1 is  1 - BARzero(1)
+    one = estimators.BAR(wF, wR, DeltaF=1.0, maximum_iterations=1)
+    assert abs(one - (1.0 - float(g[tag + ".fzero_at_1"]))) <= 1e-9
+
+
+def test_log_mean_exp():
+    from normalizingflow_b200 import estimators
+    a = torch.randn(777, 33, generator=torch.Generator().manual_seed(3)) * 30
+    ref = torch.logsumexp(a.double(), 0) - torch.log(torch.tensor(777.0, dtype=torch.float64))
+    assert rel_err(estimators.log_mean_exp(a.cuda(), 0), ref) <= 1e-6
+    assert rel_err(estimators.log_mean_exp(a.cuda(), 1), torch.logsumexp(a.double(), 1) - torch.log(torch.tensor(33.0, dtype=torch.float64))) <= 1e-6

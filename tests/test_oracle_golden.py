@@ -162,3 +162,13 @@ def test_systems_priors_and_targets():
         assert rel_err(U, g[tag + ".U"]) <= 1e-6
     lp = O.gmm_logprob(T(g["gm.x"]), T(g["gm.centers"]), T(g["gm.vars"]), 3, 2)
     assert rel_err(lp, g["gm.lp"]) <= 1e-6
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_bar_estimator(tag):
+    """BAR / BARzero (applications/src/bar.py): oracle vs the unmodified numpy reference."""
+    g = golden("bar.npz")
+    wF, wR = T(g[tag + ".wF"]), T(g[tag + ".wR"])
+    assert abs(O.bar_zero(wF, wR, 1.0) - float(g[tag + ".fzero_at_1"])) <= 1e-10
+    assert abs(O.bar(wF, wR) - float(g[tag + ".dF64"])) <= 1e-9
+    assert abs(O.bar(wF.float(), wR.float()) - float(g[tag + ".dF32"])) <= 2e-4
