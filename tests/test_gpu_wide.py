@@ -150,3 +150,30 @@ def test_nsf_layer_h800_vs_oracle(inverse):
     ro, rld = O.nsf_cl(x, sd, 32, 2, [1], 8, 3.0, inverse)[:2]
     assert rel_err(out.cpu(), ro) <= 1e-2
     assert rel_err(ld.cpu(), rld) <= 2e-2
+
+
+@pytest.mark.parametrize("N", [0, 1, 127, 129, 300])
+def test_wide_layer_edge_batches_and_nan_tails(N):
+    """Empty, single-row and ragged batches (tail tile of the 128-row M tiling), NaN / out-of-range
+    inputs pass through as identity with zero log-det (quirk Q6) on the spline-epilogue path."""
+    from normalizingflow_b200 import flows
+    torch.manual_seed(4)
+    lay = flows.NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=192, mask=[0])
+    lay.psi.precision = "bf16"
+    lay = lay.cuda()
+    x = torch.randn(N, 64, generator=torch.Generator().manual_seed(9)).cuda()
+    if N:
+        x[0, 1] = float("nan")
+        x[0, 3] = 1e30
+        x[0, 5] = -3.0000002
+    with torch.no_grad():
+        lay.fused = True
+        o1, l1 = lay.forward(x)
+        lay.fused = False
+        o2, l2 = lay.forward(x)
+    assert o1.shape == (N, 64) and l1.shape == (N,)
+    if N:
+        assert torch.isnan(o1[0, 1]) and float(o1[0, 3]) == float(x[0, 3]) and float(o1[0, 5]) == float(x[0, 5])
+        ok = ~torch.isnan(o2)
+        assert rel_err(o1[ok].cpu(), o2[ok].cpu().double()) <= 2e-4
+        assert rel_err(l1.cpu(), l2.cpu().double()) <= 1e-3
