@@ -237,6 +237,13 @@ int nfk_gemm_ws_rqs_bwd(const void* a_img, const void* w_img, const float* bias,
                         float* grad_x, void* grad_params_img, int64_t M, int KB, int kmma_last,
                         int size, int dim, const int32_t* mask, int n_mask, float B, int inverse,
                         void* stream);
+/* fp32 weight matrix W [n_src_rows, n_src_cols] (row stride ld) -> bf16 w_img for nfk_gemm_ws* with KB
+ * K blocks and the given N-tile plan.  transposed != 0 packs W^T (dgrad operands); pad_rows / pad_k
+ * != 0: the output-row / K index runs over 24-per-feature padded spline parameters whose source has 23
+ * per feature.  Everything outside the source is zero.  One launch per layer and parameter version. */
+int nfk_pack_w_img(const float* W, int64_t ld, int n_src_rows, int n_src_cols, void* img, int KB,
+                   const int32_t* tile_blocks /*host*/, int n_tiles, int transposed, int pad_rows,
+                   int pad_k, void* stream);
 /* bf16 image [ceil(M/128)][KB][128][64] -> row-major bf16 rows [M, ld], first ncols columns (ncols, ld
  * multiples of 8): hands saved activations / gradient images to the weight-gradient GEMMs */
 int nfk_unpack_img_rows(const void* img, void* rows, int64_t M, int KB, int ncols, int64_t ld,

@@ -63,6 +63,24 @@ def weight_image(w, bias, kb: int, tiles):
     return torch.cat(parts).contiguous(), bp
 
 
+def pack_weight(w, kb, tiles, transposed=False, pad_rows=False, pad_k=False):
+    """bf16 W image of the fp32 matrix ``w`` in ONE launch (nfk_pack_w_img)."""
+    dev = require_cuda(w)
+    w = f32c(w.detach())
+    img = torch.empty(sum(tiles) * 64 * kb * 64, dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        call("nfk_pack_w_img", ptr(w), w.stride(0), w.shape[0], w.shape[1], ptr(img), kb, i32_array(tiles), len(tiles),
+             int(transposed), int(pad_rows), int(pad_k), stream_ptr(dev))
+    return img
+
+
+def _pad_bias(bias, n, dev):
+    bp = torch.zeros(n, dtype=torch.float32, device=dev)
+    if bias is not None:
+        bp[:bias.numel()] = bias.detach().float()
+    return bp
+
+
 def packed(fcnn):
     """Per-layer (w_img, bias, KB, kmma_last, tiles, n_out) cached on the module."""
     layers = (fcnn.network[0], fcnn.network[2], fcnn.network[4])
@@ -76,7 +94,10 @@ def packed(fcnn):
     for l in layers:
         n_out, k_in = l.weight.shape
         tiles = plan_tiles(blocks(n_out))
-        w_img, b = weight_image(l.weight, l.bias, kb, tiles)
+        if l.weight.is_cuda:
+            w_img, b = pack_weight(l.weight, kb, tiles), _pad_bias(l.bias, sum(tiles) * 64, l.weight.device)
+        else:
+            w_img, b = weight_image(l.weight, l.bias, kb, tiles)
         kmma_last = (k_in - 64 * (kb - 1) + 15) // 16
         out.append(dict(w=w_img, b=b, KB=kb, kmma_last=kmma_last, tiles=tiles, tiles_c=i32_array(tiles),
                         n_out=n_out))
@@ -153,13 +174,11 @@ def packed_rqs(layer):
         dev = last.weight.device
         n_t = last.out_features // 23
         n_tiles = (n_t + 7) // 8
-        w3 = torch.zeros((n_tiles * 8, 24, H), dtype=torch.float32, device=dev)
-        w3[:n_t, :23] = last.weight.detach().float().reshape(n_t, 23, H)
         b3 = torch.zeros((n_tiles * 8, 24), dtype=torch.float32, device=dev)
         b3[:n_t, :23] = last.bias.detach().float().reshape(n_t, 23)
         kb = sum(l2["tiles"])
-        w_img, bp = weight_image(w3.reshape(-1, H), b3.reshape(-1), kb, [3] * n_tiles)
-        l3 = dict(w=w_img, b=bp, KB=kb, kmma_last=(H - 64 * (kb - 1) + 15) // 16)
+        w_img = pack_weight(last.weight, kb, [3] * n_tiles, pad_rows=True)      # 23 -> 24 rows per feature
+        l3 = dict(w=w_img, b=b3.reshape(-1), KB=kb, kmma_last=(H - 64 * (kb - 1) + 15) // 16)
         layer._wide_rqs_cache = cache = (key, l3)
     return l1, l2, cache[1]
 
@@ -203,14 +222,17 @@ def grad_eligible(layer) -> bool:
             and net[4].out_features == 23 * n_t)
 
 
-def _transposed(w, kb):
-    """Layer dict for out = A @ w (w [k_in, n_out]): the dgrad GEMM of y = x w^T.  No bias."""
-    wt = w.detach().float().t().contiguous()            # [n_out, k_in] in nn.Linear orientation
-    n_out, k_in = wt.shape
+def _transposed(w, kb, pad_k=False):
+    """Layer dict for out = A @ w (w [k_in, n_out] as stored, nn.Linear weight of the forward layer):
+    the dgrad GEMM of y = x w^T.  ``pad_k``: the K index runs over 24-per-feature padded spline
+    parameters.  No bias."""
+    n_out = w.shape[1]
+    k_log = kb * 64 if pad_k else w.shape[0]
     tiles = plan_tiles(blocks(n_out))
-    w_img, b = weight_image(wt, None, kb, tiles)
-    return dict(w=w_img, b=b, KB=kb, kmma_last=min(4, (k_in - 64 * (kb - 1) + 15) // 16), tiles=tiles,
-                tiles_c=i32_array(tiles), n_out=n_out)
+    w_img = pack_weight(w, kb, tiles, transposed=True, pad_k=pad_k)
+    return dict(w=w_img, b=torch.zeros(sum(tiles) * 64, dtype=torch.float32, device=w.device), KB=kb,
+                kmma_last=min(4, (k_log - 64 * (kb - 1) + 15) // 16), tiles=tiles, tiles_c=i32_array(tiles),
+                n_out=n_out)
 
 
 def packed_bwd(layer):
@@ -221,15 +243,11 @@ def packed_bwd(layer):
     cache = getattr(layer, "_wide_bwd_cache", None)
     if cache is not None and cache[0] == key:
         return cache[1]
-    H = l4.in_features
-    dev = l4.weight.device
     n_t = l4.out_features // 23
     n_tiles = (n_t + 7) // 8
-    w3 = torch.zeros((n_tiles * 8, 24, H), dtype=torch.float32, device=dev)
-    w3[:n_t, :23] = l4.weight.detach().float().reshape(n_t, 23, H)
-    t3 = _transposed(w3.reshape(-1, H), 3 * n_tiles)          # dH2 = G @ W3p
-    t2 = _transposed(l2.weight, blocks(l2.out_features))      # dH1 = dZ2 @ W2
-    t1 = _transposed(l0.weight, blocks(l0.out_features))      # dXc = dZ1 @ W1
+    t3 = _transposed(l4.weight, 3 * n_tiles, pad_k=True)          # dH2 = G @ W3p
+    t2 = _transposed(l2.weight, blocks(l2.out_features))          # dH1 = dZ2 @ W2
+    t1 = _transposed(l0.weight, blocks(l0.out_features))          # dXc = dZ1 @ W1
     layer._wide_bwd_cache = (key, (t3, t2, t1))
     return t3, t2, t1
 

@@ -740,6 +740,61 @@ pack_a_img_kernel(const float* __restrict__ x, unsigned char* __restrict__ img, 
   }
 }
 
+// fp32 weight matrix -> bf16 W image (per N tile: [KB][64*nb][64], SWIZZLE_128B): one launch per layer
+// and parameter version (training repacks after every optimizer step).  Logical element (out row o,
+// input column k); `transposed` reads W[k, o] (dgrad operands), `pad_rows` / `pad_k` map a padded
+// 24-per-feature index to the 23-per-feature source (spline parameter rows), everything outside the
+// source is zero.  One thread per 16-byte chunk.
+struct PackWArgs {
+  const float* w;
+  unsigned char* img;
+  long long ld;
+  int n_src_rows, n_src_cols;      // shape of the stored matrix
+  int KB, n_tiles, transposed, pad_rows, pad_k;
+  int nb[WS_MAX_TILES];
+};
+__device__ __forceinline__ int unpad24(int i) { return (i % 24 == 23) ? -1 : (i / 24) * 23 + (i % 24); }
+
+__global__ void __launch_bounds__(256) pack_w_img_kernel(const __grid_constant__ PackWArgs a) {
+  long long total = 0;
+  for (int t = 0; t < a.n_tiles; ++t) total += (long long)a.KB * a.nb[t] * 64 * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long rem = i;
+    int t = 0, row0 = 0;
+    for (; t < a.n_tiles; ++t) {
+      const long long sz = (long long)a.KB * a.nb[t] * 64 * 8;
+      if (rem < sz) break;
+      rem -= sz;
+      row0 += a.nb[t] * 64;
+    }
+    const int rows_t = a.nb[t] * 64;
+    const int slot = (int)(rem & 7);
+    const int r = (int)((rem >> 3) % rows_t);
+    const int kb = (int)((rem >> 3) / rows_t);
+    int o = row0 + r;
+    if (a.pad_rows) o = unpad24(o);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      int k = kb * 64 + (slot ^ (r & 7)) * 8 + e;
+      if (a.pad_k) k = unpad24(k);
+      float v = 0.f;
+      if (o >= 0 && k >= 0) {
+        const int sr = a.transposed ? k : o, sc = a.transposed ? o : k;
+        if (sr < a.n_src_rows && sc < a.n_src_cols) v = a.w[(long long)sr * a.ld + sc];
+      }
+      f[e] = v;
+    }
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]);
+    u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]);
+    u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(a.img + i * 16) = u;
+  }
+}
+
 // bf16 image [m_tiles][KB][128][64] -> row-major bf16 [M, ld] (first ncols columns): hands the saved
 // activations / gradient images to the weight-gradient GEMMs.  One thread per 16-byte chunk.
 __global__ void __launch_bounds__(256)
@@ -1014,6 +1069,36 @@ int nfk_gemm_ws_rqs_bwd(const void* a_img, const void* w_img, const float* bias,
   a.c = make_rqs_consts(8, B);
   cudaStream_t st = (cudaStream_t)stream;
   return inverse ? launch_ws<EPI_RQS_BWD, 0, true>(a, st) : launch_ws<EPI_RQS_BWD, 0, false>(a, st);
+}
+
+int nfk_pack_w_img(const float* W, int64_t ld, int n_src_rows, int n_src_cols, void* img, int KB,
+                   const int32_t* tile_blocks, int n_tiles, int transposed, int pad_rows, int pad_k, void* stream) {
+  NFK_REQUIRE(n_src_rows > 0 && n_src_cols > 0 && ld >= n_src_cols && KB > 0, "pack_w_img: bad shape");
+  NFK_REQUIRE(tile_blocks && n_tiles >= 1 && n_tiles <= WS_MAX_TILES, "pack_w_img: 1..%d N tiles", WS_MAX_TILES);
+  NFK_REQUIRE(W && img && (reinterpret_cast<uintptr_t>(img) & 15) == 0, "pack_w_img: bad pointer");
+  PackWArgs a{};
+  a.w = W;
+  a.img = reinterpret_cast<unsigned char*>(img);
+  a.ld = ld;
+  a.n_src_rows = n_src_rows;
+  a.n_src_cols = n_src_cols;
+  a.KB = KB;
+  a.n_tiles = n_tiles;
+  a.transposed = transposed;
+  a.pad_rows = pad_rows;
+  a.pad_k = pad_k;
+  long long total = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    NFK_REQUIRE(tile_blocks[t] >= 1 && tile_blocks[t] <= 4, "pack_w_img: N tile of %d blocks", tile_blocks[t]);
+    a.nb[t] = tile_blocks[t];
+    total += (long long)KB * tile_blocks[t] * 64 * 8;
+  }
+  long long grid = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  pack_w_img_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a);
+  count_launch();
+  return check_launch("pack_w_img");
 }
 
 int nfk_unpack_img_rows(const void* img, void* rows, int64_t M, int KB, int ncols, int64_t ld, void* stream) {
