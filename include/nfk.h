@@ -237,6 +237,14 @@ int nfk_gemm_ws_rqs_bwd(const void* a_img, const void* w_img, const float* bias,
                         float* grad_x, void* grad_params_img, int64_t M, int KB, int kmma_last,
                         int size, int dim, const int32_t* mask, int n_mask, float B, int inverse,
                         void* stream);
+/* weight-gradient GEMM: C[p, q] += sum_n A[n, p] * B[n, q] over the batch rows n of two bf16 images
+ * (a_img [ceil(M/128)][KBa][128][64], b_img [...][KBb][128][64]); the images are consumed as MN-major
+ * tcgen05 operands, split-K over the batch with fp32 atomic accumulation into C [P, ldc] (the caller
+ * zero-initialises C).  pad_p != 0: the A column index runs over 24-per-feature padded spline
+ * parameters and C has the 23-per-feature rows.  Replaces autograd's weight gradient of one
+ * nn.Linear of FCNN (nf/flows.py:26-35). */
+int nfk_wgrad_ws(const void* a_img, const void* b_img, float* C, int64_t ldc, int64_t M, int KBa,
+                 int KBb, int P, int Q, int pad_p, void* stream);
 /* fp32 weight matrix W [n_src_rows, n_src_cols] (row stride ld) -> bf16 w_img for nfk_gemm_ws* with KB
  * K blocks and the given N-tile plan.  transposed != 0 packs W^T (dgrad operands); pad_rows / pad_k
  * != 0: the output-row / K index runs over 24-per-feature padded spline parameters whose source has 23

@@ -67,6 +67,7 @@ SIGNATURES = {
     "nfk_gemm_ws": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int64, _P, _P]),
     "nfk_gemm_ws_rqs_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P,
                                     c_int, c_float, c_int, _P]),
+    "nfk_wgrad_ws": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "nfk_pack_w_img": (c_int, [_P, c_int64, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "nfk_unpack_img_rows": (c_int, [_P, _P, c_int64, c_int, c_int, c_int64, _P]),
     "nfk_scatter_add_cols": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, _P]),

@@ -351,13 +351,23 @@ class NsfWideFn(torch.autograd.Function):
         if not need_w:
             return (g_in,) + (None,) * 8
         net = layer.psi.network
-        H, n_t = net[4].in_features, net[4].out_features // 23
+        H, n_t, n_in = net[4].in_features, net[4].out_features // 23, net[0].in_features
         n_tiles = (n_t + 7) // 8
         l1 = packed(layer.psi)[0]
+        a0 = pack_input(xs, layer.size, layer.dim, layer._mask, l1["KB"])
+        if NATIVE_WGRAD and _lib.have("nfk_wgrad_ws"):
+            # batch contraction straight from the images (MN-major tcgen05 operands, split-K)
+            gw4 = wgrad(g_img, h2, N, n_t * 23, H, pad_p=True)
+            gw2 = wgrad(dz2, h1, N, H, H)
+            gw0 = wgrad(dz1, a0, N, H, n_in)
+            gb4 = image_colsum(g_img, n_tiles * 192).reshape(n_tiles * 8, 24)[:n_t, :23].reshape(-1)
+            gb2 = image_colsum(dz2, H)
+            gb0 = image_colsum(dz1, H)
+            return g_in, gw0, gb0, gw2, gb2, gw4, gb4, None, None
         G = unpack_rows(g_img, N, n_tiles * 192)                     # dL/dparams, 24 columns per feature
         h2r, h1r = unpack_rows(h2, N, H), unpack_rows(h1, N, H)
         dz2r, dz1r = unpack_rows(dz2, N, H), unpack_rows(dz1, N, H)
-        xc = unpack_rows(pack_input(xs, layer.size, layer.dim, layer._mask, l1["KB"]), N, net[0].in_features)
+        xc = unpack_rows(a0, N, n_in)
         gw4 = _mm_f32(G, h2r).reshape(n_tiles * 8, 24, H)[:n_t, :23].reshape(n_t * 23, H)
         gb4 = torch.sum(G, dim=0, dtype=torch.float32).reshape(n_tiles * 8, 24)[:n_t, :23].reshape(-1)
         gw2 = _mm_f32(dz2r, h1r)
@@ -365,6 +375,34 @@ class NsfWideFn(torch.autograd.Function):
         gw0 = _mm_f32(dz1r, xc)
         gb0 = torch.sum(dz1r, dim=0, dtype=torch.float32)
         return g_in, gw0, gb0, gw2, gb2, gw4, gb4, None, None
+
+
+NATIVE_WGRAD = True      # False: weight gradients through image -> rows + library GEMMs (cross-check path)
+
+
+def wgrad(a_img, b_img, M, P, Q, pad_p=False):
+    """C [P, Q] = sum over batch rows of A[n, p] * B[n, q] from two bf16 images (nfk_wgrad_ws)."""
+    dev = a_img.device
+    c = torch.zeros((P, Q), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        tm = _ops.KERNEL_TIMER
+        ev = tm.start("wgrad_ws", dev) if tm is not None else None
+        call("nfk_wgrad_ws", ptr(a_img), ptr(b_img), ptr(c), Q, M, a_img.shape[1], b_img.shape[1], P, Q, int(pad_p),
+             stream_ptr(dev))
+        if ev is not None:
+            tm.stop(ev, dev)
+    return c
+
+
+def image_colsum(img, ncols):
+    """fp32 column sums of a bf16 image over all rows (bias gradients): one reduction over the image,
+    then the 16-byte-chunk swizzle is undone on the [KB, 8, 8, 8] result."""
+    mt, kb, rows, _ = img.shape
+    t = img.view(mt, kb, rows // 8, 8, 8, 8).sum(dim=(0, 2), dtype=torch.float32)      # [kb, r%8, slot, e]
+    r7 = torch.arange(8, device=img.device)[:, None]
+    ch = torch.arange(8, device=img.device)[None, :]
+    sel = t[:, r7, ch ^ r7, :]                                                       # chunk c sits at slot c ^ (r%8)
+    return sel.sum(dim=1).reshape(kb * 64)[:ncols]
 
 
 def flow_grad_eligible(model) -> bool:

@@ -177,3 +177,29 @@ def test_wide_layer_edge_batches_and_nan_tails(N):
         ok = ~torch.isnan(o2)
         assert rel_err(o1[ok].cpu(), o2[ok].cpu().double()) <= 2e-4
         assert rel_err(l1.cpu(), l2.cpu().double()) <= 1e-3
+
+
+@pytest.mark.parametrize("M,P,Q,pad", [(128, 64, 64, False), (1000, 200, 96, False), (5000, 800, 800, False),
+                                        (3000, 736, 200, True), (700, 160, 38, False), (40000, 128, 128, False)])
+def test_wgrad_ws_matches_fp64(M, P, Q, pad):
+    """Batch-contraction GEMM straight from two bf16 images (MN-major tcgen05 operands, split-K with
+    fp32 atomics) vs an fp64 matmul of the same bf16-rounded operands; image column sums (bias
+    gradients) vs a plain sum."""
+    W = _wide()
+    g = torch.Generator().manual_seed(M + P + Q)
+    p_cols = ((P + 22) // 23) * 24 if pad else P                     # padded: 24 columns per feature, 24th zero
+    a = torch.randn(M, p_cols, generator=g)
+    if pad:
+        a.reshape(M, -1, 24)[:, :, 23] = 0
+    b = torch.randn(M, Q, generator=g)
+    a_img = W.pack_input(a.cuda(), p_cols, 1, [0], W.blocks(p_cols))
+    b_img = W.pack_input(b.cuda(), Q, 1, [0], W.blocks(Q))
+    c = W.wgrad(a_img, b_img, M, P, Q, pad_p=pad).cpu()
+    ab = a.to(torch.bfloat16).double()
+    ref = ab.t() @ b.to(torch.bfloat16).double()
+    if pad:
+        ref = ref.reshape(-1, 24, Q)[:, :23].reshape(-1, Q)[:P]
+    scale = float(ref.abs().max())
+    assert float((c - ref).abs().max()) <= 1e-4 * scale, float((c - ref).abs().max()) / scale
+    cs = W.image_colsum(a_img, p_cols).cpu()
+    assert float((cs - ab.sum(0)).abs().max()) <= 1e-4 * float(ab.sum(0).abs().max() + 1)
