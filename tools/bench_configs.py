@@ -97,11 +97,11 @@ def cfg5(C, H, precision):
     m = NormalizingFlowModel(GaussianPrior(64, device=dev), fl, device=dev).to(dev)
     sim = FlowSimulation(m, n_chains=C, nparticles=32, dim=2)
     h = HMC(sim, path_len=10, dt=0.05, dim=2, beta=1.0)
-    h.hmc(epochs=1)
+    h.hmc(epochs=3)                      # warm-up: lazy kernel loading, allocator growth, graph capture
     torch.cuda.synchronize()
     n0 = sim.grad_evals
     t0 = time.perf_counter()
-    pos, pot, logp, acc = h.hmc(epochs=5)
+    pos, pot, logp, acc = h.hmc(epochs=8)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     evals = sim.grad_evals - n0

@@ -11,6 +11,8 @@ from normalizingflow_b200.flows import NSF_CL
 from normalizingflow_b200.hmc import FlowSimulation
 from normalizingflow_b200.models import GaussianPrior, NormalizingFlowModel
 
+from normalizingflow_b200 import _lib
+_lib.lib.nfk_set_gemm_ws_pair_mode(int(os.environ.get("PAIR", -1)))
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 evals = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda:0")

@@ -10,6 +10,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from normalizingflow_b200.flows import NSF_CL
 from normalizingflow_b200.models import GaussianPrior, NormalizingFlowModel
 
+from normalizingflow_b200 import _lib
+_lib.lib.nfk_set_gemm_ws_pair_mode(int(os.environ.get("PAIR", -1)))
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 800
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
 dev = torch.device("cuda:0")
