@@ -212,6 +212,20 @@ int nfk_gemm_ws_last_clusters(void);
 int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* out, int64_t M,
                 int KB, int kmma_last, const int32_t* tile_blocks /*host*/, int n_tiles, int act,
                 int out_f32, int n_out, int64_t ldy, const void* aux, void* stream);
+/* grouped launch: n_groups independent GEMMs with the same N-tile plan, activation, output kind and
+ * row count M run in ONE persistent kernel (work items interleave the groups).  groups_dev is a DEVICE
+ * array of n_groups records {a_img, w_img, bias, out (pointers), KB, kmma_last, a_kb, pad (int32)}, each
+ * nfk_gemm_ws_group_bytes() bytes.  fp32 row outputs share ldy / n_out (a group's `out` may point at its
+ * column offset inside one [M, ldy] tensor).  Used for the dim-1 per-dimension conditioners of NSF_AR
+ * (nf/flows.py:167-169, :186). */
+int nfk_gemm_ws_group_bytes(void);
+int nfk_gemm_ws_grouped(const void* groups_dev, int n_groups, int64_t M, const int32_t* tile_blocks /*host*/,
+                        int n_tiles, int act, int out_f32, int n_out, int64_t ldy, void* stream);
+/* NSF_AR conditioner inputs in one launch (nf/flows.py:172-173, :186): the a_img
+ * [ceil(N/128)][ceil(2*dim/64)][128][64] of the interleaved features [cos(pi x_0/B), sin(pi x_0/B),
+ * cos(pi x_1/B), ...]; conditioner i reads its first ceil(2i/64) K blocks (group record a_kb =
+ * ceil(2*dim/64)) and its weight image carries the columns in the same interleaved order. */
+int nfk_nsf_ar_pack(const float* x, void* img, int64_t N, int dim, float B, void* stream);
 /* last conditioner GEMM with the RQS transform as its epilogue (any size, 2 <= dim <= 4, K = 8,
  * at most 128 transformed features): replaces the third nn.Linear of psi + nf/flows.py:232-239 /
  * :246-253 + nf/utils.py:20-152; the [N, F_t, 23] parameter tensor never reaches HBM.  w_img: each

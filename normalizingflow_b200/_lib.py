@@ -71,6 +71,9 @@ SIGNATURES = {
     "nfk_pack_w_img": (c_int, [_P, c_int64, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "nfk_unpack_img_rows": (c_int, [_P, _P, c_int64, c_int, c_int, c_int64, _P]),
     "nfk_scatter_add_cols": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, _P]),
+    "nfk_gemm_ws_group_bytes": (c_int, []),
+    "nfk_gemm_ws_grouped": (c_int, [_P, c_int, c_int64, _P, c_int, c_int, c_int, c_int, c_int64, _P]),
+    "nfk_nsf_ar_pack": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "nfk_gemm_ws_rqs": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_float, c_int,
                                 c_int, c_int, _P]),
     "nfk_pack_a_img": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, c_int, _P]),

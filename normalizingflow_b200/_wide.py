@@ -432,6 +432,111 @@ def flow_logp_and_grad(model, x):
     return logp, g
 
 
+# ---------------------------------------------------------------------------------------------
+# NSF_AR (nf/flows.py:152-209): the dim-1 per-dimension conditioners as THREE grouped launches
+# ---------------------------------------------------------------------------------------------
+def nsf_ar_grouped_ok(layer) -> bool:
+    ls = list(layer.layers)
+    return (_lib.have("nfk_gemm_ws_grouped") and _lib.have("nfk_nsf_ar_pack") and available() and 2 <= layer.dim <= 128
+            and len(ls) == layer.dim - 1 and all(getattr(f, "precision", None) == "bf16" for f in ls)
+            and all(hasattr(f, "network") and len(f.network) == 5 for f in ls)
+            and len({f.network[0].out_features for f in ls}) == 1)
+
+
+def _group_table(records, dev):
+    """device array of WsGroup records {a_img, w_img, bias, out, KB, kmma_last, a_kb, pad}"""
+    import numpy as np
+    dt = np.dtype([("a", "<u8"), ("w", "<u8"), ("b", "<u8"), ("o", "<u8"), ("kb", "<i4"), ("km", "<i4"),
+                   ("akb", "<i4"), ("pad", "<i4")])
+    assert dt.itemsize == _lib.lib.nfk_gemm_ws_group_bytes()
+    arr = np.array(records, dtype=dt)
+    return torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
+
+
+def _nsf_ar_packs(layer):
+    """Per conditioner (l1, l2, l3) with l1 packed for the INTERLEAVED [cos_0, sin_0, cos_1, ...] input
+    order of the shared feature image (the reference order is [cos_0..cos_{i-1}, sin_0..sin_{i-1}])."""
+    key = tuple((f.network[0].weight._version, f.network[2].weight._version, f.network[4].weight._version,
+                 f.network[0].weight.data_ptr()) for f in layer.layers)
+    cache = getattr(layer, "_ar_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    out = []
+    for g, f in enumerate(layer.layers):
+        i = g + 1
+        l0 = f.network[0]
+        perm = torch.arange(2 * i, device=l0.weight.device).reshape(2, i).t().reshape(-1)   # [0, i, 1, i+1, ...]
+        kb = blocks(2 * i)
+        tiles = plan_tiles(blocks(l0.out_features))
+        l1 = dict(w=pack_weight(l0.weight.detach()[:, perm].contiguous(), kb, tiles),
+                  b=_pad_bias(l0.bias, sum(tiles) * 64, l0.weight.device), KB=kb,
+                  kmma_last=(2 * i - 64 * (kb - 1) + 15) // 16, tiles=tiles, tiles_c=i32_array(tiles),
+                  n_out=l0.out_features)
+        _, l2, l3 = packed(f)
+        out.append((l1, l2, l3))
+    layer._ar_cache = (key, out)
+    layer._ar_tables = {}                 # group tables hold raw addresses of the old weight images
+    return out
+
+
+def nsf_ar_params(layer, x, max_rows=None):
+    """Raw spline parameters [N, dim, 3K-1] of an NSF_AR layer for known inputs x (forward direction):
+    one launch builds the shared trig-feature image, three grouped GEMM launches run the dim-1
+    conditioners (work items interleave the groups), row 0 is ``init_param``."""
+    dev = require_cuda(x)
+    x = f32c(x)
+    N, dim = x.shape
+    P = 3 * layer.K - 1
+    G = dim - 1
+    packs = _nsf_ar_packs(layer)
+    obh = sum(packs[0][0]["tiles"])
+    out = torch.empty((N, dim, P), dtype=torch.float32, device=dev)
+    out[:, 0, :] = layer.init_param.detach().to(dev).float()
+    if max_rows is None:                                           # bound the two hidden-activation buffers to ~8 GB
+        max_rows = max(ROWS, int(4e9 // (G * obh * 64 * 2)) // ROWS * ROWS)
+    kb_img = blocks(2 * dim)
+    tables = getattr(layer, "_ar_tables", None)
+    if tables is None:
+        tables = layer._ar_tables = {}
+    with torch.cuda.device(dev):
+        for r0 in range(0, N, max_rows):
+            r1 = min(N, r0 + max_rows)
+            n = r1 - r0
+            mt = (n + ROWS - 1) // ROWS
+            a0 = torch.empty((mt, kb_img, ROWS, 64), dtype=torch.bfloat16, device=dev)
+            call("nfk_nsf_ar_pack", ptr(x[r0:r1]), ptr(a0), n, dim, float(layer.B), stream_ptr(dev))
+            h1 = torch.empty((G, mt, obh, ROWS, 64), dtype=torch.bfloat16, device=dev)
+            h2 = torch.empty_like(h1)
+            ob = out[r0:r1]
+            hs = mt * obh * ROWS * 64 * 2
+            # the group tables hold raw addresses: rebuilt only when a buffer or a weight image moved
+            key = (a0.data_ptr(), h1.data_ptr(), h2.data_ptr(), ob.data_ptr(), n, id(packs))
+            tabs = tables.get(key)
+            if tabs is None:
+                if len(tables) > 8:
+                    tables.clear()
+                t1 = _group_table([(a0.data_ptr(), packs[g][0]["w"].data_ptr(), packs[g][0]["b"].data_ptr(),
+                                    h1.data_ptr() + g * hs, packs[g][0]["KB"], packs[g][0]["kmma_last"], kb_img, 0)
+                                   for g in range(G)], dev)
+                t2 = _group_table([(h1.data_ptr() + g * hs, packs[g][1]["w"].data_ptr(), packs[g][1]["b"].data_ptr(),
+                                    h2.data_ptr() + g * hs, packs[g][1]["KB"], packs[g][1]["kmma_last"], packs[g][1]["KB"], 0)
+                                   for g in range(G)], dev)
+                t3 = _group_table([(h2.data_ptr() + g * hs, packs[g][2]["w"].data_ptr(), packs[g][2]["b"].data_ptr(),
+                                    ob.data_ptr() + (g + 1) * P * 4, packs[g][2]["KB"], packs[g][2]["kmma_last"],
+                                    packs[g][2]["KB"], 0) for g in range(G)], dev)
+                tabs = tables[key] = (t1, t2, t3)
+            tm = _ops.KERNEL_TIMER
+            for tab, lay, act, f32, tag in ((tabs[0], packs[0][0], 1, 0, "gemm_ws_grouped_l1"),
+                                            (tabs[1], packs[0][1], 1, 0, "gemm_ws_grouped_l2"),
+                                            (tabs[2], packs[0][2], 0, 1, "gemm_ws_grouped_l3")):
+                ev = tm.start(tag, dev) if tm is not None else None
+                call("nfk_gemm_ws_grouped", ptr(tab), G, n, lay["tiles_c"], len(lay["tiles"]), act, f32, P, dim * P,
+                     stream_ptr(dev))
+                if ev is not None:
+                    tm.stop(ev, dev)
+    return out
+
+
 def image_to_rows(img, n_rows, n_cols):
     """Inverse of the image layout (tests): [m_tiles, KB, 128, 64] bf16 image -> [n_rows, n_cols]."""
     m_tiles, kb, rows, _ = img.shape

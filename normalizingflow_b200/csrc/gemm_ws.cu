@@ -76,7 +76,21 @@ static_assert(ws_smem<EPI_BF16_IMG>() <= 227 * 1024 && ws_smem<EPI_RQS>() <= 227
                   ws_smem<EPI_RQS_BWD>() <= 227 * 1024,
               "gemm_ws exceeds the 227 KB shared-memory limit");
 
+// grouped launch: several independent GEMMs (same N-tile plan, own operands / K depth) share one
+// persistent kernel -- the dim-1 per-dimension conditioners of the autoregressive flow NSF_AR
+struct WsGroup {
+  const unsigned char* a_img;
+  const unsigned char* w_img;
+  const float* bias;
+  void* out;
+  int KB, kmma_last;
+  int a_kb;                // K blocks per M tile of a_img (>= KB: several groups may read a prefix of one image)
+  int pad_;
+};
+
 struct WsArgs {
+  const WsGroup* groups;   // device array, or null
+  int n_groups;
   const unsigned char* a_img;
   const unsigned char* w_img;
   const float* bias;       // [64 * sum nb], zero padded
@@ -105,6 +119,25 @@ struct WsArgs {
   const float* gld;        // [M] dL/dlogdet, or null: gld_const for every row
   float gld_const;
 };
+
+// work item pt -> (operands of its group, M-tile index inside the group)
+__device__ __forceinline__ WsGroup ws_item(const WsArgs& a, long long pt, long long& ptile) {
+  if (a.n_groups > 0) {
+    ptile = pt / a.n_groups;
+    return a.groups[pt % a.n_groups];
+  }
+  ptile = pt;
+  WsGroup g;
+  g.a_img = a.a_img;
+  g.w_img = a.w_img;
+  g.bias = a.bias;
+  g.out = a.out;
+  g.KB = a.KB;
+  g.kmma_last = a.kmma_last;
+  g.a_kb = a.KB;
+  g.pad_ = 0;
+  return g;
+}
 
 __device__ __forceinline__ bool ws_elect_one() {
   uint32_t pred;
@@ -217,20 +250,22 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
   const uint32_t tmem = tmem_base_s;
   // work items: M tiles (pair mode: pairs of M tiles, CTA rank r owns tile 2*pt + r)
   const long long first = TWO ? (blockIdx.x >> 1) : blockIdx.x, stride = TWO ? (gridDim.x >> 1) : gridDim.x;
-  const long long n_pt = TWO ? (a.m_tiles + 1) / 2 : a.m_tiles;
+  const long long n_pt = (TWO ? (a.m_tiles + 1) / 2 : a.m_tiles) * (a.n_groups > 0 ? a.n_groups : 1);
 
   if (warp == 0) {
     // ================================ producer ================================
     uint32_t s = 0, ph = 0;
     for (long long pt = first; pt < n_pt; pt += stride) {
-      const long long mt = TWO ? 2 * pt + crank : pt;
+      long long ptile;
+      const WsGroup G = ws_item(a, pt, ptile);
+      const long long mt = TWO ? 2 * ptile + crank : ptile;
       const long long mt_ld = mt < a.m_tiles ? mt : a.m_tiles - 1;      // odd tile count: the pair's spare half
-      const unsigned char* ag = a.a_img + (size_t)mt_ld * a.KB * WS_BLK;
-      const unsigned char* wg = a.w_img;
+      const unsigned char* ag = G.a_img + (size_t)mt_ld * G.a_kb * WS_BLK;
+      const unsigned char* wg = G.w_img;
       for (int t = 0; t < a.n_tiles; ++t) {
         const uint32_t bb = (uint32_t)a.nb[t] * 64u * 128u;
         const uint32_t bl = TWO ? bb / 2 : bb;                           // pair mode: this CTA's half of the B rows
-        for (int kb = 0; kb < a.KB; ++kb) {
+        for (int kb = 0; kb < G.KB; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           if (lane == 0) {
             unsigned char* st = sm + s * WS_STAGE_BYTES;
@@ -244,7 +279,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
             ph ^= 1;
           }
         }
-        wg += (size_t)a.KB * bb;
+        wg += (size_t)G.KB * bb;
       }
     }
   } else if (warp == 1) {
@@ -252,9 +287,11 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
     uint32_t s = 0, ph = 0, tl = 0;
     if (TWO && crank == 1) {
       // odd CTA of the pair: no MMA issue -- forward "my operands landed" to the even CTA
-      for (long long pt = first; pt < n_pt; pt += stride)
+      for (long long pt = first; pt < n_pt; pt += stride) {
+        long long ptile;
+        const WsGroup G = ws_item(a, pt, ptile);
         for (int t = 0; t < a.n_tiles; ++t)
-          for (int kb = 0; kb < a.KB; ++kb) {
+          for (int kb = 0; kb < G.KB; ++kb) {
             mbar_wait(&full[s], ph);
             if (lane == 0) mbar_arrive_leader(&pfull[s]);
             __syncwarp();
@@ -263,21 +300,24 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
               ph ^= 1;
             }
           }
+      }
     } else {
       for (long long pt = first; pt < n_pt; pt += stride) {
+        long long ptile;
+        const WsGroup G = ws_item(a, pt, ptile);
         for (int t = 0; t < a.n_tiles; ++t, ++tl) {
           const uint32_t acc = tl & 1;
           const uint32_t idesc = make_idesc_bf16(TWO ? 2 * WS_M : WS_M, a.nb[t] * 64);
           mbar_wait(&tempty[acc], ((tl >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d = tmem + acc * 256;
-          for (int kb = 0; kb < a.KB; ++kb) {
+          for (int kb = 0; kb < G.KB; ++kb) {
             mbar_wait(&full[s], ph);
             if (TWO) mbar_wait(&pfull[s], ph);
             tc_fence_after();
             if (ws_elect_one()) {
               const uint32_t aa = smem_u32(sm + s * WS_STAGE_BYTES), ba = aa + WS_A_BYTES;
-              const int nm = (kb == a.KB - 1) ? a.kmma_last : 4;
+              const int nm = (kb == G.KB - 1) ? G.kmma_last : 4;
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 if (k < nm) {
@@ -288,10 +328,10 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
                 }
               if (TWO) {
                 umma2_commit(&empty[s]);                     // frees the stage in both CTAs
-                if (kb == a.KB - 1) umma2_commit(&tfull[acc]);
+                if (kb == G.KB - 1) umma2_commit(&tfull[acc]);
               } else {
                 umma_commit(&empty[s]);
-                if (kb == a.KB - 1) umma_commit(&tfull[acc]);
+                if (kb == G.KB - 1) umma_commit(&tfull[acc]);
               }
             }
             __syncwarp();
@@ -319,7 +359,9 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
     const int mask0 = a.mask[0], mask1 = a.mask[1], mask2 = a.mask[2];
     uint32_t tl = 0, it = 0;
     for (long long pt = first; pt < n_pt; pt += stride, ++it) {
-      const long long mt = TWO ? 2 * pt + crank : pt;
+      long long ptile;
+      const WsGroup G = ws_item(a, pt, ptile);
+      const long long mt = TWO ? 2 * ptile + crank : ptile;
       const long long grow = mt * WS_M + row;
       const bool live = grow < a.M;
       const float* xr = a.x + grow * d;
@@ -411,7 +453,9 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
     const int ob_total = 3 * a.n_tiles;
     uint32_t tl = 0;
     for (long long pt = first; pt < n_pt; pt += stride) {
-      const long long mt = TWO ? 2 * pt + crank : pt;
+      long long ptile;
+      const WsGroup G = ws_item(a, pt, ptile);
+      const long long mt = TWO ? 2 * ptile + crank : ptile;
       const long long grow = mt * WS_M + row;
       const bool live = grow < a.M;
       const float* xr = a.x + grow * d;
@@ -501,7 +545,9 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
     int ob_total = 0;
     for (int t = 0; t < a.n_tiles; ++t) ob_total += a.nb[t];
     for (long long pt = first; pt < n_pt; pt += stride) {
-      const long long mt = TWO ? 2 * pt + crank : pt;
+      long long ptile;
+      const WsGroup G = ws_item(a, pt, ptile);
+      const long long mt = TWO ? 2 * ptile + crank : ptile;
       int ob0 = 0;
       for (int t = 0; t < a.n_tiles; ++t, ++tl) {
         const uint32_t acc = tl & 1;
@@ -525,7 +571,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
             if (lane == 0) { if (TWO) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
           }
           const int colb = (ob0 + b) * 64 + h * 32;        // first padded output column of v[]
-          const float4* bp = reinterpret_cast<const float4*>(a.bias + colb);
+          const float4* bp = reinterpret_cast<const float4*>(G.bias + colb);
           uint4 u[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -570,7 +616,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
           fence_proxy_async();
           asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
           if (issuer && mt < a.m_tiles) {
-            unsigned char* og = reinterpret_cast<unsigned char*>(a.out) +
+            unsigned char* og = reinterpret_cast<unsigned char*>(G.out) +
                                 ((size_t)mt * ob_total + (ob0 + b)) * WS_BLK;
             bulk_s2g(og, sb, WS_BLK);
             bulk_commit();
@@ -593,7 +639,9 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
     int ob_total = 0;
     for (int t = 0; t < a.n_tiles; ++t) ob_total += a.nb[t];
     for (long long pt = first; pt < n_pt; pt += stride) {
-      const long long mt = TWO ? 2 * pt + crank : pt;
+      long long ptile;
+      const WsGroup G = ws_item(a, pt, ptile);
+      const long long mt = TWO ? 2 * ptile + crank : ptile;
       int ob0 = 0;
       for (int t = 0; t < a.n_tiles; ++t, ++tl) {
         const uint32_t acc = tl & 1;
@@ -611,7 +659,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
             if (lane == 0) { if (TWO) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
           }
           const int colb = (ob0 + b) * 64 + h * 32;        // first padded output column of v[]
-          const float4* bp = reinterpret_cast<const float4*>(a.bias + colb);
+          const float4* bp = reinterpret_cast<const float4*>(G.bias + colb);
           if (!OUT_F32) {
             unsigned char* sb = stg + (bc & 1) * WS_BLK;
 #pragma unroll
@@ -644,7 +692,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
             if (issuer) bulk_wait_read<0>();
             asm volatile("bar.sync 1, %0;" ::"n"(WS_EPI_WARPS * 32) : "memory");
             if (issuer) {
-              unsigned char* og = reinterpret_cast<unsigned char*>(a.out) +
+              unsigned char* og = reinterpret_cast<unsigned char*>(G.out) +
                                   ((size_t)mt * ob_total + (ob0 + b)) * WS_BLK;
               bulk_s2g(og, sb, WS_BLK);
               bulk_commit();
@@ -672,7 +720,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
             }
             asm volatile("bar.sync 1, %0;" ::"n"(WS_EPI_WARPS * 32) : "memory");
             const int col0 = (ob0 + b) * 64;
-            float* og = reinterpret_cast<float*>(a.out);
+            float* og = reinterpret_cast<float*>(G.out);
 #pragma unroll 4
             for (int rr = 0; rr < 16; ++rr) {
               const int r = ew * 16 + rr;
@@ -795,6 +843,43 @@ __global__ void __launch_bounds__(256) pack_w_img_kernel(const __grid_constant__
   }
 }
 
+// NSF_AR conditioner inputs (reference nf/flows.py:172-173, :186): trig_transform(x[:, :i]) for every
+// dimension i is a PREFIX of one interleaved feature row [cos(pi x_0/B), sin(pi x_0/B), cos(pi x_1/B), ...]:
+// one image of 2*dim columns serves all dim-1 conditioners (conditioner i reads its first ceil(2i/64)
+// K blocks; its weight image is zero beyond column 2i, which masks the later dimensions).
+__global__ void __launch_bounds__(256)
+nsf_ar_pack_kernel(const float* __restrict__ x, unsigned char* __restrict__ img, long long N, long long m_tiles,
+                   int dim, int KB, float pi_f32, float B) {
+  const long long total = m_tiles * KB * 128 * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int slot = (int)(i & 7);
+    const int r = (int)((i >> 3) & 127);
+    const long long blk = i >> 10;
+    const int kb = (int)(blk % KB);
+    const long long row = (blk / KB) * 128 + r;
+    const int k0 = kb * 64 + (slot ^ (r & 7)) * 8;            // 8 columns = 4 dimensions (cos, sin) each
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = (k0 >> 1) + e;
+      float c = 0.f, sn = 0.f;
+      if (row < N && j < dim) {
+        const float ang = pi_f32 * x[row * dim + j] / B;      // torch.tensor(pi) * x / B
+        sincosf(ang, &sn, &c);
+      }
+      f[2 * e] = c;
+      f[2 * e + 1] = sn;
+    }
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]);
+    u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]);
+    u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(img + i * 16) = u;
+  }
+}
+
 // bf16 image [m_tiles][KB][128][64] -> row-major bf16 [M, ld] (first ncols columns): hands the saved
 // activations / gradient images to the weight-gradient GEMMs.  One thread per 16-byte chunk.
 __global__ void __launch_bounds__(256)
@@ -863,13 +948,14 @@ static int launch_ws(const WsArgs& a, cudaStream_t st) {
   constexpr unsigned threads = (2 + WsCfg<EPI>::EPI_WARPS) * 32;
   const long long cap = sm_count();
   // CTA pairs (cta_group::2) once there are enough M tiles to keep every SM pair busy
+  const long long ng = a.n_groups > 0 ? a.n_groups : 1;
   const bool two = g_ws_pair_mode < 0 ? (a.m_tiles >= 2 * cap) : (g_ws_pair_mode != 0 && a.m_tiles >= 2);
   cudaError_t e;
   if (two) {
     auto kern = gemm_ws_kernel<EPI, MODE, INVERSE, PAIRS, true>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-      const long long pairs = (a.m_tiles + 1) / 2;
+      const long long pairs = ((a.m_tiles + 1) / 2) * ng;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)cap);
       cfg.blockDim = dim3(threads);
@@ -903,7 +989,7 @@ static int launch_ws(const WsArgs& a, cudaStream_t st) {
     auto kern = gemm_ws_kernel<EPI, MODE, INVERSE, PAIRS, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-      const unsigned grid = (unsigned)(a.m_tiles < cap ? a.m_tiles : cap);
+      const unsigned grid = (unsigned)(a.m_tiles * ng < cap ? a.m_tiles * ng : cap);
       kern<<<grid, threads, smem, st>>>(a);
     }
   }
@@ -994,6 +1080,53 @@ int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* o
   a.aux = reinterpret_cast<const unsigned char*>(aux);
   cudaStream_t st = (cudaStream_t)stream;
   return out_f32 ? launch_ws<EPI_F32_ROWS, 0, false>(a, st) : launch_ws<EPI_BF16_IMG, 0, false>(a, st);
+}
+
+int nfk_gemm_ws_grouped(const void* groups_dev, int n_groups, int64_t M, const int32_t* tile_blocks, int n_tiles,
+                        int act, int out_f32, int n_out, int64_t ldy, void* stream) {
+  NFK_REQUIRE(M >= 0 && n_groups >= 1, "gemm_ws_grouped: bad shape");
+  NFK_REQUIRE(tile_blocks && n_tiles >= 1 && n_tiles <= WS_MAX_TILES, "gemm_ws_grouped: 1..%d N tiles", WS_MAX_TILES);
+  NFK_REQUIRE(act == 0 || act == 1, "gemm_ws_grouped: act must be 0 (identity) or 1 (tanh)");
+  WsArgs a{};
+  int ob = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    NFK_REQUIRE(tile_blocks[t] >= 1 && tile_blocks[t] <= 4, "gemm_ws_grouped: N tile of %d blocks", tile_blocks[t]);
+    a.nb[t] = tile_blocks[t];
+    ob += tile_blocks[t];
+  }
+  if (out_f32) NFK_REQUIRE(n_out >= 1 && n_out <= ob * 64 && ldy >= n_out, "gemm_ws_grouped: bad fp32 output shape");
+  if (M == 0) return NFK_OK;
+  NFK_REQUIRE(groups_dev && (reinterpret_cast<uintptr_t>(groups_dev) & 7) == 0, "gemm_ws_grouped: bad group table");
+  a.groups = reinterpret_cast<const WsGroup*>(groups_dev);
+  a.n_groups = n_groups;
+  a.m_tiles = (M + WS_M - 1) / WS_M;
+  a.M = M;
+  a.ldy = ldy;
+  a.n_tiles = n_tiles;
+  a.n_out = n_out;
+  a.act = act;
+  a.KB = 1;
+  a.kmma_last = 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  return out_f32 ? launch_ws<EPI_F32_ROWS, 0, false>(a, st) : launch_ws<EPI_BF16_IMG, 0, false>(a, st);
+}
+
+int nfk_gemm_ws_group_bytes(void) { return (int)sizeof(WsGroup); }
+
+int nfk_nsf_ar_pack(const float* x, void* img, int64_t N, int dim, float B, void* stream) {
+  NFK_REQUIRE(N >= 0 && dim >= 2 && B > 0.f, "nsf_ar_pack: need dim >= 2 and B > 0");
+  if (N == 0) return NFK_OK;
+  NFK_REQUIRE(x && img && (reinterpret_cast<uintptr_t>(img) & 15) == 0, "nsf_ar_pack: bad pointer");
+  const long long m_tiles = (N + 127) / 128;
+  const int KB = (2 * dim + 63) / 64;
+  const long long total = m_tiles * KB * 1024;
+  long long grid = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  nsf_ar_pack_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<unsigned char*>(img), N,
+                                                                      m_tiles, dim, KB, 3.14159274101257324f, B);
+  count_launch();
+  return check_launch("nsf_ar_pack");
 }
 
 int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, const float* x, float* out,

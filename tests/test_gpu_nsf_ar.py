@@ -85,3 +85,29 @@ def test_reference_checkpoint_reproduces_reference_outputs():
         z, plp, ld = m.forward(T(g["x"]).cuda())
     assert rel_err(z, g["z"]) <= 3 * RTOL_FP32
     assert rel_err(plp, g["plp"]) <= 5e-5 and rel_err(ld, g["ld"]) <= 5e-5
+
+
+@pytest.mark.parametrize("dim,K,H", [(12, 8, 24), (40, 32, 200), (96, 8, 130)])
+def test_nsf_ar_grouped_conditioners_match_per_layer_path(dim, K, H):
+    """bf16 conditioners: the grouped path (one trig-feature pack launch + three grouped tcgen05 GEMM
+    launches for all dim-1 conditioners) vs running the conditioners one by one, and vs the fp32
+    layer (1e-2 class)."""
+    from normalizingflow_b200 import _wide, flows
+    torch.manual_seed(dim)
+    lay = flows.NSF_AR(dim, K=K, B=3.0, hidden_dim=H).cuda()
+    x = (1.3 * torch.randn(700, dim, generator=torch.Generator().manual_seed(2))).cuda()
+    with torch.no_grad():
+        z32, ld32 = lay.forward(x)                          # fp32 conditioners
+        for f in lay.layers:
+            f.precision = "bf16"
+        assert _wide.nsf_ar_grouped_ok(lay)
+        zg, ldg = lay.forward(x)                            # grouped
+        pg = _wide.nsf_ar_params(lay, x, max_rows=256)      # row-chunked: same numbers
+        P = 3 * K - 1
+        ang = torch.tensor(np.pi, dtype=torch.float32, device="cuda") * x / 3.0
+        c, s = torch.cos(ang), torch.sin(ang)
+        cols = [lay.init_param.expand(700, P)] + [lay.layers[i - 1](torch.cat((c[:, :i], s[:, :i]), -1)) for i in range(1, dim)]
+        pl = torch.stack(cols, 1)                           # one conditioner at a time (bf16)
+    assert rel_err(pg, pl.double().cpu()) <= 2e-2, rel_err(pg, pl.double().cpu())
+    assert rel_err(_wide.nsf_ar_params(lay, x), pg.double().cpu()) <= 1e-6
+    assert rel_err(zg, z32.double().cpu()) <= 2e-2 and rel_err(ldg, ld32.double().cpu()) <= 5e-2
