@@ -14,7 +14,8 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ Bm,
                 long long ldb, const float* __restrict__ bias, float* __restrict__ C,
-                long long ldc, long long M, long long N, long long K, int act, int accumulate) {
+                long long ldc, long long M, long long N, long long K, int act, int accumulate,
+                long long kchunk) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -26,7 +27,12 @@ gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (long long k0 = 0; k0 < K; k0 += BK) {
+  // split-K (kchunk > 0): blockIdx.z owns K range [z*kchunk, (z+1)*kchunk) and ADDS its partial tile
+  // into C with atomics (C zeroed by the launcher) -- weight gradients have a tiny output and a
+  // batch-long K, which would otherwise run on a handful of CTAs
+  const long long kb = kchunk > 0 ? (long long)blockIdx.z * kchunk : 0;
+  const long long ke = kchunk > 0 ? (kb + kchunk < K ? kb + kchunk : K) : K;
+  for (long long k0 = kb; k0 < ke; k0 += BK) {
     // A tile: BM x BK
 #pragma unroll
     for (int i = 0; i < (BM * BK) / 256; ++i) {
@@ -41,7 +47,7 @@ gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restr
       }
       const long long gm = m0 + m, gk = k0 + k;
       float v = 0.f;
-      if (gm < M && gk < K) v = TA ? A[gk * lda + gm] : A[gm * lda + gk];
+      if (gm < M && gk < ke) v = TA ? A[gk * lda + gm] : A[gm * lda + gk];
       As[k][m] = v;
     }
 #pragma unroll
@@ -57,7 +63,7 @@ gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restr
       }
       const long long gn = n0 + n, gk = k0 + k;
       float v = 0.f;
-      if (gn < N && gk < K) v = TB ? Bm[gn * ldb + gk] : Bm[gk * ldb + gn];
+      if (gn < N && gk < ke) v = TB ? Bm[gn * ldb + gk] : Bm[gk * ldb + gn];
       Bs[k][n] = v;
     }
     __syncthreads();
@@ -87,7 +93,10 @@ gemm_f32_kernel(const float* __restrict__ A, long long lda, const float* __restr
       if (bias) v += bias[gn];
       if (act == 1) v = tanhf(v);
       float* cp = C + gm * ldc + gn;
-      *cp = accumulate ? *cp + v : v;
+      if (kchunk > 0)
+        atomicAdd(cp, v);
+      else
+        *cp = accumulate ? *cp + v : v;
     }
   }
 }
@@ -99,19 +108,39 @@ static int launch_gemm(const float* A, long long lda, int ta, const float* Bm, l
   const long long gy = (M + BM - 1) / BM, gx = (N + BN - 1) / BN;
   NFK_REQUIRE(gy <= 65535 * 1024LL, "%s: too many rows", what);
   // rows beyond the 65535 limit of gridDim.y are handled by launching in slabs
+  // split-K when the output tile grid cannot fill the chip and K is long (no bias / activation then)
+  long long kchunk = 0, splits = 1;
+  const long long sms = sm_count();
+  if (!bias && act == 0 && gx * gy * 2 <= sms && K >= 1024) {
+    splits = sms / (gx * gy);
+    if (splits > (K + 255) / 256) splits = (K + 255) / 256;
+    if (splits > 1) {
+      kchunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+      splits = (K + kchunk - 1) / kchunk;
+      if (!accumulate) {
+        cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st);
+        if (e != cudaSuccess) {
+          set_error("%s: cannot zero the split-K output: %s", what, cudaGetErrorString(e));
+          return NFK_ECUDA;
+        }
+      }
+    } else {
+      splits = 1;
+    }
+  }
   const long long slab = 65535;
   for (long long y0 = 0; y0 < gy; y0 += slab) {
     const long long ny = (gy - y0 < slab) ? gy - y0 : slab;
-    dim3 grid((unsigned)gx, (unsigned)ny);
+    dim3 grid((unsigned)gx, (unsigned)ny, (unsigned)splits);
     const float* A2 = A + (ta ? y0 * BM : y0 * BM * lda);
     float* C2 = C + y0 * BM * ldc;
     const long long M2 = M - y0 * BM < ny * BM ? M - y0 * BM : ny * BM;
     if (ta) {
-      if (tb) gemm_f32_kernel<true, true><<<grid, 256, 0, st>>>(A2, lda, Bm, ldb, bias, C2, ldc, M2, N, K, act, accumulate);
-      else    gemm_f32_kernel<true, false><<<grid, 256, 0, st>>>(A2, lda, Bm, ldb, bias, C2, ldc, M2, N, K, act, accumulate);
+      if (tb) gemm_f32_kernel<true, true><<<grid, 256, 0, st>>>(A2, lda, Bm, ldb, bias, C2, ldc, M2, N, K, act, accumulate, kchunk);
+      else    gemm_f32_kernel<true, false><<<grid, 256, 0, st>>>(A2, lda, Bm, ldb, bias, C2, ldc, M2, N, K, act, accumulate, kchunk);
     } else {
-      if (tb) gemm_f32_kernel<false, true><<<grid, 256, 0, st>>>(A2, lda, Bm, ldb, bias, C2, ldc, M2, N, K, act, accumulate);
-      else    gemm_f32_kernel<false, false><<<grid, 256, 0, st>>>(A2, lda, Bm, ldb, bias, C2, ldc, M2, N, K, act, accumulate);
+      if (tb) gemm_f32_kernel<false, true><<<grid, 256, 0, st>>>(A2, lda, Bm, ldb, bias, C2, ldc, M2, N, K, act, accumulate, kchunk);
+      else    gemm_f32_kernel<false, false><<<grid, 256, 0, st>>>(A2, lda, Bm, ldb, bias, C2, ldc, M2, N, K, act, accumulate, kchunk);
     }
     count_launch();
     if (int rc = check_launch(what)) return rc;

@@ -187,7 +187,12 @@ class NSF_CL(nn.Module):
     # conditioner input x[:, :, mask].flatten(1) (flows.py:230)
     def _lower(self, x):
         if x.requires_grad and torch.is_grad_enabled():
-            return x.reshape(-1, self.size, self.dim)[:, :, self._mask].flatten(start_dim=1)
+            # device-resident index (a Python list would be uploaded on every call, which also breaks
+            # CUDA-graph capture of a training step)
+            idx = getattr(self, "_mask_dev", None)
+            if idx is None or idx.device != x.device:
+                idx = self._mask_dev = torch.tensor(self._mask, dtype=torch.long, device=x.device)
+            return x.reshape(-1, self.size, self.dim).index_select(2, idx).flatten(start_dim=1)
         if getattr(self.psi, "precision", None) == "bf16":
             # gather straight into the padded bf16 operand of the first tensor-core GEMM
             w = self.size * len(self._mask)

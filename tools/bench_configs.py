@@ -46,8 +46,23 @@ def cfg1(H):
         opt.step()
     t_train = timeit(train_step)
     t_sample = timeit(lambda: m.sample(4096))
+    # the same step / sampling call captured once as a CUDA graph (launch-latency-bound at this size)
+    from normalizingflow_b200.graphs import GraphedCallable, GraphedTrainStep
+    opt_g = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True)
+
+    def loss_fn():
+        z = m.prior.sample((4096,))
+        x, ld = m.inverse(z)
+        return (m.prior.log_prob(z) - ld - double_well_logp(x)).mean()
+    gstep = GraphedTrainStep(loss_fn, opt_g)
+    t_train_g = timeit(gstep)
+    gsample = GraphedCallable(lambda z: m.inverse(z)[0], m.prior.sample((4096,)))
+    zz = m.prior.sample((4096,))
+    t_sample_g = timeit(lambda: gsample(zz))
     return {"config": f"1: 8 x RealNVP(2, H={H}), batch 4096, reverse-KL on a 2-D double well",
-            "train_step_ms": t_train, "sample_ms": t_sample, "train_samples_per_s": 4096 / t_train * 1e3}
+            "train_step_ms": t_train, "sample_ms": t_sample, "train_samples_per_s": 4096 / t_train * 1e3,
+            "graphed_train_step_ms": t_train_g, "graphed_sample_ms": t_sample_g,
+            "graphed_train_samples_per_s": 4096 / t_train_g * 1e3}
 
 
 def cfg3(N, H=800, precision="bf16"):
