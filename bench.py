@@ -107,6 +107,24 @@ def cpu_baseline(a, sd, budget_s=12.0):
                       f"{torch.get_num_threads()} threads), {t:.2f} s"}
 
 
+def parity_check(a, sd, model, hx, hz, dev, rows=2048):
+    """The timed configuration checked against the oracle (CPU restatement of the reference, fp32) on
+    the first rows of the timed inputs: max |a-b| / max(1, |b|) of z, x, the log-dets and the prior
+    log-prob.  The oracle is the checker here, nothing of it is timed."""
+    from oracle import nf_oracle as O
+    x, z = hx[:rows].clone(), hz[:rows].clone()
+    with torch.no_grad():
+        (rz, rplp, rld), (rx, rldi) = O.flow_fwd_inv_pass(specs(), sd, x, z)
+        gz, gplp, gld = model.forward(x.to(dev))
+        gx, gldi = model.inverse(z.to(dev))
+
+    def rel(g, r):
+        return float(((g.double().cpu() - r.double()).abs() / r.double().abs().clamp_min(1.0)).max())
+    return {"rows": rows, "against": "oracle/nf_oracle.py (fp32, host)", "z": rel(gz, rz), "log_det_fwd": rel(gld, rld),
+            "prior_logprob": rel(gplp, rplp), "x": rel(gx, rx), "log_det_inv": rel(gldi, rldi),
+            "class": "1e-5 per layer (fp32 conditioner)" if a.conditioner == "fp32" else "1e-2 (bf16 conditioner GEMMs)"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -203,6 +221,7 @@ def run_native(a):
     cond = a.conditioner
     if cond == "auto":
         cond = "bf16" if _lib.have("nfk_linear_bf16") else "fp32"
+    a.conditioner = cond
     if a.arith == "auto":
         # bf16 GEMMs already move the spline parameters by ~1e-3, so bit-exact bin search buys nothing
         # there: the 1e-2 parity class of that path is met by the FAST spline arithmetic (<= 1e-5)
@@ -361,6 +380,7 @@ def run_native(a):
                 "roofline": roofline, "clocks": clk, "gpu_launches": launches, "e2e": e2e}
         if not a.no_cpu_baseline and world == 1:       # reported at N=1 only
             line["cpu_baseline"] = cpu_baseline(a, sd)
+            line["parity"] = parity_check(a, sd, model, hx, hz, dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
