@@ -39,7 +39,11 @@ enum {
                            bins, outputs and per-element log-dets bit-identical to it */
   NFK_ARITH_HYBRID = 1, /* searched-side knot chain EXACT (bins bit-identical), the rest
                            FMA-contracted with MUFU ex2/lg2/rcp (a few ulp) -- the default */
-  NFK_ARITH_FAST = 2    /* all approximations; a bin may differ within a few ulp of a knot */
+  NFK_ARITH_FAST = 2    /* MUFU ex2/lg2/rcp everywhere (a few ulp).  The stand-alone transform kernels
+                           (nfk_rqs_coupling, nfk_unconstrained_rqs, nfk_rqs_elementwise) still return the
+                           reference's bin: an input within 1.2e-4*(B/3) of a fast-chain knot has its bin
+                           re-decided on the exact chain.  The fused bf16 layer kernels skip that fix-up --
+                           their parameters already differ from the reference's. */
 };
 
 int nfk_abi_version(void);

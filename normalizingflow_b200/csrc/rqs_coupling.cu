@@ -111,7 +111,7 @@ rqs_coupling_tiled(const __grid_constant__ CouplingArgs a) {
 
     mbar_wait(&full[stage], phase);
     if (has_el) {
-      const RqsOut o = rqs_element<MODE, KT, INVERSE, true>(SmemPtr{pst + (size_t)tid * P}, xst[xoff], a.c);
+      const RqsOut o = rqs_element<MODE, KT, INVERSE, true, true>(SmemPtr{pst + (size_t)tid * P}, xst[xoff], a.c);
       ob[ooff] = o.y;
       lb[tid] = o.lad;
       if (a.bins) a.bins[row_base * F_t + tid] = (int8_t)o.bin;
@@ -196,7 +196,7 @@ rqs_coupling_pairs(const __grid_constant__ CouplingArgs a) {
     const float2 xc = xn;
     if (it + 1 < my_tiles) xn = __ldcs(x2 + (tile + stride) * T + tid);
     mbar_wait(&full[stage], phase);
-    const RqsOut o = rqs_element<MODE, KT, INVERSE, true>(SmemPtr{pth + (size_t)stage * ptile},
+    const RqsOut o = rqs_element<MODE, KT, INVERSE, true, true>(SmemPtr{pth + (size_t)stage * ptile},
                                                           cond_first ? xc.y : xc.x, a.c);
     // out pair = (conditioning value, transformed value)  (flows.py:239, quirk Q5)
     __stcs(o2 + tile * T + tid, make_float2(cond_first ? xc.x : xc.y, o.y));
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(128) rqs_coupling_rows(const __grid_constant__
   for (int f = tid; f < a.F_t; f += 128) {
     const int s = f / a.n_unm, j = f - s * a.n_unm;
     const float xin = xr[s * a.dim + s_unm[j]];
-    const RqsOut o = rqs_element<MODE, KT, INVERSE, true>(
+    const RqsOut o = rqs_element<MODE, KT, INVERSE, true, true>(
         GmemPtr{a.params + (row * a.F_t + f) * a.P}, xin, a.c);
     outr[s * a.dim + a.n_mask + j] = o.y;
     if (a.bins) a.bins[row * a.F_t + f] = (int8_t)o.bin;
@@ -277,7 +277,7 @@ unconstrained_rqs_kernel(const float* __restrict__ inputs, const float* __restri
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= M) return;
   const int K = KT ? KT : c.K;
-  const RqsOut o = rqs_element<MODE, KT, INVERSE, false>(
+  const RqsOut o = rqs_element<MODE, KT, INVERSE, false, true>(
       SplitPtr{W + e * K, H + e * K, D + e * (K - 1), K}, inputs[e], c);
   out[e] = o.y;
   lad[e] = o.lad;
@@ -301,7 +301,7 @@ rqs_elementwise_kernel(const float* __restrict__ inputs, const float* __restrict
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= M) return;
   const int K = KT ? KT : c.K;
-  const RqsOut o = rqs_element<MODE, KT, INVERSE, true>(PackedPtr{params + e * (3 * K - 1)}, inputs[e], c);
+  const RqsOut o = rqs_element<MODE, KT, INVERSE, true, true>(PackedPtr{params + e * (3 * K - 1)}, inputs[e], c);
   out[e] = o.y;
   lad[e] = o.lad;
   if (bins) bins[e] = (int8_t)o.bin;
@@ -339,6 +339,7 @@ static RqsConsts make_consts(int K, float B) {
   c.g0 = c.twoB * LOG2E;
   c.q0 = c.twoB * c.one_m;
   c.kstep = c.twoB * 1e-3f;
+  c.bin_eps = c.twoB * 2e-5f;
   c.K = K;
   c.scan_order = scan_order();
   return c;
