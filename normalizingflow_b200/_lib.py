@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnfk.so")
+LIB_PATH = os.environ.get("NFK_LIB") or os.path.join(_HERE, "libnfk.so")     # NFK_LIB: timing experiments (tools/ubench)
 
 NFK_OK, NFK_EINVAL, NFK_ECUDA, NFK_EUNSUPPORTED = 0, 1, 2, 3
 ARITH_EXACT, ARITH_HYBRID, ARITH_FAST = 0, 1, 2

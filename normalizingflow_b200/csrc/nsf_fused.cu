@@ -232,7 +232,11 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
+#ifdef NFK_ABLATE_NOTANH   // timing experiment only
+          f[j] = 0.5f * (__uint_as_float(v[t * 8 + j]) + bias[slice * 32 + t * 8 + j]);
+#else
           f[j] = tanh_approx(__uint_as_float(v[t * 8 + j]) + bias[slice * 32 + t * 8 + j]);
+#endif
         uint4 u;
         u.x = pack_bf16x2(f[0], f[1]);
         u.y = pack_bf16x2(f[2], f[3]);
@@ -329,8 +333,14 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
         if (lane == 0) mbar_arrive_cnt(&bar_d3e[c & 1]);      // the buffer may be overwritten
         float2* pr = reinterpret_cast<float2*>(xs + row * FU_XLD + 2 * f);
         const float2 xc = *pr;
+#ifdef NFK_ABLATE_NOELEM   // timing experiment only (tools/ubench/README.md): everything but the spline math
+        RqsOut o;
+        o.y = (a.cond_first ? xc.y : xc.x) + __uint_as_float(v[0] ^ v[7] ^ v[15] ^ v[22]);
+        o.lad = __uint_as_float(v[1] ^ v[9] ^ v[17]);
+#else
         const RqsOut o = rqs_element<MODE, 8, INVERSE, true>(RegParams{v, sB3 + f * FU_PC},
                                                               a.cond_first ? xc.y : xc.x, a.c);
+#endif
         *pr = make_float2(a.cond_first ? xc.x : xc.y, o.y);  // (conditioning, transformed): Q5
         lad_acc += o.lad;
         NFK_STAMP(32);

@@ -336,6 +336,7 @@ static RqsConsts make_consts(int K, float B) {
   c.one_m = (float)(1.0 - 1e-3 * (double)K);
   c.min_d = 1e-3f;
   c.edge_c = (float)log(exp(1.0 - 1e-3) - 1.0);
+  c.edge_d = 1e-3f + log1pf(expf(c.edge_c));
   c.g0 = c.twoB * LOG2E;
   c.q0 = c.twoB * c.one_m;
   c.kstep = c.twoB * 1e-3f;
