@@ -57,6 +57,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// wait of a warp that has nothing else to do (a control / producer warp): the failed probe suspends
+// the thread in hardware for up to `ns` instead of spinning, so the warp leaves the issue port and the
+// MIO queue of its SM sub-partition to the warps that compute
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity, uint32_t ns = 2000) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+  } while (!ok);
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

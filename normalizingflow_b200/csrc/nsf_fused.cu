@@ -58,7 +58,7 @@ struct FusedArgs {
   long long n_tiles;
   int cond_first;         // 1: conditioning column is column 0 of each pair (mask = [0])
   int accumulate;
-  long long* trace;       // optional [2][32] clock64 stamps of CTA 0, tile 2 (tools/trace_fused.py)
+  long long* trace;       // optional [17][32] clock64 stamps of CTA 0, tile 2: control warp, then the 16 epilogue warps (tools/trace_fused.py)
   RqsConsts c;
 };
 
@@ -147,7 +147,7 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
         bulk_g2s(sW2, a.w2_img, FU_W2_BYTES, bar_w);
         for (unsigned g = 0; g < FU_W3STAGES && g < total_chunks; ++g) issue_w3(g);
       }
-      if (lane == 0) mbar_wait(bar_w, 0);
+      if (lane == 0) mbar_wait_idle(bar_w, 0);
       __syncwarp();
     }
     unsigned g = 0, na = 0;          // running GEMM3 chunk counter, running bar_a phase counter
@@ -159,7 +159,7 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
 #define NFK_STAMP(base) do { if (tr) a.trace[(base) + ts++] = clock64(); } while (0)
       // GEMM1: D12 = A1 W1^T
       NFK_STAMP(0);
-      mbar_wait(bar_a, na++ & 1);
+      mbar_wait_idle(bar_a, na++ & 1);
       NFK_STAMP(0);
       tc_fence_after();
       if (elect_one()) {
@@ -172,7 +172,7 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
       NFK_STAMP(0);
       // GEMM2: D12 = A2 W2^T
       NFK_STAMP(0);
-      mbar_wait(bar_a, na++ & 1);
+      mbar_wait_idle(bar_a, na++ & 1);
       NFK_STAMP(0);
       tc_fence_after();
       if (elect_one()) {
@@ -187,12 +187,12 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
       __syncwarp();
       NFK_STAMP(0);
       // GEMM3 chunks: D3[g & 1] = A3 W3chunk^T
-      mbar_wait(bar_a, na++ & 1);
+      mbar_wait_idle(bar_a, na++ & 1);
       NFK_STAMP(0);
       for (int c = 0; c < FU_NCHUNK; ++c, ++g) {
         const int s = g % FU_W3STAGES;
-        mbar_wait(&bar_w3[s], (g / FU_W3STAGES) & 1);
-        if (g >= 2) mbar_wait(&bar_d3e[g & 1], ((g >> 1) + 1) & 1);   // chunk g-2 left this buffer
+        mbar_wait_idle(&bar_w3[s], (g / FU_W3STAGES) & 1);
+        if (g >= 2) mbar_wait_idle(&bar_d3e[g & 1], ((g >> 1) + 1) & 1);   // chunk g-2 left this buffer
         tc_fence_after();
         const uint32_t d = tmem + 128 + (g & 1) * FU_NC;
         const uint32_t bbase = aW3 + s * FU_W3C_BYTES;
@@ -209,7 +209,7 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
         NFK_STAMP(0);
         if (g >= 1 && g + 2 < total_chunks) {
           // chunk g-1 has been consumed by the tensor core: refill its ring slot with chunk g+2
-          mbar_wait(&bar_d3f[(g - 1) & 1], ((g - 1) >> 1) & 1);
+          mbar_wait_idle(&bar_d3f[(g - 1) & 1], ((g - 1) >> 1) & 1);
           if (lane == 0) issue_w3(g + 2);
           __syncwarp();
         }
@@ -273,12 +273,12 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
       float* xs = sX + (it & 1) * FU_ROWS * FU_XLD;
       float ld_old = 0.f;
       if (lane < 8 && a.accumulate) ld_old = __ldg(a.logdet + tile * FU_ROWS + myrow);   // consumed in P7
-      const bool tr = a.trace && blockIdx.x == 0 && it == 2 && tid == 0;
+      const bool tr = a.trace && blockIdx.x == 0 && it == 2 && lane == 0;     // every epilogue warp: [32 + 32 * warp ...]
       int ts = 0;
       // ---- P1: conditioning columns -> A1 (K block 0; columns 32..63 are zero padding)
-      NFK_STAMP(32);
+      NFK_STAMP(32 + 32 * warp);
       mbar_wait(&bar_x[it & 1], (it >> 1) & 1);
-      NFK_STAMP(32);
+      NFK_STAMP(32 + 32 * warp);
       for (int i = tid; i < FU_ROWS * 8; i += FU_EPI_WARPS * 32) {
         const int r = i >> 3, ch = i & 7;
         uint4 u = make_uint4(0u, 0u, 0u, 0u);
@@ -297,7 +297,7 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive_cnt(bar_a);
-      NFK_STAMP(32);
+      NFK_STAMP(32 + 32 * warp);
       // prefetch the next tile into the other buffer (this lane stored that row one tile ago)
       if (it >= 1 && it + 1 < my_tiles) {
         if (lane < 8) bulk_wait_read<0>();
@@ -306,21 +306,21 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
       }
       // ---- P3 / P5: hidden-layer epilogues
       mbar_wait(bar_mma, 0);
-      NFK_STAMP(32);
+      NFK_STAMP(32 + 32 * warp);
       tc_fence_after();
       hidden_epilogue(sB1);
-      NFK_STAMP(32);
+      NFK_STAMP(32 + 32 * warp);
       mbar_wait(bar_mma, 1);
-      NFK_STAMP(32);
+      NFK_STAMP(32 + 32 * warp);
       tc_fence_after();
       hidden_epilogue(sB2);
-      NFK_STAMP(32);
+      NFK_STAMP(32 + 32 * warp);
       // ---- P6: spline transform as the epilogue of the GEMM3 chunks
       float lad_acc = 0.f;
 #pragma unroll 1
       for (int c = 0; c < FU_NCHUNK; ++c) {
         mbar_wait(&bar_d3f[c & 1], (c >> 1) & 1);
-        NFK_STAMP(32);
+        NFK_STAMP(32 + 32 * warp);
         tc_fence_after();
         const int f = c * FU_CF + slice;                     // feature of this thread
         uint32_t v[24];
@@ -343,7 +343,7 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
 #endif
         *pr = make_float2(a.cond_first ? xc.x : xc.y, o.y);  // (conditioning, transformed): Q5
         lad_acc += o.lad;
-        NFK_STAMP(32);
+        NFK_STAMP(32 + 32 * warp);
       }
       // ---- P7: the four warps of this lane quadrant own these 32 rows: exchange the partial
       // log-dets through the row padding, then lanes 0..7 finish 8 rows each
@@ -394,7 +394,7 @@ static long long* g_fused_trace = nullptr;
 
 extern "C" {
 
-/* test hook: device buffer of 64 int64 that receives clock64 stamps of CTA 0 / tile 2 */
+/* test hook: device buffer of 17 x 32 int64 that receives clock64 stamps of CTA 0 / tile 2 */
 int nfk_set_fused_trace(void* dev_buf) {
   g_fused_trace = reinterpret_cast<long long*>(dev_buf);
   return NFK_OK;
