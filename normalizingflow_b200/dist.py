@@ -118,6 +118,61 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], average: bool = Tr
     return flat.numel() * 4
 
 
+class GradBucket:
+    """Persistent flat fp32 gradient bucket: every parameter's ``.grad`` is a view into ONE buffer, so the
+    per-step gradient exchange is a single in-place all-reduce with no gather / scatter copies around it
+    (``allreduce_gradients`` builds the bucket with ``torch.cat`` and copies the result back: at 10 M
+    gradient elements that is ~1.3 ms per step on a B200 around a 0.2 ms NVLink all-reduce).
+
+        bucket = GradBucket(model.parameters())
+        for batch in data:
+            bucket.zero()                  # instead of optimizer.zero_grad()
+            loss(batch).backward()         # autograd accumulates into the views
+            bucket.allreduce()             # one NCCL all-reduce (sum, then 1/world)
+            optimizer.step()
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise ValueError("GradBucket holds fp32 gradients (the reference trains in fp32)")
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def zero(self) -> None:
+        self.flat.zero_()
+        for p, off in zip(self.params, self._offsets()):
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * off:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)     # someone called zero_grad(set_to_none=True)
+
+    def _offsets(self):
+        off = 0
+        for p in self.params:
+            yield off
+            off += p.numel()
+
+    def allreduce(self, average: bool = True) -> int:
+        if not (dist.is_available() and dist.is_initialized()):
+            return 0
+        world = dist.get_world_size(self.group)
+        if world == 1:
+            return 0
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        if average:
+            self.flat.mul_(1.0 / world)
+        return self.nbytes
+
+
 def global_mean(t: torch.Tensor, group=None) -> torch.Tensor:
     """Mean of a per-row quantity over all ranks (e.g. the reported mean log-prob)."""
     s = torch.stack([t.float().sum(), torch.tensor(float(t.numel()), device=t.device)])

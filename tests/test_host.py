@@ -249,6 +249,14 @@ def _worker(rank, world, port, out):
     loss = net(x[a:b]).pow(2).mean()
     loss.backward()
     nbytes = nd.allreduce_gradients(net.parameters(), average=True)
+    # the persistent flat bucket gives the same averaged gradients with one in-place all-reduce
+    flat_a = torch.cat([p.grad.flatten() for p in net.parameters()]).clone()
+    bucket = nd.GradBucket(net.parameters())
+    bucket.zero()
+    net(x[a:b]).pow(2).mean().backward()
+    assert bucket.allreduce() == nbytes
+    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters())
+    assert torch.allclose(bucket.flat, flat_a, rtol=1e-6, atol=1e-7)
     gm = nd.global_mean(net(x[a:b]).detach().flatten())
     flat = torch.cat([p.grad.flatten() for p in net.parameters()])
     wts = torch.cat([p.detach().flatten() for p in net.parameters()])
