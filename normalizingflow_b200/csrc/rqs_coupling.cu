@@ -386,24 +386,23 @@ static int launch_coupling(CouplingArgs& a, long long N, cudaStream_t st) {
       }
     }
   } else if (aligned) {
-    // ---- generic geometry: one element per thread per tile.  Rows per tile (a multiple of 4 so
-    // every tile stays 16-byte aligned) are chosen to maximise resident warps per SM.
+    // ---- generic geometry: one element per thread per tile.  Rows per tile: a multiple of 4 (every
+    // tile stays 16-byte aligned), as FEW as fill a 128-thread CTA.  Small tiles mean many co-resident
+    // CTAs, i.e. many independent TMA rings and barriers per SM; measured on B200 (FAST, 524,288 rows):
+    // F_t = 38: R = 4 63.1 %, 8 59.6 %, 12 47.6 %, 16 54.3 % of the HBM peak; F_t = 76: R = 4 65.8 %, 8 62.3 %
+    // Ring depth: a CTA keeps stages - 1 tiles in flight while it computes one.  Where registers /
+    // threads already cap the co-resident CTAs at <= 5 a third stage costs at most one CTA and pays
+    // (F_t = 38: 46.6 % -> 62.8 %; F_t = 76: unchanged); where 6 CTAs fit (F_t = 32, 8) the lost CTA
+    // costs more than the deeper ring gains (71.5 % -> 66.7 %), so those keep two stages.
     const size_t row_floats = (size_t)F_t * a.P + a.d;
-    const int stages = g_tune_stages > 0 ? g_tune_stages : 2;
+    int stages = g_tune_stages > 0 ? g_tune_stages : 2;
     int R = g_tune_R > 0 ? ((g_tune_R + 3) & ~3) : 0;
     if (R == 0) {
-      int best_warps = -1;
       for (int r = 4; r <= 64 && r * F_t <= MAX_THREADS; r += 4) {
-        const int thr = (r * F_t + 31) & ~31;
         const size_t sm = (size_t)stages * r * row_floats * 4 + (size_t)2 * r * a.d * 4 + (size_t)2 * r * F_t * 4 + 320;
         if (sm > 226 * 1024) break;
-        int ctas = (int)((227 * 1024) / (sm + 1024));
-        ctas = min(ctas, min(2048 / thr, 65536 / (thr * 80)));
-        const int warps = ctas * (thr / 32) * (r * F_t) / thr;      // discount idle lanes
-        if (warps > best_warps) {
-          best_warps = warps;
-          R = r;
-        }
+        R = r;
+        if (r * F_t >= 128) break;
       }
       if (R == 0) R = 4;
     }
@@ -411,6 +410,15 @@ static int launch_coupling(CouplingArgs& a, long long N, cudaStream_t st) {
     const int threads = (n_el + 31) & ~31;
     const size_t stage_bytes = (size_t)R * row_floats * 4;
     const size_t fixed = (size_t)2 * R * a.d * 4 + (size_t)2 * n_el * 4 + 8 * 8 + 128;
+    if (g_tune_stages <= 0) {
+      auto ctas_for = [&](int st) {
+        const size_t sm = fixed + (size_t)st * stage_bytes;
+        if (sm > 226 * 1024) return 0;
+        return max(1, min((int)((227 * 1024) / (sm + 1024)), min(2048 / threads, 65536 / (threads * 80))));
+      };
+      const int c2 = ctas_for(2), c3 = ctas_for(3);
+      if (c3 > 0 && c2 <= 5 && c3 >= c2 - 1) stages = 3;
+    }
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     const long long n_tiles = N / R;
     if (threads <= MAX_THREADS && smem <= 226 * 1024 && n_tiles > 0 && n_tiles < (1LL << 31)) {
