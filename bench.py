@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--chunk-rows", type=int, default=131072, help="row chunk of the host-buffer (e2e) pipeline")
+    ap.add_argument("--chunk-rows", type=int, default=262144, help="row chunk of the host-buffer (e2e) pipeline")
     ap.add_argument("--e2e-wait", type=int, default=0, help="1: order the current stream after every host-API call")
     ap.add_argument("--no-fused", action="store_true", help="run the layer as separate GEMM + spline kernels")
     return ap.parse_args()
