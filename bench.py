@@ -122,16 +122,23 @@ def parity_check(a, sd, model, hx, hz, dev, rows=2048):
         return float(((g.double().cpu() - r.double()).abs() / r.double().abs().clamp_min(1.0)).max())
     # the gate proper is per layer on identical inputs: feed every layer the oracle's own
     # intermediate activation and compare that one layer
-    per_z, per_ld, cur = 0.0, 0.0, x
+    # ... and, for the tolerance the north star states on the conditioner GEMMs themselves, the spline
+    # parameters (output of the conditioner MLP as the layer's own GEMM kernels compute it, un-fused)
+    # against the oracle's fp32 MLP on the same conditioning columns
+    per_z, per_ld, per_p, cur = 0.0, 0.0, 0.0, x
     sp = specs()
     with torch.no_grad():
         for i, layer in enumerate(model.flows):
             ro, rl = O.apply_layer(sp[i], sd, i, cur, False)
             go, gl = layer.forward(cur.to(dev))
             per_z, per_ld = max(per_z, rel(go, ro)), max(per_ld, rel(gl, rl))
+            lower = cur.view(rows, SIZE, DIM)[:, :, sp[i]["mask"][0]].contiguous()
+            rp = O.fcnn(lower, sd, f"flows.{i}.psi.")
+            gp = layer.psi(lower.to(dev))
+            per_p = max(per_p, rel(gp, rp))
             cur = ro
     return {"rows": rows, "against": "oracle/nf_oracle.py (fp32, host)",
-            "per_layer_identical_inputs": {"z": per_z, "log_det": per_ld},
+            "per_layer_identical_inputs": {"z": per_z, "log_det": per_ld, "conditioner_output_spline_params": per_p},
             "chain_of_8_layers": {"z": rel(gz, rz), "log_det_fwd": rel(gld, rld), "prior_logprob": rel(gplp, rplp),
                                   "x": rel(gx, rx), "log_det_inv": rel(gldi, rldi)},
             "class": "1e-5 per layer (fp32 conditioner)" if a.conditioner == "fp32" else

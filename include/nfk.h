@@ -163,6 +163,11 @@ int nfk_gauss_logprob(const float* z, const float* add /*nullable*/, float add_s
  * act: 0 = identity, 1 = tanh.  fp32 CUDA-core kernel (parity mode). */
 int nfk_linear_f32(const float* X, int64_t ldx, const float* W, const float* b, float* Y,
                    int64_t M, int K, int Nout, int act, void* stream);
+/* The same layer on the tensor cores with fp32-class accuracy (3xTF32: x = hi + lo, hi*hi + hi*lo + lo*hi
+ * accumulated in fp32 in TMEM, tcgen05.mma.kind::tf32): the parity mode's forward GEMM wherever
+ * K % 4 == 0 and the rows are 16-byte aligned.  X [M, K] row stride ldx, W [Nout, K] row stride ldw. */
+int nfk_linear_tf32x3(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* b, float* Y,
+                      int64_t ldy, int64_t M, int K, int Nout, int act, void* stream);
 /* generic fp32 GEMM used by the conditioner backward: C[M,N] (+)= op(A) op(B),
  * ta/tb: 0 = as stored row-major [M,K]/[K,N], 1 = stored transposed ([K,M]/[N,K]). */
 int nfk_gemm_f32(const float* A, int64_t lda, int ta, const float* Bm, int64_t ldb, int tb,

@@ -54,6 +54,7 @@ SIGNATURES = {
     "nfk_radial_bwd": (c_int, [_P] * 12 + [c_int64, c_int, c_int, _P]),
     "nfk_gauss_logprob": (c_int, [_P, _P, c_float, _P, c_int64, c_int, c_float, _P]),
     "nfk_linear_f32": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "nfk_linear_tf32x3": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P]),
     "nfk_linear_bf16": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P]),
     "nfk_nsf_fused_rows_per_tile": (c_int, []),
     "nfk_set_fused_trace": (c_int, [_P]),

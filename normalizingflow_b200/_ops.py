@@ -213,8 +213,12 @@ def gemm_f32(A, ta: bool, Bm, tb: bool, out=None, accumulate=False):
     return out
 
 
-def linear_f32(x, weight, bias, act: int):
-    """act(x @ weight.T + bias); x may be a row-strided 2-D view (inner stride 1)."""
+TF32X3 = True             # parity-mode forward GEMMs on the tensor cores (3xTF32) when the shape allows
+
+
+def linear_f32(x, weight, bias, act: int, allow_tc: bool = True):
+    """act(x @ weight.T + bias); x may be a row-strided 2-D view (inner stride 1).  ``allow_tc=False`` keeps the
+    CUDA-core fp32 kernel (training: the saved activations feed the hand-written backward)."""
     dev = require_cuda(x, weight, bias)
     if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
         x = f32c(x.reshape(x.shape[0], -1))
@@ -225,9 +229,15 @@ def linear_f32(x, weight, bias, act: int):
     if weight.shape[1] != Kd:
         raise ValueError(f"weight is {tuple(weight.shape)}, input has {Kd} features")
     y = torch.empty((M, Nout), dtype=torch.float32, device=dev)
+    ldx = x.stride(0) if M > 1 else max(Kd, x.stride(0))
     with torch.cuda.device(dev):
-        call("nfk_linear_f32", ptr(x), x.stride(0) if M > 1 else max(Kd, x.stride(0)), ptr(weight), ptr(bias),
-             ptr(y), M, Kd, Nout, act, stream_ptr(dev))
+        if (TF32X3 and allow_tc and Kd % 4 == 0 and ldx % 4 == 0 and x.data_ptr() % 16 == 0
+                and weight.data_ptr() % 16 == 0):
+            # fp32-class accuracy on the tensor cores (3xTF32, csrc/linear_tf32.cu)
+            call("nfk_linear_tf32x3", ptr(x), ldx, ptr(weight), weight.stride(0), ptr(bias), ptr(y), Nout, M, Kd,
+                 Nout, act, stream_ptr(dev))
+        else:
+            call("nfk_linear_f32", ptr(x), ldx, ptr(weight), ptr(bias), ptr(y), M, Kd, Nout, act, stream_ptr(dev))
     return y
 
 
@@ -236,7 +246,7 @@ class LinearF32Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, act):
-        y = linear_f32(x, weight, bias, act)
+        y = linear_f32(x, weight, bias, act, allow_tc=False)      # the saved activations feed the hand-written backward
         ctx.save_for_backward(x, weight, y)
         ctx.act = act
         ctx.has_bias = bias is not None

@@ -50,6 +50,12 @@ class FCNN(nn.Module):
             return _bf16.mlp3(self, x)
         if self.precision != "fp32":
             raise ValueError(f"unknown conditioner precision {self.precision!r}")
+        if not torch.is_grad_enabled():
+            # inference: the three GEMMs on the tensor cores with fp32-class accuracy (3xTF32,
+            # csrc/linear_tf32.cu) wherever the shape allows; same 1e-5 parity class as the CUDA-core kernel
+            h = _ops.linear_f32(x, l0.weight, l0.bias, 1)
+            h = _ops.linear_f32(h, l2.weight, l2.bias, 1)
+            return _ops.linear_f32(h, l4.weight, l4.bias, 0)
         h = _ops.LinearF32Fn.apply(x, l0.weight, l0.bias, 1)
         h = _ops.LinearF32Fn.apply(h, l2.weight, l2.bias, 1)
         return _ops.LinearF32Fn.apply(h, l4.weight, l4.bias, 0)
