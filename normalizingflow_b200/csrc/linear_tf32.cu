@@ -84,22 +84,29 @@ linear_tf32x3_kernel(const float* __restrict__ X, long long ldx, const float* __
   constexpr int A_PER = LT_M * 8 / LT_THREADS;          // 16-byte pieces of the A tile per thread (4)
   constexpr int B_PER = LT_BN * 8 / LT_THREADS;         // ... of the widest B tile (4)
   Piece pa[A_PER], pb[B_PER];
+  // piece j of this thread is always the same (row, 16-byte column) of the tile: pointers hoisted out of the K loop
+  const int pc = (tid & 7) * 4;                          // first fp32 column of this thread's pieces within a K block
+  const float* ap[A_PER];
+  const float* bp[B_PER];
+#pragma unroll
+  for (int j = 0; j < A_PER; ++j) {
+    const long long gr = m0 + ((tid + j * LT_THREADS) >> 3);
+    ap[j] = gr < M ? X + gr * ldx + pc : nullptr;
+  }
+#pragma unroll
+  for (int j = 0; j < B_PER; ++j) {
+    const int r = (tid + j * LT_THREADS) >> 3;
+    bp[j] = (r < bn && n0 + r < N) ? W + (long long)(n0 + r) * ldw + pc : nullptr;
+  }
   auto fetch = [&](int kb) {
     const int k0 = kb * LT_KF;
+    const bool in_k = k0 + pc < K;
 #pragma unroll
-    for (int j = 0; j < A_PER; ++j) {
-      const int i = tid + j * LT_THREADS, r = i >> 3, c = i & 7;
-      const long long gr = m0 + r;
-      const int gk = k0 + c * 4;
-      pa[j].v = (gr < M && gk < K) ? __ldg(reinterpret_cast<const uint4*>(X + gr * ldx + gk)) : make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int j = 0; j < A_PER; ++j)
+      pa[j].v = (ap[j] && in_k) ? __ldg(reinterpret_cast<const uint4*>(ap[j] + k0)) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int j = 0; j < B_PER; ++j) {
-      const int i = tid + j * LT_THREADS, r = i >> 3, c = i & 7;
-      const int gn = n0 + r, gk = k0 + c * 4;
-      pb[j].v = (r < bn && gn < N && gk < K) ? __ldg(reinterpret_cast<const uint4*>(W + (long long)gn * ldw + gk))
-                                              : make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int j = 0; j < B_PER; ++j)
+      pb[j].v = (bp[j] && in_k) ? __ldg(reinterpret_cast<const uint4*>(bp[j] + k0)) : make_uint4(0u, 0u, 0u, 0u);
   };
   auto split_store = [&](unsigned char* hi_tile, unsigned char* lo_tile, int i, const uint4& v) {
     const int r = i >> 3, c = i & 7;
@@ -158,6 +165,7 @@ linear_tf32x3_kernel(const float* __restrict__ X, long long ldx, const float* __
   const int q = warp & 3;
   const long long row_w0 = m0 + q * 32;
   const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) && (ldy % 4 == 0) && (n0 % 4 == 0);
   for (int c0 = (warp >> 2) * 32; c0 < bn; c0 += 64) {
     uint32_t v[32];
     float acc[32];
@@ -184,9 +192,22 @@ linear_tf32x3_kernel(const float* __restrict__ X, long long ldx, const float* __
     }
     __syncwarp();
     float* yb = Y + n0 + c0;
-    if (lane < ncol)
+    if (vec_ok && ncol == 32) {
+      // 8 lanes x 16 bytes cover one 128-byte row segment: four rows per store instruction
+      const int rr = lane >> 3, cc = (lane & 7) * 4;
+      float* yrow = yb + (row_w0 + rr) * ldy + cc;
+#pragma unroll
+      for (int r = 0; r < 32; r += 4) {
+        if (row_w0 + r + rr < M) {
+          const float* sp = stg + (r + rr) * 33 + cc;
+          *reinterpret_cast<float4*>(yrow) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+        }
+        yrow += 4 * ldy;
+      }
+    } else if (lane < ncol) {
       for (int r = 0; r < 32; ++r)
         if (row_w0 + r < M) yb[(row_w0 + r) * ldy + lane] = stg[r * 33 + lane];
+    }
     __syncwarp();
   }
   tc_fence_before();
