@@ -27,9 +27,13 @@ namespace nfk {
 constexpr int LT_M = 128;
 constexpr int LT_KF = 32;          // fp32 per K block
 constexpr int LT_THREADS = 256;
-constexpr int LT_BN = 64;          // widest N tile: 96 KB of operand stages -> two CTAs per SM (one's epilogue under the other's main loop)
-constexpr int LT_REGIONS = 4;      // TMEM accumulators used round-robin over the K blocks (see the epilogue)
-constexpr int LT_STAGES = 2;
+// Two tile configurations (template parameters LT_BN = widest N tile, LT_REGIONS = TMEM accumulators used
+// round-robin over the k-steps, LT_STAGES = shared-memory operand stages), both two CTAs per SM (one CTA's
+// epilogue runs under the other's main loop):
+//   K <= 256: <128, 2, 1>  64 KB of operands, 2 x 128 TMEM columns; X is split half as often as with 64-wide
+//             tiles (2^20 x 128 -> 736: 2.16 ms against 3.07 ms); a chain is at most 16 k-steps
+//   K >  256: < 64, 4, 2>  96 KB, 4 x 64 TMEM columns: four accumulators keep the chains short where K is long
+//             (K = 800: 6.1e-6 of the output scale against 1.2e-5 with two accumulators)
 
 // kind::tf32 instruction descriptor: D fp32 (bits 4-5 = 1), A/B TF32 (format 2 in bits 7-9, 10-12),
 // both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
@@ -50,6 +54,7 @@ struct Piece {
   uint4 v;
 };
 
+template <int LT_BN, int LT_REGIONS, int LT_STAGES>
 __global__ void __launch_bounds__(LT_THREADS)
 linear_tf32x3_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ W, long long ldw,
                      const float* __restrict__ bias, float* __restrict__ Y, long long ldy, long long M, int K,
@@ -232,22 +237,25 @@ int nfk_linear_tf32x3(const float* X, int64_t ldx, const float* W, int64_t ldw, 
   NFK_REQUIRE(X && W && Y, "linear_tf32x3: null device pointer");
   NFK_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W)) & 15) == 0,
               "linear_tf32x3: X and W must be 16-byte aligned");
-  const int n_tiles = (Nout + LT_BN - 1) / LT_BN;
+  const bool wide = K <= 256;
+  const int bn_max = wide ? 128 : 64, regions = wide ? 2 : 4, stages = wide ? 1 : 2;
+  const int n_tiles = (Nout + bn_max - 1) / bn_max;
   int BN = (((Nout + n_tiles - 1) / n_tiles) + 15) & ~15;
   if (BN < 16) BN = 16;
   uint32_t cols = 32;
   while ((int)cols < BN) cols <<= 1;
-  cols *= LT_REGIONS;                        // LT_REGIONS accumulators of a power-of-two width each (<= 256 columns)
-  const size_t smem = LT_STAGES * (2 * (size_t)LT_M * 128 + 2 * (size_t)BN * 128) + 1024;
+  cols *= regions;                           // `regions` accumulators of a power-of-two width each (<= 256 columns)
+  const size_t smem = stages * (2 * (size_t)LT_M * 128 + 2 * (size_t)BN * 128) + 1024;
   const long long gm = (M + LT_M - 1) / LT_M;
   NFK_REQUIRE(gm * n_tiles < (1LL << 31), "linear_tf32x3: too many tiles");
-  cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = wide ? linear_tf32x3_kernel<128, 2, 1> : linear_tf32x3_kernel<64, 4, 2>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("linear_tf32x3: cannot set %zu B dynamic shared memory: %s", smem, cudaGetErrorString(e));
     return NFK_ECUDA;
   }
-  linear_tf32x3_kernel<<<(unsigned)(gm * n_tiles), LT_THREADS, smem, (cudaStream_t)stream>>>(
-      X, ldx, W, ldw, b, Y, ldy, M, K, Nout, BN, n_tiles, act, cols);
+  kern<<<(unsigned)(gm * n_tiles), LT_THREADS, smem, (cudaStream_t)stream>>>(X, ldx, W, ldw, b, Y, ldy, M, K, Nout, BN,
+                                                                             n_tiles, act, cols);
   count_launch();
   return check_launch("linear_tf32x3");
 }
