@@ -281,3 +281,42 @@ def test_gradient_allreduce_matches_single_process_gloo_world2(tmp_path):
     assert torch.allclose(got["grad"], ref, rtol=1e-5, atol=1e-6)
     assert got["bytes"] == ref.numel() * 4
     assert torch.allclose(got["gm"], net(x).detach().mean(), rtol=1e-5, atol=1e-6)
+
+
+def test_grad_bucket_views_survive_zero_grad_set_to_none():
+    """GradBucket keeps every .grad a view into one flat buffer; an optimizer.zero_grad(set_to_none=True)
+    in between is repaired by bucket.zero(), and autograd accumulates into the views."""
+    from normalizingflow_b200 import dist as nd
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Tanh(), torch.nn.Linear(3, 2))
+    bucket = nd.GradBucket(net.parameters())
+    assert bucket.nbytes == 4 * sum(p.numel() for p in net.parameters())
+    x = torch.randn(5, 4)
+    net(x).pow(2).sum().backward()
+    ref = torch.cat([p.grad.flatten() for p in net.parameters()]).clone()
+    assert torch.equal(bucket.flat, ref) and float(ref.abs().sum()) > 0
+    torch.optim.SGD(net.parameters(), lr=0.1).zero_grad(set_to_none=True)
+    assert all(p.grad is None for p in net.parameters())
+    bucket.zero()
+    assert all(p.grad is not None for p in net.parameters()) and float(bucket.flat.abs().sum()) == 0
+    net(x).pow(2).sum().backward()
+    assert torch.equal(bucket.flat, ref)
+    assert bucket.allreduce() == 0            # not distributed: nothing to exchange
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the native one) prints ONE JSON line
+    with the contract's keys and runs without a GPU."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--cpu-rows", "256"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rqs_flow_samples_per_sec_fwd_inv_logdet" and d["unit"] == "samples/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"]
