@@ -142,7 +142,9 @@ def parity_check(a, sd, model, hx, hz, dev, rows=2048):
             "chain_of_8_layers": {"z": rel(gz, rz), "log_det_fwd": rel(gld, rld), "prior_logprob": rel(gplp, rplp),
                                   "x": rel(gx, rx), "log_det_inv": rel(gldi, rldi)},
             "class": "1e-5 per layer (fp32 conditioner)" if a.conditioner == "fp32" else
-            "bf16 conditioner GEMMs (north star: 1e-2 class); log_det is a sum of 32 per-feature terms per layer"}
+            "16-bit tensor-core conditioner GEMMs (north star: 1e-2 class): fp16 operands in the fused layer kernel "
+            "(hidden <= 128), bf16 images on the wide path; conditioner_output_spline_params is measured on the layer's "
+            "un-fused bf16 GEMM kernels; log_det is a sum of 32 per-feature terms per layer"}
 
 
 def run_reference(a):

@@ -6,10 +6,14 @@
 // exists in HBM: per row the kernel reads 256 B of x and writes 256 B of z plus the log-det.
 //
 // Persistent CTA (16 warps), 128 rows per tile:
-//   P1  x tile (TMA bulk, double buffered) -> conditioning columns -> bf16 -> A operand in the
+// Operands are IEEE fp16, not bf16: the activations are tanh outputs in (-1, 1) and the weights O(1), so
+// fp16's range is ample (the conditioning inputs are clamped to +-65504) and its 11-bit significand carries
+// 8x less quantisation noise than bf16's 8 bits at the same tensor-core rate (measured on the timed
+// configuration, per layer vs the fp32 oracle: spline parameters 3.5e-3 -> see DESIGN.md section 6).
+//   P1  x tile (TMA bulk, double buffered) -> conditioning columns -> fp16 -> A operand in the
 //       K-major SWIZZLE_128B layout (shared memory)
 //   P2  GEMM1  D12[128x128] = A1 W1^T      (tcgen05.mma, M=128 N=128 K=16 x4, accumulators in TMEM)
-//   P3  epilogue 1: tcgen05.ld -> +b1 -> tanh -> bf16 -> A operand (same buffer)
+//   P3  epilogue 1: tcgen05.ld -> +b1 -> tanh -> fp16 -> A operand (same buffer)
 //   P4  GEMM2  D12 = A2 W2^T ; P5 epilogue 2 -> A3
 //   P6  for each of 8 chunks of 4 features (4 x 24 = 96 accumulator columns, the 23 parameters
 //       of a feature padded to 24): GEMM3 chunk into one of two TMEM buffers while the previous
@@ -36,7 +40,7 @@ constexpr int FU_NC = FU_CF * FU_PC;      // 96 columns per chunk
 constexpr int FU_NCHUNK = FU_NF / FU_CF;  // 8
 constexpr int FU_W3STAGES = 3;
 
-constexpr uint32_t FU_W1_BYTES = FU_HP * 128;                    // [128 x 64] bf16
+constexpr uint32_t FU_W1_BYTES = FU_HP * 128;                    // [128 x 64] fp16
 constexpr uint32_t FU_W2_BYTES = 2 * FU_HP * 128;                // 2 K blocks of [128 x 64]
 constexpr uint32_t FU_A_BYTES = 2 * FU_ROWS * 128;               // 2 K blocks of [128 x 64]
 constexpr uint32_t FU_W3C_BYTES = 2 * FU_NC * 128;               // 2 K blocks of [96 x 64]
@@ -129,8 +133,8 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
 
   if (warp == FU_EPI_WARPS) {
     // =============================== control warp ===============================
-    const uint32_t idesc12 = make_idesc_bf16(FU_ROWS, FU_HP);
-    const uint32_t idesc3 = make_idesc_bf16(FU_ROWS, FU_NC);
+    const uint32_t idesc12 = make_idesc_f16(FU_ROWS, FU_HP);
+    const uint32_t idesc3 = make_idesc_f16(FU_ROWS, FU_NC);
     const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
     auto issue_w3 = [&](unsigned g) {        // lane 0
       const int s = g % FU_W3STAGES;
@@ -238,10 +242,10 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
           f[j] = tanh_approx(__uint_as_float(v[t * 8 + j]) + bias[slice * 32 + t * 8 + j]);
 #endif
         uint4 u;
-        u.x = pack_bf16x2(f[0], f[1]);
-        u.y = pack_bf16x2(f[2], f[3]);
-        u.z = pack_bf16x2(f[4], f[5]);
-        u.w = pack_bf16x2(f[6], f[7]);
+        u.x = pack_f16x2(f[0], f[1]);
+        u.y = pack_f16x2(f[2], f[3]);
+        u.z = pack_f16x2(f[4], f[5]);
+        u.w = pack_f16x2(f[6], f[7]);
         const int ch = (slice & 1) * 4 + t;
         *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = u;
       }
@@ -287,10 +291,10 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = xr[2 * (ch * 8 + j)];
-          u.x = pack_bf16x2(f[0], f[1]);
-          u.y = pack_bf16x2(f[2], f[3]);
-          u.z = pack_bf16x2(f[4], f[5]);
-          u.w = pack_bf16x2(f[6], f[7]);
+          u.x = pack_f16x2_sat(f[0], f[1]);                  // conditioning inputs: saturate to the fp16 range
+          u.y = pack_f16x2_sat(f[2], f[3]);
+          u.z = pack_f16x2_sat(f[4], f[5]);
+          u.w = pack_f16x2_sat(f[6], f[7]);
         }
         *reinterpret_cast<uint4*>(sA + r * 128 + ((ch ^ (r & 7)) << 4)) = u;
       }

@@ -1,6 +1,7 @@
 // tcgen05 / TMEM inline-PTX wrappers shared by the tensor-core kernels (sm_100a).
 #pragma once
 #include "nfk_common.cuh"
+#include <cuda_fp16.h>
 
 namespace nfk {
 
@@ -95,6 +96,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
         "=r"(v[7])
       : "r"(taddr)
       : "memory");
+}
+// kind::f16 with IEEE fp16 operands (A/B format 0): 11-bit significands instead of bf16's 8
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 p = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+// the same with saturation to +-65504 instead of +-inf (one F2FP.SATFINITE: inputs of unknown range)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);

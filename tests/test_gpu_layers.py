@@ -200,10 +200,9 @@ def test_models_match_reference():
 
 @pytest.mark.parametrize("H", [128, 24, 100])
 def test_fused_layer_kernel_matches_unfused_and_reference(H):
-    """nsf_fused.cu (MLP on tcgen05 + spline epilogue, one launch) vs (a) the unfused bf16 path
-    on the same weights — same bf16 operands, so the spline parameters agree to accumulation
-    order and results to ~1e-3 — and (b) the fp32 oracle within the bf16 class (1e-2 on z; the
-    log-det sums 32 terms whose parameters carry bf16 noise)."""
+    """nsf_fused.cu (MLP on tcgen05 with fp16 operands + spline epilogue, one launch) vs (a) the unfused
+    bf16 path on the same weights (bf16 class) and (b) the fp32 oracle (z within 3e-3, log-det — a sum of
+    32 terms — within 1e-2), including a ragged batch whose last tile is padded."""
     from oracle import nf_oracle as O
     _, _, flows, _ = _mods()
     from normalizingflow_b200 import _fused
@@ -224,8 +223,10 @@ def test_fused_layer_kernel_matches_unfused_and_reference(H):
                 zu, lu = layer._transform(x.cuda(), inv)
             ro, rl, _, _ = O.nsf_cl(x, sd, 32, 2, mask, 8, 3.0, inv, prefix="psi.")
             assert zf.shape == (N, 64) and lf.shape == (N,)
-            assert rel_err(zf, zu) <= 5e-3 and rel_err(lf, lu) <= 2e-2, (mask, inv, rel_err(zf, zu), rel_err(lf, lu))
-            assert rel_err(zf, ro) <= 2e-2 and rel_err(lf, rl) <= 5e-2, (mask, inv, rel_err(zf, ro), rel_err(lf, rl))
+            # the fused kernel's operands are fp16 (11-bit significands), the unfused path's bf16: the two differ
+            # by the bf16 class, and the fused kernel is ~8x closer to the fp32 oracle
+            assert rel_err(zf, zu) <= 1e-2 and rel_err(lf, lu) <= 5e-2, (mask, inv, rel_err(zf, zu), rel_err(lf, lu))
+            assert rel_err(zf, ro) <= 3e-3 and rel_err(lf, rl) <= 1e-2, (mask, inv, rel_err(zf, ro), rel_err(lf, rl))
             # conditioning columns pass through bit-exactly, in the reference's column order (Q5)
             assert torch.equal(zf.cpu().reshape(N, 32, 2)[:, :, 0], x.reshape(N, 32, 2)[:, :, mask[0]])
             acc = torch.full((N,), 1.5, device="cuda")
