@@ -393,7 +393,10 @@ def run_native(a):
                 pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(3, a.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32" if cond == "fp32" else "f32 transforms / bf16 conditioner GEMMs",
+                "vs_baseline": None,
+                "dtype": "f32" if cond == "fp32" else
+                ("f32 transforms / fp16-operand conditioner GEMMs (fp32 accumulate)"
+                 if (not a.no_fused and a.hidden <= 128) else "f32 transforms / bf16 conditioner GEMMs"),
                 "data": "synthetic",
                 "config": {"workload": workload_name(a), "hidden": a.hidden, "arith": a.arith, "conditioner": cond,
                            "fused_layer_kernel": bool(not a.no_fused and cond == "bf16" and a.hidden <= 128),
