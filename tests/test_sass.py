@@ -1,0 +1,87 @@
+"""Static checks of the built library (no GPU needed: cuobjdump reads the sm_100a cubins in libnfk.so):
+the hot kernels use the Blackwell instructions the design claims (tcgen05.mma = UTCHMMA, TMA bulk copies =
+UBLKCP, packed fp32x2 = FFMA2/FADD2, TMEM loads = LDTM), the spline element costs the MUFU operations the
+roofline analysis counts, and none of them spills registers to local memory."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "normalizingflow_b200", "libnfk.so")
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(LIB) and os.path.exists(CUOBJDUMP)),
+                                reason="needs the built libnfk.so and cuobjdump")
+
+
+def _usage():
+    out = subprocess.run([CUOBJDUMP, "-res-usage", LIB], capture_output=True, text=True, check=True).stdout
+    res, name = {}, None
+    for line in out.splitlines():
+        m = re.match(r"\s*Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        elif name and "REG:" in line:
+            res[name] = {k: int(v) for k, v in re.findall(r"(REG|STACK|LOCAL):(\d+)", line)}
+            name = None
+    return res
+
+
+def _sass(fn):
+    return subprocess.run([CUOBJDUMP, "-sass", "-fun", fn, LIB], capture_output=True, text=True, check=True).stdout
+
+
+def _count(sass, mnemonic):
+    return len(re.findall(r"\s" + re.escape(mnemonic) + r"[\s.;]", sass))
+
+
+FUSED = "_ZN3nfk22nsf_pairs_fused_kernelILi2ELb0EEEvNS_9FusedArgsE"
+PAIRS = "_ZN3nfk18rqs_coupling_pairsILi2ELi8ELb0EEEvNS_12CouplingArgsE"
+
+
+def test_only_sm100a_code_and_no_spills_in_the_hot_kernels():
+    archs = subprocess.run([CUOBJDUMP, "-lelf", LIB], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in archs and not re.search(r"sm_(?!100a)\d+", archs), archs
+    res = _usage()
+    # K = 8 instantiations of the spline kernels (the generic-K ones hold up to 2 x 33 knots and spill by design)
+    hot = [k for k in res if any(t in k for t in ("nsf_pairs_fused_kernel", "gemm_ws_kernel", "wgrad_ws_kernel",
+                                                  "linear_tf32x3_kernel"))
+           or re.search(r"rqs_coupling_(pairs|tiled)ILi\dELi8E", k)]
+    assert len(hot) >= 20
+    spilled = {k: v for k, v in res.items() if k in hot and (v["STACK"] or v["LOCAL"])}
+    assert not spilled, spilled
+    # the fused layer kernel shares sub-partition 0 with its control warp: 5 warps -> at most 96 registers
+    assert res[FUSED]["REG"] <= 96, res[FUSED]
+
+
+def test_fused_layer_kernel_instruction_mix():
+    s = _sass(FUSED)
+    assert _count(s, "UTCHMMA") == 20                 # 4 (GEMM1) + 8 (GEMM2) + 8 (one GEMM3 chunk) tcgen05.mma
+    assert _count(s, "UBLKCP") >= 4                   # TMA bulk copies: weights, W3 ring, x rows in, z rows out
+    assert _count(s, "LDTM") >= 4                     # tcgen05.ld: two hidden-layer epilogues + the spline chunk
+    assert _count(s, "MUFU.TANH") == 64               # 2 hidden layers x 32 columns per thread
+    assert _count(s, "FFMA2") >= 20 and _count(s, "FADD2") >= 12     # packed fp32x2 knot chains
+    assert "F2FP.SATFINITE.F16" in s                  # fp16 operands, saturating conversion of the inputs
+    # one spline element: 43 MUFU operations (profiles/fused_analysis_r01.md): 32 ex2 of the double softmaxes
+    # + 2 x (ex2, lg2) of the double softplus + 6 rcp + 1 lg2
+    mufu = _count(s, "MUFU.EX2") + _count(s, "MUFU.LG2") + _count(s, "MUFU.RCP")
+    assert 43 <= mufu <= 46, mufu
+
+
+def test_standalone_pairs_kernel_uses_tma_ring_and_packed_math():
+    s = _sass(PAIRS)
+    assert _count(s, "UBLKCP") >= 1 and _count(s, "SYNCS") >= 2       # TMA bulk loads completing on mbarriers
+    assert _count(s, "FFMA2") >= 20
+    assert _count(s, "SHFL") >= 5                     # log-det: warp-shuffle reduction (north star item 3)
+    assert "LDG.E.64" in s or "LDG.E.EF.64" in s or re.search(r"LDG\.E\.[A-Z.]*64", s)      # 8-byte coalesced activations
+
+
+def test_tensor_core_gemms_issue_tcgen05():
+    res = _usage()
+    for tag in ("gemm_ws_kernel", "wgrad_ws_kernel", "linear_tf32x3_kernel", "linear_bf16_kernel"):
+        fn = next(k for k in res if tag in k)
+        s = _sass(fn)
+        assert _count(s, "UTCHMMA") >= 1, tag
