@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NFK_ABI_VERSION 1
+#define NFK_ABI_VERSION 2
 
 enum {
   NFK_OK = 0,
@@ -42,8 +42,17 @@ enum {
   NFK_ARITH_FAST = 2    /* MUFU ex2/lg2/rcp everywhere (a few ulp).  The stand-alone transform kernels
                            (nfk_rqs_coupling, nfk_unconstrained_rqs, nfk_rqs_elementwise) still return the
                            reference's bin: an input within 1.2e-4*(B/3) of a fast-chain knot has its bin
-                           re-decided on the exact chain.  The fused bf16 layer kernels skip that fix-up --
-                           their parameters already differ from the reference's. */
+                           re-decided on the exact chain.  So do the fused layer kernels
+                           (nfk_nsf_pairs_fused, nfk_gemm_ws_rqs), on the parameters they compute. */
+};
+
+/* 16-bit element format of the tensor-core operand images of the wide conditioner path */
+enum {
+  NFK_IMG_BF16 = 0, /* bfloat16: 8-bit significand, fp32's range -- gradient images need the range, so the
+                       training / log-prob-gradient path keeps every image in bf16 */
+  NFK_IMG_F16 = 1   /* IEEE fp16: 11-bit significand (8x less quantisation noise at the same tensor-core
+                       rate); values saturate at +-65504.  Inference forward: activations are tanh outputs
+                       in (-1, 1), weights O(1) */
 };
 
 int nfk_abi_version(void);
@@ -189,16 +198,22 @@ int nfk_linear_bf16(const void* X, int64_t ldx, const void* W, int64_t ldw, cons
  * rows padded to 24) in the K-major SWIZZLE_128B shared-memory layout (16-byte chunk j of row r
  * holds source chunk j ^ (r % 8)); b1, b2 [128], b3 [32*24] fp32 padded the same way. */
 int nfk_nsf_fused_rows_per_tile(void);
-/* test hook: device buffer of 64 int64 receiving clock64 stamps of CTA 0, third tile (NULL = off) */
+/* In every arithmetic the bin an element uses is the one searchsorted (nf/utils.py:20-25) finds on the
+ * spline parameters THIS kernel computed (EXACT / HYBRID search the exact knot chain, FAST re-decides on
+ * it next to a knot).  Test hooks (NULL in production): dbg_params [N][32][24] receives those raw
+ * parameters (accumulator + b3; the 24th column is padding), dbg_bins [N][32] the bins (-1 = tail).
+ * test hook: device buffer of 64 int64 receiving clock64 stamps of CTA 0, third tile (NULL = off) */
 int nfk_set_fused_trace(void* dev_buf);
 int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w1_img,
                         const void* w2_img, const void* w3_img, const float* b1, const float* b2,
                         const float* b3, int64_t N, int mask_col, float B, int inverse,
-                        int accumulate, int arith, void* stream);
+                        int accumulate, int arith, float* dbg_params /*nullable*/,
+                        int8_t* dbg_bins /*nullable*/, void* stream);
 
 /* ---- wide conditioner path (hidden width > 128; the class default is 800, nf/flows.py:216):
  * persistent warp-specialised tcgen05 GEMM  Y = act(A W^T + b)  over operands stored in HBM as
- * *shared-memory images*: 128-row x 64-column bf16 blocks (16 KB) in the K-major SWIZZLE_128B
+ * *shared-memory images*: 128-row x 64-column blocks of 16-bit elements (16 KB; `fmt` = NFK_IMG_BF16 or
+ * NFK_IMG_F16, the same for every image of one launch) in the K-major SWIZZLE_128B
  * layout (16-byte chunk j of row r holds source chunk j ^ (r % 8)), moved by 1-D TMA bulk copies.
  *   a_img [ceil(M/128)][KB][128][64] bf16                    activations (rows >= M are zero)
  *   w_img for N tile t of 64*tile_blocks[t] output columns:  [KB][64*tile_blocks[t]][64] bf16,
@@ -220,7 +235,7 @@ int nfk_set_gemm_ws_pair_mode(int mode);
 int nfk_gemm_ws_last_clusters(void);
 int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* out, int64_t M,
                 int KB, int kmma_last, const int32_t* tile_blocks /*host*/, int n_tiles, int act,
-                int out_f32, int n_out, int64_t ldy, const void* aux, void* stream);
+                int out_f32, int n_out, int64_t ldy, const void* aux, int fmt, void* stream);
 /* grouped launch: n_groups independent GEMMs with the same N-tile plan, activation, output kind and
  * row count M run in ONE persistent kernel (work items interleave the groups).  groups_dev is a DEVICE
  * array of n_groups records {a_img, w_img, bias, out (pointers), KB, kmma_last, a_kb, pad (int32)}, each
@@ -229,23 +244,26 @@ int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* o
  * (nf/flows.py:167-169, :186). */
 int nfk_gemm_ws_group_bytes(void);
 int nfk_gemm_ws_grouped(const void* groups_dev, int n_groups, int64_t M, const int32_t* tile_blocks /*host*/,
-                        int n_tiles, int act, int out_f32, int n_out, int64_t ldy, void* stream);
+                        int n_tiles, int act, int out_f32, int n_out, int64_t ldy, int fmt, void* stream);
 /* NSF_AR conditioner inputs in one launch (nf/flows.py:172-173, :186): the a_img
  * [ceil(N/128)][ceil(2*dim/64)][128][64] of the interleaved features [cos(pi x_0/B), sin(pi x_0/B),
  * cos(pi x_1/B), ...]; conditioner i reads its first ceil(2i/64) K blocks (group record a_kb =
  * ceil(2*dim/64)) and its weight image carries the columns in the same interleaved order. */
-int nfk_nsf_ar_pack(const float* x, void* img, int64_t N, int dim, float B, void* stream);
+int nfk_nsf_ar_pack(const float* x, void* img, int64_t N, int dim, float B, int fmt, void* stream);
 /* last conditioner GEMM with the RQS transform as its epilogue (any size, 2 <= dim <= 4, K = 8,
  * at most 128 transformed features): replaces the third nn.Linear of psi + nf/flows.py:232-239 /
  * :246-253 + nf/utils.py:20-152; the [N, F_t, 23] parameter tensor never reaches HBM.  w_img: each
  * feature's 23 weight rows padded to 24, N tiles of 8 features (192 rows; the last tile zero
  * padded), layout as nfk_gemm_ws; bias [ceil(F_t/8)*8*24] padded the same way.  x, out
  * [M, size*dim] fp32 (out in the reference's column order, quirk Q5); logdet [M] (+= when
- * accumulate); mask is a HOST array of n_mask conditioning columns. */
+ * accumulate); mask is a HOST array of n_mask conditioning columns.  Test hooks (NULL in production):
+ * dbg_params [M][8*ceil(F_t/8)][24] / dbg_bins [M][8*ceil(F_t/8)] receive the raw parameters
+ * (accumulator + bias) and the bin of every element, as for nfk_nsf_pairs_fused. */
 int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, const float* x,
                     float* out, float* logdet, int64_t M, int KB, int kmma_last, int size, int dim,
                     const int32_t* mask, int n_mask, float B, int inverse, int accumulate,
-                    int arith, void* stream);
+                    int arith, int fmt, float* dbg_params /*nullable*/, int8_t* dbg_bins /*nullable*/,
+                    void* stream);
 /* BACKWARD twin of nfk_gemm_ws_rqs: recomputes the spline parameters with the same GEMM
  * (a_img = saved last hidden activation, w_img / bias as the forward) and runs the spline's
  * adjoint as the epilogue: grad_x [M, size*dim] receives the direct path (transformed columns
@@ -274,7 +292,7 @@ int nfk_wgrad_ws(const void* a_img, const void* b_img, float* C, int64_t ldc, in
  * per feature.  Everything outside the source is zero.  One launch per layer and parameter version. */
 int nfk_pack_w_img(const float* W, int64_t ld, int n_src_rows, int n_src_cols, void* img, int KB,
                    const int32_t* tile_blocks /*host*/, int n_tiles, int transposed, int pad_rows,
-                   int pad_k, void* stream);
+                   int pad_k, int fmt, void* stream);
 /* bf16 image [ceil(M/128)][KB][128][64] -> row-major bf16 rows [M, ld], first ncols columns (ncols, ld
  * multiples of 8): hands saved activations / gradient images to the weight-gradient GEMMs */
 int nfk_unpack_img_rows(const void* img, void* rows, int64_t M, int KB, int ncols, int64_t ld,
@@ -285,7 +303,7 @@ int nfk_scatter_add_cols(float* g, const float* dxc, int64_t N, int size, int di
                          const int32_t* cols /*host*/, int n_cols, void* stream);
 /* x[:, :, cols].flatten(1) (nf/flows.py:230) -> bf16 a_img [ceil(N/128)][KB][128][64], zero padded */
 int nfk_pack_a_img(const float* x, void* img, int64_t N, int size, int dim, const int32_t* cols /*host*/,
-                   int n_cols, int KB, void* stream);
+                   int n_cols, int KB, int fmt, void* stream);
 
 /* x[:, cols] gather -> dense fp32 or bf16 [N, size*n_cols] (conditioner input, flows.py:230) */
 int nfk_gather_cols(const float* x, void* out, int64_t N, int size, int dim,

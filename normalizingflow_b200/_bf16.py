@@ -17,8 +17,8 @@ def _pad8(n: int) -> int:
 def _packed_weights(fcnn):
     """[(W_bf16 [out, pad8(in)], bias fp32)] for the three Linear layers, cached on the module."""
     layers = (fcnn.network[0], fcnn.network[2], fcnn.network[4])
-    key = tuple((l.weight._version, l.weight.data_ptr(), l.bias._version if l.bias is not None else -1)
-                for l in layers)
+    key = (_lib.param_epoch(),) + tuple(
+        (l.weight._version, l.weight.data_ptr(), l.bias._version if l.bias is not None else -1) for l in layers)
     cache = getattr(fcnn, "_bf16_cache", None)
     if cache is not None and cache[0] == key:
         return cache[1]
@@ -64,8 +64,9 @@ def to_bf16_padded(x):
 
 
 class MLP3Bf16Fn(torch.autograd.Function):
-    """Whole FCNN on the bf16 tensor-core path.  Backward uses plain library GEMMs (torch.matmul,
-    cuBLAS) on the saved bf16 activations — dgrad/wgrad are not fused hot ops."""
+    """Cross-check path (tests; taken in product code only if libnfk lacks nfk_wgrad_ws, which build()
+    rejects): FCNN forward on nfk_linear_bf16, backward through library GEMMs.  The product path for
+    bf16 training is _wide.Mlp3WideFn."""
 
     @staticmethod
     def forward(ctx, x, w0, b0, w2, b2, w4, b4, fcnn):
@@ -97,6 +98,11 @@ def mlp3(fcnn, x):
     if x.dim() != 2:
         x = x.reshape(x.shape[0], -1)
     if torch.is_grad_enabled() and (x.requires_grad or l0.weight.requires_grad):
+        from . import _wide
+        if x.dtype == torch.float32 and x.is_cuda and _wide.mlp3_grad_ok(fcnn):
+            # forward AND backward on the hand-written tensor-core GEMMs (images, dgrad with fused tanh
+            # backward, nfk_wgrad_ws); MLP3Bf16Fn below is the library cross-check kept for tests
+            return _wide.Mlp3WideFn.apply(x, l0.weight, l0.bias, l2.weight, l2.bias, l4.weight, l4.bias, fcnn)
         return MLP3Bf16Fn.apply(x, l0.weight, l0.bias, l2.weight, l2.bias, l4.weight, l4.bias, fcnn)
     if x.dtype == torch.float32:
         from . import _wide

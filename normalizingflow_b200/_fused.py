@@ -36,7 +36,8 @@ def _swizzle_image(mat):
 def packed(layer):
     net = layer.psi.network
     l0, l2, l4 = net[0], net[2], net[4]
-    key = tuple((l.weight._version, l.weight.data_ptr(), l.bias._version) for l in (l0, l2, l4))
+    key = (_lib.param_epoch(),) + tuple((l.weight._version, l.weight.data_ptr(), l.bias._version)
+                                        for l in (l0, l2, l4))
     cache = getattr(layer, "_fused_cache", None)
     if cache is not None and cache[0] == key:
         return cache[1]
@@ -67,6 +68,26 @@ def packed(layer):
     return pk
 
 
+def run_debug(layer, x, inverse):
+    """Test hook: (out, logdet, params [N, 32, 23], bins [N, 32] int8) — the raw spline parameters the fused
+    kernel computed for every element (accumulator + b3) and the bin it used.  N must be a multiple of 128."""
+    dev = require_cuda(x)
+    x = f32c(x)
+    N = x.shape[0]
+    if N % ROWS:
+        raise ValueError(f"run_debug needs a multiple of {ROWS} rows")
+    pk = packed(layer)
+    out = torch.empty((N, 64), dtype=torch.float32, device=dev)
+    logdet = torch.empty((N,), dtype=torch.float32, device=dev)
+    params = torch.empty((N, NF, PC), dtype=torch.float32, device=dev)
+    bins = torch.empty((N, NF), dtype=torch.int8, device=dev)
+    with torch.cuda.device(dev):
+        call("nfk_nsf_pairs_fused", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
+             ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), N, layer._mask[0], float(layer.B), int(bool(inverse)), 0,
+             _ops._arith(layer.arith), ptr(params), ptr(bins), stream_ptr(dev))
+    return out, logdet, params[:, :, :23].contiguous(), bins
+
+
 def run(layer, x, inverse, logdet=None):
     """(out, logdet) of one NSF_CL layer through the fused kernel (whole 128-row tiles; a partial last
     tile is padded)."""
@@ -85,7 +106,7 @@ def run(layer, x, inverse, logdet=None):
             ev = tm.start("nsf_pairs_fused", dev) if tm is not None else None
             call("nfk_nsf_pairs_fused", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
                  ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), n_main, layer._mask[0], float(layer.B),
-                 int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), stream_ptr(dev))
+                 int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), ptr(None), ptr(None), stream_ptr(dev))
             if ev is not None:
                 tm.stop(ev, dev)
     if n_main < N:
@@ -101,7 +122,7 @@ def run(layer, x, inverse, logdet=None):
         with torch.cuda.device(dev):
             call("nfk_nsf_pairs_fused", ptr(xp), ptr(op), ptr(lp), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
                  ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), ROWS, layer._mask[0], float(layer.B),
-                 int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), stream_ptr(dev))
+                 int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), ptr(None), ptr(None), stream_ptr(dev))
         out[n_main:] = op[:nt]
         logdet[n_main:] = lp[:nt]
     return out, logdet

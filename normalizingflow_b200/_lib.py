@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("NFK_LIB") or os.path.join(_HERE, "libnfk.so")     # N
 NFK_OK, NFK_EINVAL, NFK_ECUDA, NFK_EUNSUPPORTED = 0, 1, 2, 3
 ARITH_EXACT, ARITH_HYBRID, ARITH_FAST = 0, 1, 2
 ARITH = {"exact": ARITH_EXACT, "hybrid": ARITH_HYBRID, "fast": ARITH_FAST}
+IMG_BF16, IMG_F16 = 0, 1          # NFK_IMG_*: element format of the wide path's operand images
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -59,25 +60,26 @@ SIGNATURES = {
     "nfk_nsf_fused_rows_per_tile": (c_int, []),
     "nfk_set_fused_trace": (c_int, [_P]),
     "nfk_nsf_pairs_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int,
-                                    c_int, _P]),
+                                    c_int, _P, _P, _P]),
     "nfk_gemm_f32": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int64,
                              c_int, _P]),
     "nfk_gemm_ws_rows_per_tile": (c_int, []),
     "nfk_set_gemm_ws_pair_mode": (c_int, [c_int]),
     "nfk_gemm_ws_last_clusters": (c_int, []),
-    "nfk_gemm_ws": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int64, _P, _P]),
+    "nfk_gemm_ws": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int64, _P, c_int,
+                            _P]),
     "nfk_gemm_ws_rqs_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P,
                                     c_int, c_float, c_int, _P]),
     "nfk_wgrad_ws": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
-    "nfk_pack_w_img": (c_int, [_P, c_int64, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
+    "nfk_pack_w_img": (c_int, [_P, c_int64, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "nfk_unpack_img_rows": (c_int, [_P, _P, c_int64, c_int, c_int, c_int64, _P]),
     "nfk_scatter_add_cols": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, _P]),
     "nfk_gemm_ws_group_bytes": (c_int, []),
-    "nfk_gemm_ws_grouped": (c_int, [_P, c_int, c_int64, _P, c_int, c_int, c_int, c_int, c_int64, _P]),
-    "nfk_nsf_ar_pack": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
+    "nfk_gemm_ws_grouped": (c_int, [_P, c_int, c_int64, _P, c_int, c_int, c_int, c_int, c_int64, c_int, _P]),
+    "nfk_nsf_ar_pack": (c_int, [_P, _P, c_int64, c_int, c_float, c_int, _P]),
     "nfk_gemm_ws_rqs": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_float, c_int,
-                                c_int, c_int, _P]),
-    "nfk_pack_a_img": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, c_int, _P]),
+                                c_int, c_int, c_int, _P, _P, _P]),
+    "nfk_pack_a_img": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int, _P]),
     "nfk_gather_cols": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_int64, _P]),
     "nfk_cast_f32_bf16": (c_int, [_P, _P, c_int64, _P]),
     "nfk_einstein_logprob": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_float, c_float, _P]),
@@ -172,3 +174,21 @@ def i32_array(values):
 
 def launch_count() -> int:
     return int(lib.nfk_launch_count())
+
+
+# Weight-image caches (fused / wide / bf16 / NSF_AR packs, host chunk graphs, HMC trajectory graphs) are
+# keyed on Parameter._version and data_ptr.  Writes that bypass the version counter -- a replayed CUDA
+# graph that contains the optimizer step, ``p.data`` writes such as dist.broadcast -- must bump this
+# epoch, which is part of every cache key.
+_PARAM_EPOCH = 0
+
+
+def param_epoch() -> int:
+    return _PARAM_EPOCH
+
+
+def invalidate_caches() -> None:
+    """Drop every cached weight image / captured graph on next use (call after writing parameters in a
+    way autograd's version counter does not see)."""
+    global _PARAM_EPOCH
+    _PARAM_EPOCH += 1

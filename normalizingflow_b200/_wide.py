@@ -12,6 +12,14 @@ from ._lib import call, f32c, i32_array, ptr, require_cuda, stream_ptr
 
 ROWS = 128
 MIN_HIDDEN = 129      # narrower conditioners use the fused layer kernel / nfk_linear_bf16
+BF16, F16 = _lib.IMG_BF16, _lib.IMG_F16
+# Element format of the operand images on the no-grad (inference) forward: IEEE fp16 -- the activations
+# are tanh outputs in (-1, 1), the weights O(1) and the conditioning inputs saturate at +-65504, so fp16's
+# range suffices and its 11-bit significand carries 8x less quantisation noise than bf16 at the same
+# tensor-core rate.  The gradient paths (training, log-prob gradients) keep every image in bf16: gradient
+# images need bf16's range and the backward kernels read the saved activations as bf16.
+INFER_FMT = F16
+_TORCH_FMT = {BF16: torch.bfloat16, F16: torch.float16}
 
 
 def available() -> bool:
@@ -46,13 +54,15 @@ def _swizzle_image(mat):
     return blk[:, r, j ^ (r & 7), :].contiguous()
 
 
-def weight_image(w, bias, kb: int, tiles):
+def weight_image(w, bias, kb: int, tiles, fmt=BF16):
     """(w_img, bias_pad) for W [n_out, k_in] and the N-tile plan ``tiles``."""
     n_out, k_in = w.shape
     ob = sum(tiles)
     dev = w.device
-    wp = torch.zeros((ob * 64, kb * 64), dtype=torch.bfloat16, device=dev)
-    wp[:n_out, :k_in] = w.detach().to(torch.bfloat16)
+    dt = _TORCH_FMT[fmt]
+    wp = torch.zeros((ob * 64, kb * 64), dtype=dt, device=dev)
+    wd = w.detach().float()
+    wp[:n_out, :k_in] = (wd.clamp(-65504.0, 65504.0) if fmt == F16 else wd).to(dt)
     parts, r0 = [], 0
     for nb in tiles:
         parts.append(_swizzle_image(wp[r0:r0 + nb * 64]).reshape(-1))
@@ -63,14 +73,14 @@ def weight_image(w, bias, kb: int, tiles):
     return torch.cat(parts).contiguous(), bp
 
 
-def pack_weight(w, kb, tiles, transposed=False, pad_rows=False, pad_k=False):
-    """bf16 W image of the fp32 matrix ``w`` in ONE launch (nfk_pack_w_img)."""
+def pack_weight(w, kb, tiles, transposed=False, pad_rows=False, pad_k=False, fmt=BF16):
+    """16-bit W image of the fp32 matrix ``w`` in ONE launch (nfk_pack_w_img)."""
     dev = require_cuda(w)
     w = f32c(w.detach())
-    img = torch.empty(sum(tiles) * 64 * kb * 64, dtype=torch.bfloat16, device=dev)
+    img = torch.empty(sum(tiles) * 64 * kb * 64, dtype=_TORCH_FMT[fmt], device=dev)
     with torch.cuda.device(dev):
         call("nfk_pack_w_img", ptr(w), w.stride(0), w.shape[0], w.shape[1], ptr(img), kb, i32_array(tiles), len(tiles),
-             int(transposed), int(pad_rows), int(pad_k), stream_ptr(dev))
+             int(transposed), int(pad_rows), int(pad_k), fmt, stream_ptr(dev))
     return img
 
 
@@ -81,12 +91,13 @@ def _pad_bias(bias, n, dev):
     return bp
 
 
-def packed(fcnn):
-    """Per-layer (w_img, bias, KB, kmma_last, tiles, n_out) cached on the module."""
+def packed(fcnn, fmt=BF16):
+    """Per-layer (w_img, bias, KB, kmma_last, tiles, n_out, fmt) cached on the module, one entry per format."""
     layers = (fcnn.network[0], fcnn.network[2], fcnn.network[4])
-    key = tuple((l.weight._version, l.weight.data_ptr(), l.bias._version if l.bias is not None else -1)
-                for l in layers)
-    cache = getattr(fcnn, "_wide_cache", None)
+    key = (_lib.param_epoch(),) + tuple(
+        (l.weight._version, l.weight.data_ptr(), l.bias._version if l.bias is not None else -1) for l in layers)
+    caches = fcnn.__dict__.setdefault("_wide_cache", {})
+    cache = caches.get(fmt)
     if cache is not None and cache[0] == key:
         return cache[1]
     out = []
@@ -95,26 +106,26 @@ def packed(fcnn):
         n_out, k_in = l.weight.shape
         tiles = plan_tiles(blocks(n_out))
         if l.weight.is_cuda:
-            w_img, b = pack_weight(l.weight, kb, tiles), _pad_bias(l.bias, sum(tiles) * 64, l.weight.device)
+            w_img, b = pack_weight(l.weight, kb, tiles, fmt=fmt), _pad_bias(l.bias, sum(tiles) * 64, l.weight.device)
         else:
-            w_img, b = weight_image(l.weight, l.bias, kb, tiles)
+            w_img, b = weight_image(l.weight, l.bias, kb, tiles, fmt)
         kmma_last = (k_in - 64 * (kb - 1) + 15) // 16
         out.append(dict(w=w_img, b=b, KB=kb, kmma_last=kmma_last, tiles=tiles, tiles_c=i32_array(tiles),
-                        n_out=n_out))
+                        n_out=n_out, fmt=fmt))
         kb = sum(tiles)
-    fcnn._wide_cache = (key, out)
+    caches[fmt] = (key, out)
     return out
 
 
-def pack_input(x, size, dim, cols, kb):
-    """x[:, :, cols].flatten(1) (nf/flows.py:230) -> bf16 A image."""
+def pack_input(x, size, dim, cols, kb, fmt=BF16):
+    """x[:, :, cols].flatten(1) (nf/flows.py:230) -> 16-bit A image."""
     dev = require_cuda(x)
     x = f32c(x)
     N = x.shape[0]
     m_tiles = (N + ROWS - 1) // ROWS
-    img = torch.empty((m_tiles, kb, ROWS, 64), dtype=torch.bfloat16, device=dev)
+    img = torch.empty((m_tiles, kb, ROWS, 64), dtype=_TORCH_FMT[fmt], device=dev)
     with torch.cuda.device(dev):
-        call("nfk_pack_a_img", ptr(x), ptr(img), N, size, dim, i32_array(cols), len(cols), kb, stream_ptr(dev))
+        call("nfk_pack_a_img", ptr(x), ptr(img), N, size, dim, i32_array(cols), len(cols), kb, fmt, stream_ptr(dev))
     return img
 
 
@@ -122,18 +133,21 @@ def gemm(a_img, layer, M, act, out_f32, tag="gemm_ws", aux=None):
     dev = a_img.device
     m_tiles = (M + ROWS - 1) // ROWS
     ob = sum(layer["tiles"])
+    fmt = layer.get("fmt", BF16)
+    if a_img.dtype != _TORCH_FMT[fmt]:
+        raise ValueError(f"gemm: activation image is {a_img.dtype}, weight image is {_TORCH_FMT[fmt]}")
     if out_f32:
         out = torch.empty((M, layer["n_out"]), dtype=torch.float32, device=dev)
         ldy = layer["n_out"]
     else:
-        out = torch.empty((m_tiles, ob, ROWS, 64), dtype=torch.bfloat16, device=dev)
+        out = torch.empty((m_tiles, ob, ROWS, 64), dtype=_TORCH_FMT[fmt], device=dev)
         ldy = 0
     with torch.cuda.device(dev):
         tm = _ops.KERNEL_TIMER
         ev = tm.start(tag, dev) if tm is not None else None
         call("nfk_gemm_ws", ptr(a_img), ptr(layer["w"]), ptr(layer["b"]), ptr(out), M, layer["KB"],
              layer["kmma_last"], layer["tiles_c"], len(layer["tiles"]), act, int(out_f32), layer["n_out"], ldy,
-             ptr(aux), stream_ptr(dev))
+             ptr(aux), fmt, stream_ptr(dev))
         if ev is not None:
             tm.stop(ev, dev)
     return out
@@ -142,11 +156,11 @@ def gemm(a_img, layer, M, act, out_f32, tag="gemm_ws", aux=None):
 def mlp3(fcnn, x, size=None, dim=1, cols=(0,)):
     """FCNN(x[:, :, cols].flatten(1)) -> fp32 [N, out_dim]; with the defaults x is the plain
     [N, in_dim] conditioner input."""
-    l1, l2, l3 = packed(fcnn)
+    l1, l2, l3 = packed(fcnn, INFER_FMT)
     if size is None:
         size = x.shape[1]
     N = x.shape[0]
-    a0 = pack_input(x, size, dim, list(cols), l1["KB"])
+    a0 = pack_input(x, size, dim, list(cols), l1["KB"], INFER_FMT)
     h1 = gemm(a0, l1, N, 1, False, "gemm_ws_l1")
     h2 = gemm(h1, l2, N, 1, False, "gemm_ws_l2")
     return gemm(h2, l3, N, 0, True, "gemm_ws_l3")
@@ -161,14 +175,15 @@ def rqs_eligible(layer) -> bool:
             and layer.psi.network[4].out_features == 23 * n_t)
 
 
-def packed_rqs(layer):
+def packed_rqs(layer, fmt=BF16):
     """(l1, l2, l3) of the layer's conditioner with l3 in the per-feature padded (23 -> 24 rows)
     layout of the fused spline epilogue: N tiles of 8 features."""
     fcnn = layer.psi
-    l1, l2, _ = packed(fcnn)
+    l1, l2, _ = packed(fcnn, fmt)
     last = fcnn.network[4]
-    key = (last.weight._version, last.weight.data_ptr(), last.bias._version)
-    cache = getattr(layer, "_wide_rqs_cache", None)
+    key = (_lib.param_epoch(), last.weight._version, last.weight.data_ptr(), last.bias._version)
+    caches = layer.__dict__.setdefault("_wide_rqs_cache", {})
+    cache = caches.get(fmt)
     if cache is None or cache[0] != key:
         H = last.in_features
         dev = last.weight.device
@@ -177,33 +192,42 @@ def packed_rqs(layer):
         b3 = torch.zeros((n_tiles * 8, 24), dtype=torch.float32, device=dev)
         b3[:n_t, :23] = last.bias.detach().float().reshape(n_t, 23)
         kb = sum(l2["tiles"])
-        w_img = pack_weight(last.weight, kb, [3] * n_tiles, pad_rows=True)      # 23 -> 24 rows per feature
-        l3 = dict(w=w_img, b=b3.reshape(-1), KB=kb, kmma_last=(H - 64 * (kb - 1) + 15) // 16)
-        layer._wide_rqs_cache = cache = (key, l3)
+        w_img = pack_weight(last.weight, kb, [3] * n_tiles, pad_rows=True, fmt=fmt)      # 23 -> 24 rows per feature
+        l3 = dict(w=w_img, b=b3.reshape(-1), KB=kb, kmma_last=(H - 64 * (kb - 1) + 15) // 16, fmt=fmt)
+        caches[fmt] = cache = (key, l3)
     return l1, l2, cache[1]
 
 
-def run_layer(layer, x, inverse, logdet=None):
-    """(out, logdet) of one eligible NSF_CL layer: pack + 2 GEMMs + GEMM-with-spline-epilogue."""
+def run_layer(layer, x, inverse, logdet=None, debug=False):
+    """(out, logdet) of one eligible NSF_CL layer: pack + 2 GEMMs + GEMM-with-spline-epilogue.
+    ``debug`` (test hook): also return the raw spline parameters [N, F_t, 23] the epilogue computed and the
+    bins [N, F_t] it used."""
     dev = require_cuda(x, logdet)
     x = f32c(x)
     N = x.shape[0]
-    l1, l2, l3 = packed_rqs(layer)
-    a0 = pack_input(x, layer.size, layer.dim, layer._mask, l1["KB"])
+    l1, l2, l3 = packed_rqs(layer, INFER_FMT)
+    a0 = pack_input(x, layer.size, layer.dim, layer._mask, l1["KB"], INFER_FMT)
     h1 = gemm(a0, l1, N, 1, False, "gemm_ws_l1")
     h2 = gemm(h1, l2, N, 1, False, "gemm_ws_l2")
     out = torch.empty((N, layer.size * layer.dim), dtype=torch.float32, device=dev)
     accumulate = logdet is not None
     if not accumulate:
         logdet = torch.empty((N,), dtype=torch.float32, device=dev)
+    n_t = layer.size * (layer.dim - len(layer._mask))
+    ftp = (n_t + 7) // 8 * 8
+    dbg_p = torch.zeros((N, ftp, 24), dtype=torch.float32, device=dev) if debug else None
+    dbg_b = torch.full((N, ftp), -1, dtype=torch.int8, device=dev) if debug else None
     with torch.cuda.device(dev):
         tm = _ops.KERNEL_TIMER
         ev = tm.start("gemm_ws_rqs", dev) if tm is not None else None
         call("nfk_gemm_ws_rqs", ptr(h2), ptr(l3["w"]), ptr(l3["b"]), ptr(x), ptr(out), ptr(logdet), N, l3["KB"],
              l3["kmma_last"], layer.size, layer.dim, i32_array(layer._mask), len(layer._mask), float(layer.B),
-             int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), stream_ptr(dev))
+             int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), INFER_FMT, ptr(dbg_p), ptr(dbg_b),
+             stream_ptr(dev))
         if ev is not None:
             tm.stop(ev, dev)
+    if debug:
+        return out, logdet, dbg_p[:, :n_t, :23].contiguous(), dbg_b[:, :n_t].contiguous()
     return out, logdet
 
 
@@ -239,7 +263,7 @@ def packed_bwd(layer):
     """dgrad operands (W3p^T, W2^T, W1^T images), cached per parameter version."""
     net = layer.psi.network
     l0, l2, l4 = net[0], net[2], net[4]
-    key = tuple((l.weight._version, l.weight.data_ptr()) for l in (l0, l2, l4))
+    key = (_lib.param_epoch(),) + tuple((l.weight._version, l.weight.data_ptr()) for l in (l0, l2, l4))
     cache = getattr(layer, "_wide_bwd_cache", None)
     if cache is not None and cache[0] == key:
         return cache[1]
@@ -268,7 +292,7 @@ def layer_forward_saving(layer, x, inverse, logdet=None):
     with torch.cuda.device(dev):
         call("nfk_gemm_ws_rqs", ptr(h2), ptr(l3["w"]), ptr(l3["b"]), ptr(x), ptr(out), ptr(logdet), N, l3["KB"],
              l3["kmma_last"], layer.size, layer.dim, i32_array(layer._mask), len(layer._mask), float(layer.B),
-             int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), stream_ptr(dev))
+             int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), BF16, ptr(None), ptr(None), stream_ptr(dev))
     return out, logdet, (x, h1, h2, bool(inverse))
 
 
@@ -314,9 +338,8 @@ def unpack_rows(img, M, ncols):
 
 
 def _mm_f32(a_t, b):
-    """a_t^T-contracted GEMM of two bf16 row-major operands with an fp32 result: [K, M]^T... i.e.
-    a_t [N, P], b [N, Q] -> a_t.T @ b [P, Q] (weight gradient: contraction over the batch).
-    Plain library GEMM (cuBLAS) — the batch-contraction GEMM is not on the inference hot path."""
+    """TEST-ONLY cross-check of nfk_wgrad_ws (reached only with ``NATIVE_WGRAD = False``, which no product
+    path sets): a_t [N, P], b [N, Q] -> a_t.T @ b [P, Q] through the library GEMM."""
     try:
         return torch.mm(a_t.t(), b, out_dtype=torch.float32)
     except TypeError:
@@ -355,7 +378,9 @@ class NsfWideFn(torch.autograd.Function):
         n_tiles = (n_t + 7) // 8
         l1 = packed(layer.psi)[0]
         a0 = pack_input(xs, layer.size, layer.dim, layer._mask, l1["KB"])
-        if NATIVE_WGRAD and _lib.have("nfk_wgrad_ws"):
+        if NATIVE_WGRAD:
+            if not _lib.have("nfk_wgrad_ws"):
+                raise RuntimeError("libnfk.so does not export nfk_wgrad_ws; rebuild the library")
             # batch contraction straight from the images (MN-major tcgen05 operands, split-K)
             gw4 = wgrad(g_img, h2, N, n_t * 23, H, pad_p=True)
             gw2 = wgrad(dz2, h1, N, H, H)
@@ -375,6 +400,59 @@ class NsfWideFn(torch.autograd.Function):
         gw0 = _mm_f32(dz1r, xc)
         gb0 = torch.sum(dz1r, dim=0, dtype=torch.float32)
         return g_in, gw0, gb0, gw2, gb2, gw4, gb4, None, None
+
+
+class Mlp3WideFn(torch.autograd.Function):
+    """A whole FCNN (nf/flows.py:20-35) with bf16 tensor-core GEMMs in BOTH directions, for layers that
+    are not grad_eligible NSF_CL layers (RealNVP s/t nets, NSF_AR conditioners, K != 8): forward = pack +
+    3 x nfk_gemm_ws keeping the activation images; backward = the gradient packed as an image, two
+    act = 2 dgrad GEMMs (tanh backward fused), one fp32-row dgrad GEMM, and nfk_wgrad_ws for the three
+    weight gradients (bias gradients = column sums of the gradient images)."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w2, b2, w4, b4, fcnn):
+        l1, l2, l3 = packed(fcnn)
+        xs = f32c(x.detach())
+        N, n_in = xs.shape
+        a0 = pack_input(xs, n_in, 1, [0], l1["KB"])
+        h1 = gemm(a0, l1, N, 1, False, "gemm_ws_l1")
+        h2 = gemm(h1, l2, N, 1, False, "gemm_ws_l2")
+        out = gemm(h2, l3, N, 0, True, "gemm_ws_l3")
+        ctx.save_for_backward(a0, h1, h2)
+        ctx.fcnn, ctx.N = fcnn, N
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a0, h1, h2 = ctx.saved_tensors
+        fcnn, N = ctx.fcnn, ctx.N
+        net = fcnn.network
+        l0, l2, l4 = net[0], net[2], net[4]
+        H, n_out, n_in = l4.in_features, l4.out_features, l0.in_features
+        key = (_lib.param_epoch(),) + tuple((l.weight._version, l.weight.data_ptr()) for l in (l0, l2, l4))
+        cache = getattr(fcnn, "_wide_bwd_cache", None)
+        if cache is None or cache[0] != key:
+            cache = fcnn._wide_bwd_cache = (key, (_transposed(l4.weight, blocks(n_out)),
+                                                  _transposed(l2.weight, blocks(H)),
+                                                  _transposed(l0.weight, blocks(H))))
+        t3, t2, t1 = cache[1]
+        g_img = pack_input(f32c(g), n_out, 1, [0], t3["KB"])
+        dz2 = gemm(g_img, t3, N, 2, False, "gemm_ws_d3", aux=h2)
+        dz1 = gemm(dz2, t2, N, 2, False, "gemm_ws_d2", aux=h1)
+        gx = gemm(dz1, t1, N, 0, True, "gemm_ws_d1") if ctx.needs_input_grad[0] else None
+        if not any(ctx.needs_input_grad[1:7]):
+            return (gx,) + (None,) * 7
+        gw4, gb4 = wgrad(g_img, h2, N, n_out, H), image_colsum(g_img, n_out)
+        gw2, gb2 = wgrad(dz2, h1, N, H, H), image_colsum(dz2, H)
+        gw0, gb0 = wgrad(dz1, a0, N, H, n_in), image_colsum(dz1, H)
+        return gx, gw0, gb0, gw2, gb2, gw4, gb4, None
+
+
+def mlp3_grad_ok(fcnn) -> bool:
+    net = getattr(fcnn, "network", None)
+    return (available() and _lib.have("nfk_wgrad_ws") and _lib.have("nfk_pack_w_img")
+            and getattr(fcnn, "precision", None) == "bf16" and net is not None and len(net) == 5
+            and all(net[i].bias is not None for i in (0, 2, 4)) and net[0].weight.is_cuda)
 
 
 NATIVE_WGRAD = True      # False: weight gradients through image -> rows + library GEMMs (cross-check path)
@@ -408,8 +486,7 @@ def image_colsum(img, ncols):
 def flow_grad_eligible(model) -> bool:
     """All layers are grad_eligible NSF_CL layers under a GaussianPrior."""
     from .flows import NSF_CL
-    prior = model.prior
-    return (hasattr(prior, "var") and hasattr(prior, "dim") and len(model.flows) > 0
+    return (hasattr(model, "_prior_var") and model._prior_var() is not None and len(model.flows) > 0
             and all(isinstance(f, NSF_CL) and grad_eligible(f) for f in model.flows))
 
 
@@ -418,15 +495,15 @@ def flow_logp_and_grad(model, x):
     grad_eligible NSF_CL layers under a GaussianPrior; None when the model does not qualify."""
     if not flow_grad_eligible(model):
         return None
-    prior = model.prior
+    var = model._prior_var()
     h = f32c(x.detach())
     logdet = torch.zeros(h.shape[0], dtype=torch.float32, device=h.device)
     ctxs = []
     for f in model.flows:
         h, logdet, ctx = layer_forward_saving(f, h, False, logdet)
         ctxs.append(ctx)
-    logp = _ops.gauss_logprob(h, prior.var) + logdet
-    g = h * (-1.0 / prior.var)                                      # d log N(z; 0, var I) / dz
+    logp = _ops.gauss_logprob(h, var, add=logdet, add_sign=1.0)
+    g = h * (-1.0 / var)                                      # d log N(z; 0, var I) / dz
     for f, ctx in zip(reversed(model.flows), reversed(ctxs)):
         g = layer_backward(f, ctx, g, None, 1.0)
     return logp, g
@@ -456,8 +533,10 @@ def _group_table(records, dev):
 def _nsf_ar_packs(layer):
     """Per conditioner (l1, l2, l3) with l1 packed for the INTERLEAVED [cos_0, sin_0, cos_1, ...] input
     order of the shared feature image (the reference order is [cos_0..cos_{i-1}, sin_0..sin_{i-1}])."""
-    key = tuple((f.network[0].weight._version, f.network[2].weight._version, f.network[4].weight._version,
-                 f.network[0].weight.data_ptr()) for f in layer.layers)
+    key = (_lib.param_epoch(),) + tuple(
+        (f.network[0].weight._version, f.network[2].weight._version, f.network[4].weight._version,
+         f.network[0].weight.data_ptr()) + tuple(f.network[i].bias._version for i in (0, 2, 4))
+        for f in layer.layers)
     cache = getattr(layer, "_ar_cache", None)
     if cache is not None and cache[0] == key:
         return cache[1]
@@ -468,11 +547,11 @@ def _nsf_ar_packs(layer):
         perm = torch.arange(2 * i, device=l0.weight.device).reshape(2, i).t().reshape(-1)   # [0, i, 1, i+1, ...]
         kb = blocks(2 * i)
         tiles = plan_tiles(blocks(l0.out_features))
-        l1 = dict(w=pack_weight(l0.weight.detach()[:, perm].contiguous(), kb, tiles),
+        l1 = dict(w=pack_weight(l0.weight.detach()[:, perm].contiguous(), kb, tiles, fmt=INFER_FMT), fmt=INFER_FMT,
                   b=_pad_bias(l0.bias, sum(tiles) * 64, l0.weight.device), KB=kb,
                   kmma_last=(2 * i - 64 * (kb - 1) + 15) // 16, tiles=tiles, tiles_c=i32_array(tiles),
                   n_out=l0.out_features)
-        _, l2, l3 = packed(f)
+        _, l2, l3 = packed(f, INFER_FMT)
         out.append((l1, l2, l3))
     layer._ar_cache = (key, out)
     layer._ar_tables = {}                 # group tables hold raw addresses of the old weight images
@@ -503,9 +582,9 @@ def nsf_ar_params(layer, x, max_rows=None):
             r1 = min(N, r0 + max_rows)
             n = r1 - r0
             mt = (n + ROWS - 1) // ROWS
-            a0 = torch.empty((mt, kb_img, ROWS, 64), dtype=torch.bfloat16, device=dev)
-            call("nfk_nsf_ar_pack", ptr(x[r0:r1]), ptr(a0), n, dim, float(layer.B), stream_ptr(dev))
-            h1 = torch.empty((G, mt, obh, ROWS, 64), dtype=torch.bfloat16, device=dev)
+            a0 = torch.empty((mt, kb_img, ROWS, 64), dtype=_TORCH_FMT[INFER_FMT], device=dev)
+            call("nfk_nsf_ar_pack", ptr(x[r0:r1]), ptr(a0), n, dim, float(layer.B), INFER_FMT, stream_ptr(dev))
+            h1 = torch.empty((G, mt, obh, ROWS, 64), dtype=_TORCH_FMT[INFER_FMT], device=dev)
             h2 = torch.empty_like(h1)
             ob = out[r0:r1]
             hs = mt * obh * ROWS * 64 * 2
@@ -531,7 +610,7 @@ def nsf_ar_params(layer, x, max_rows=None):
                                             (tabs[2], packs[0][2], 0, 1, "gemm_ws_grouped_l3")):
                 ev = tm.start(tag, dev) if tm is not None else None
                 call("nfk_gemm_ws_grouped", ptr(tab), G, n, lay["tiles_c"], len(lay["tiles"]), act, f32, P, dim * P,
-                     stream_ptr(dev))
+                     INFER_FMT, stream_ptr(dev))
                 if ev is not None:
                     tm.stop(ev, dev)
     return out

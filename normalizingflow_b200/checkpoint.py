@@ -19,14 +19,21 @@ def save_checkpoint(path, model, optimizer=None, scheduler=None, epoch=0, losses
                 "epoch": int(epoch), "loss": list(losses)}, path)
 
 
-def load_checkpoint(path, model, optimizer=None, scheduler=None, strict=False, device=None):
+def load_checkpoint(path, model, optimizer=None, scheduler=None, strict=False, device=None, trusted=False):
     """Load a reference-format checkpoint (applications/src/setup.py:102-109).  Returns
     (epoch, losses, load_state_dict result).  ``strict=False`` as in the reference; the returned
-    result lists missing / unexpected keys so a caller can insist on an exact match."""
+    result lists missing / unexpected keys so a caller can insist on an exact match.
+
+    The reference's checkpoints hold only tensors, dicts, lists and numbers, so the file is read with
+    ``weights_only=True`` (no arbitrary unpickling).  ``trusted=True`` allows the full unpickler for a
+    file from a trusted source that fails the restricted load."""
     try:
+        blob = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as e:                              # noqa: BLE001 - pickle / torch raise several types
+        if not trusted:
+            raise ValueError(f"{path}: cannot be read with weights_only=True ({type(e).__name__}: {e}); pass "
+                             "trusted=True to unpickle arbitrary objects from a file you trust") from e
         blob = torch.load(path, map_location="cpu", weights_only=False)
-    except TypeError:                                   # older torch without weights_only
-        blob = torch.load(path, map_location="cpu")
     if not isinstance(blob, dict) or "model" not in blob:
         raise ValueError(f"{path}: not a reference checkpoint (expected a dict with keys {KEYS})")
     result = model.load_state_dict(blob["model"], strict=strict)

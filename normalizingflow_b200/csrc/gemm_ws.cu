@@ -29,6 +29,7 @@
 // the [N, 32, 23] parameter tensor never exists in HBM.
 #include "rqs_bwd_math.cuh"
 #include "tc05.cuh"
+#include <type_traits>
 
 namespace nfk {
 
@@ -104,12 +105,15 @@ struct WsArgs {
   int nb[WS_MAX_TILES];    // 64-column blocks per N tile (1..4)
   int n_out;               // real output columns (fp32 row output)
   int act;                 // 0 identity, 1 tanh
+  int fmt;                 // 16-bit format of every operand / output image of this launch: NFK_IMG_BF16 or NFK_IMG_F16
   // EPI_RQS only
   const float* x;          // [M, size*dim]
   float* logdet;           // [M]
   int dim, n_mask, n_feat; // columns per group, conditioning columns per group, transformed features
   int mask[4], unm[4];     // conditioning / transformed column indices inside a group
   int accumulate;
+  float* dbg_params;       // optional test hook [M][8*n_tiles][24]: raw spline parameters (accumulator + b3)
+  signed char* dbg_bins;   // optional [M][8*n_tiles]: bin used per element (-1 = identity tail)
   RqsConsts c;
   // act == 2 (bf16 image epilogue): out = acc * (1 - h^2), h = aux image laid out like out
   const unsigned char* aux;
@@ -137,6 +141,11 @@ __device__ __forceinline__ WsGroup ws_item(const WsArgs& a, long long pt, long l
   g.a_kb = a.KB;
   g.pad_ = 0;
   return g;
+}
+
+// two fp32 -> one 32-bit word of the image format (fp16 saturates to +-65504: operands of unknown range)
+__device__ __forceinline__ uint32_t pack_img2(float lo, float hi, int fmt) {
+  return fmt == NFK_IMG_F16 ? pack_f16x2_sat(lo, hi) : pack_bf16x2(lo, hi);
 }
 
 __device__ __forceinline__ bool ws_elect_one() {
@@ -307,7 +316,8 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
         const WsGroup G = ws_item(a, pt, ptile);
         for (int t = 0; t < a.n_tiles; ++t, ++tl) {
           const uint32_t acc = tl & 1;
-          const uint32_t idesc = make_idesc_bf16(TWO ? 2 * WS_M : WS_M, a.nb[t] * 64);
+          const uint32_t idesc = a.fmt == NFK_IMG_F16 ? make_idesc_f16(TWO ? 2 * WS_M : WS_M, a.nb[t] * 64)
+                                                      : make_idesc_bf16(TWO ? 2 * WS_M : WS_M, a.nb[t] * 64);
           mbar_wait(&tempty[acc], ((tl >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d = tmem + acc * 256;
@@ -407,7 +417,14 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
             __syncwarp();
             if (lane == 0) { if (TWO) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }      // the accumulator may be overwritten
           }
-          const RqsOut o = rqs_element<MODE, 8, INVERSE, true>(RegParams{v, sB3 + f * WS_PC}, xin[e], a.c);
+          const RqsOut o = rqs_element<MODE, 8, INVERSE, true, true>(RegParams{v, sB3 + f * WS_PC}, xin[e], a.c);
+          if (a.dbg_params && live) {            // test hook (uniform branch)
+            const size_t ei = (size_t)grow * (a.n_tiles * WS_TF) + f;
+#pragma unroll
+            for (int i = 0; i < WS_PC; ++i)
+              a.dbg_params[ei * WS_PC + i] = i < 23 ? __uint_as_float(v[i]) + sB3[f * WS_PC + i] : 0.f;
+            if (a.dbg_bins) a.dbg_bins[ei] = (signed char)(gbase[e] >= 0 ? o.bin : -1);
+          }
           if (gbase[e] >= 0) {
             // transformed columns follow the conditioning ones inside a group: quirk Q5
             if (PAIRS) {
@@ -573,6 +590,9 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
           const int colb = (ob0 + b) * 64 + h * 32;        // first padded output column of v[]
           const float4* bp = reinterpret_cast<const float4*>(G.bias + colb);
           uint4 u[4];
+          // the image format is uniform per launch: one specialised copy of the conversion loop per format
+          auto convert = [&](auto is_f16) {
+          constexpr int FMT = decltype(is_f16)::value ? NFK_IMG_F16 : NFK_IMG_BF16;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 b0 = __ldg(bp + 2 * j), b1 = __ldg(bp + 2 * j + 1);
@@ -600,11 +620,13 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
                 f[2 * e + 1] *= fmaf(-h1, h1, 1.f);
               }
             }
-            u[j].x = pack_bf16x2(f[0], f[1]);
-            u[j].y = pack_bf16x2(f[2], f[3]);
-            u[j].z = pack_bf16x2(f[4], f[5]);
-            u[j].w = pack_bf16x2(f[6], f[7]);
+            u[j].x = pack_img2(f[0], f[1], FMT);
+            u[j].y = pack_img2(f[2], f[3], FMT);
+            u[j].z = pack_img2(f[4], f[5], FMT);
+            u[j].w = pack_img2(f[6], f[7], FMT);
           }
+          };
+          if (a.fmt == NFK_IMG_F16) convert(std::true_type{}); else convert(std::false_type{});
           // the team's previous bulk store must have finished reading the staging block
           if (issuer) bulk_wait_read<0>();
           asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
@@ -679,10 +701,10 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
                 for (int e = 0; e < 8; ++e) f[e] = tanh_approx(f[e]);
               }
               uint4 u;
-              u.x = pack_bf16x2(f[0], f[1]);
-              u.y = pack_bf16x2(f[2], f[3]);
-              u.z = pack_bf16x2(f[4], f[5]);
-              u.w = pack_bf16x2(f[6], f[7]);
+              u.x = pack_img2(f[0], f[1], a.fmt);
+              u.y = pack_img2(f[2], f[3], a.fmt);
+              u.z = pack_img2(f[4], f[5], a.fmt);
+              u.w = pack_img2(f[6], f[7], a.fmt);
               const int ch = h * 4 + j;
               *reinterpret_cast<uint4*>(sb + row * 128 + ((ch ^ (row & 7)) << 4)) = u;
             }
@@ -754,7 +776,7 @@ gemm_ws_kernel(const __grid_constant__ WsArgs a) {
 // One thread per 16-byte chunk of the image: coalesced 16-byte stores.
 __global__ void __launch_bounds__(256)
 pack_a_img_kernel(const float* __restrict__ x, unsigned char* __restrict__ img, long long N, long long m_tiles,
-                  int size, int dim, int n_cols, int c0, int c1, int c2, int c3, int KB) {
+                  int size, int dim, int n_cols, int c0, int c1, int c2, int c3, int KB, int fmt) {
   const int per_row = size * n_cols;
   const long long total = m_tiles * KB * 128 * 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -782,7 +804,7 @@ pack_a_img_kernel(const float* __restrict__ x, unsigned char* __restrict__ img, 
         f[e] = v;
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) w[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+      for (int e = 0; e < 4; ++e) w[e] = pack_img2(f[2 * e], f[2 * e + 1], fmt);
     }
     *reinterpret_cast<uint4*>(img + i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -798,7 +820,7 @@ struct PackWArgs {
   unsigned char* img;
   long long ld;
   int n_src_rows, n_src_cols;      // shape of the stored matrix
-  int KB, n_tiles, transposed, pad_rows, pad_k;
+  int KB, n_tiles, transposed, pad_rows, pad_k, fmt;
   int nb[WS_MAX_TILES];
 };
 __device__ __forceinline__ int unpad24(int i) { return (i % 24 == 23) ? -1 : (i / 24) * 23 + (i % 24); }
@@ -835,10 +857,10 @@ __global__ void __launch_bounds__(256) pack_w_img_kernel(const __grid_constant__
       f[e] = v;
     }
     uint4 u;
-    u.x = pack_bf16x2(f[0], f[1]);
-    u.y = pack_bf16x2(f[2], f[3]);
-    u.z = pack_bf16x2(f[4], f[5]);
-    u.w = pack_bf16x2(f[6], f[7]);
+    u.x = pack_img2(f[0], f[1], a.fmt);
+    u.y = pack_img2(f[2], f[3], a.fmt);
+    u.z = pack_img2(f[4], f[5], a.fmt);
+    u.w = pack_img2(f[6], f[7], a.fmt);
     *reinterpret_cast<uint4*>(a.img + i * 16) = u;
   }
 }
@@ -849,7 +871,7 @@ __global__ void __launch_bounds__(256) pack_w_img_kernel(const __grid_constant__
 // K blocks; its weight image is zero beyond column 2i, which masks the later dimensions).
 __global__ void __launch_bounds__(256)
 nsf_ar_pack_kernel(const float* __restrict__ x, unsigned char* __restrict__ img, long long N, long long m_tiles,
-                   int dim, int KB, float pi_f32, float B) {
+                   int dim, int KB, float pi_f32, float B, int fmt) {
   const long long total = m_tiles * KB * 128 * 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -872,10 +894,10 @@ nsf_ar_pack_kernel(const float* __restrict__ x, unsigned char* __restrict__ img,
       f[2 * e + 1] = sn;
     }
     uint4 u;
-    u.x = pack_bf16x2(f[0], f[1]);
-    u.y = pack_bf16x2(f[2], f[3]);
-    u.z = pack_bf16x2(f[4], f[5]);
-    u.w = pack_bf16x2(f[6], f[7]);
+    u.x = pack_img2(f[0], f[1], fmt);
+    u.y = pack_img2(f[2], f[3], fmt);
+    u.z = pack_img2(f[4], f[5], fmt);
+    u.w = pack_img2(f[6], f[7], fmt);
     *reinterpret_cast<uint4*>(img + i * 16) = u;
   }
 }
@@ -1017,9 +1039,13 @@ int nfk_set_gemm_ws_pair_mode(int mode) {
   return NFK_OK;
 }
 
+#define NFK_REQUIRE_FMT(who) \
+  NFK_REQUIRE(fmt == NFK_IMG_BF16 || fmt == NFK_IMG_F16, who ": fmt must be NFK_IMG_BF16 (0) or NFK_IMG_F16 (1)")
+
 int nfk_pack_a_img(const float* x, void* img, int64_t N, int size, int dim, const int32_t* cols, int n_cols,
-                   int KB, void* stream) {
+                   int KB, int fmt, void* stream) {
   NFK_REQUIRE(N >= 0 && size > 0 && dim > 0 && KB > 0, "pack_a_img: bad shape");
+  NFK_REQUIRE_FMT("pack_a_img");
   NFK_REQUIRE(cols && n_cols >= 1 && n_cols <= 4, "pack_a_img: 1..4 columns supported");
   NFK_REQUIRE((long long)size * n_cols <= (long long)KB * 64, "pack_a_img: %d columns do not fit %d K blocks",
               size * n_cols, KB);
@@ -1037,15 +1063,17 @@ int nfk_pack_a_img(const float* x, void* img, int64_t N, int size, int dim, cons
   const long long cap = (long long)sm_count() * 16;
   if (grid > cap) grid = cap;
   pack_a_img_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<unsigned char*>(img), N, m_tiles, size, dim, n_cols, c[0], c[1], c[2], c[3], KB);
+      x, reinterpret_cast<unsigned char*>(img), N, m_tiles, size, dim, n_cols, c[0], c[1], c[2], c[3], KB, fmt);
   count_launch();
   return check_launch("pack_a_img");
 }
 
 int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* out, int64_t M, int KB,
                 int kmma_last, const int32_t* tile_blocks, int n_tiles, int act, int out_f32, int n_out,
-                int64_t ldy, const void* aux, void* stream) {
+                int64_t ldy, const void* aux, int fmt, void* stream) {
   NFK_REQUIRE(M >= 0 && KB > 0, "gemm_ws: bad shape M=%lld KB=%d", (long long)M, KB);
+  NFK_REQUIRE_FMT("gemm_ws");
+  NFK_REQUIRE(act != 2 || fmt == NFK_IMG_BF16, "gemm_ws: act 2 (tanh backward) reads and writes bf16 images");
   NFK_REQUIRE(kmma_last >= 1 && kmma_last <= 4, "gemm_ws: kmma_last must be 1..4");
   NFK_REQUIRE(tile_blocks && n_tiles >= 1 && n_tiles <= WS_MAX_TILES, "gemm_ws: 1..%d N tiles", WS_MAX_TILES);
   NFK_REQUIRE(act >= 0 && act <= 2, "gemm_ws: act must be 0 (identity), 1 (tanh) or 2 (tanh backward)");
@@ -1077,14 +1105,16 @@ int nfk_gemm_ws(const void* a_img, const void* w_img, const float* bias, void* o
   a.n_tiles = n_tiles;
   a.n_out = n_out;
   a.act = act;
+  a.fmt = fmt;
   a.aux = reinterpret_cast<const unsigned char*>(aux);
   cudaStream_t st = (cudaStream_t)stream;
   return out_f32 ? launch_ws<EPI_F32_ROWS, 0, false>(a, st) : launch_ws<EPI_BF16_IMG, 0, false>(a, st);
 }
 
 int nfk_gemm_ws_grouped(const void* groups_dev, int n_groups, int64_t M, const int32_t* tile_blocks, int n_tiles,
-                        int act, int out_f32, int n_out, int64_t ldy, void* stream) {
+                        int act, int out_f32, int n_out, int64_t ldy, int fmt, void* stream) {
   NFK_REQUIRE(M >= 0 && n_groups >= 1, "gemm_ws_grouped: bad shape");
+  NFK_REQUIRE_FMT("gemm_ws_grouped");
   NFK_REQUIRE(tile_blocks && n_tiles >= 1 && n_tiles <= WS_MAX_TILES, "gemm_ws_grouped: 1..%d N tiles", WS_MAX_TILES);
   NFK_REQUIRE(act == 0 || act == 1, "gemm_ws_grouped: act must be 0 (identity) or 1 (tanh)");
   WsArgs a{};
@@ -1105,6 +1135,7 @@ int nfk_gemm_ws_grouped(const void* groups_dev, int n_groups, int64_t M, const i
   a.n_tiles = n_tiles;
   a.n_out = n_out;
   a.act = act;
+  a.fmt = fmt;
   a.KB = 1;
   a.kmma_last = 4;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1113,8 +1144,9 @@ int nfk_gemm_ws_grouped(const void* groups_dev, int n_groups, int64_t M, const i
 
 int nfk_gemm_ws_group_bytes(void) { return (int)sizeof(WsGroup); }
 
-int nfk_nsf_ar_pack(const float* x, void* img, int64_t N, int dim, float B, void* stream) {
+int nfk_nsf_ar_pack(const float* x, void* img, int64_t N, int dim, float B, int fmt, void* stream) {
   NFK_REQUIRE(N >= 0 && dim >= 2 && B > 0.f, "nsf_ar_pack: need dim >= 2 and B > 0");
+  NFK_REQUIRE_FMT("nsf_ar_pack");
   if (N == 0) return NFK_OK;
   NFK_REQUIRE(x && img && (reinterpret_cast<uintptr_t>(img) & 15) == 0, "nsf_ar_pack: bad pointer");
   const long long m_tiles = (N + 127) / 128;
@@ -1124,15 +1156,17 @@ int nfk_nsf_ar_pack(const float* x, void* img, int64_t N, int dim, float B, void
   const long long cap = (long long)sm_count() * 16;
   if (grid > cap) grid = cap;
   nsf_ar_pack_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<unsigned char*>(img), N,
-                                                                      m_tiles, dim, KB, 3.14159274101257324f, B);
+                                                                      m_tiles, dim, KB, 3.14159274101257324f, B, fmt);
   count_launch();
   return check_launch("nsf_ar_pack");
 }
 
 int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, const float* x, float* out,
                     float* logdet, int64_t M, int KB, int kmma_last, int size, int dim, const int32_t* mask,
-                    int n_mask, float B, int inverse, int accumulate, int arith, void* stream) {
+                    int n_mask, float B, int inverse, int accumulate, int arith, int fmt, float* dbg_params,
+                    int8_t* dbg_bins, void* stream) {
   NFK_REQUIRE(M >= 0 && KB > 0, "gemm_ws_rqs: bad shape M=%lld KB=%d", (long long)M, KB);
+  NFK_REQUIRE_FMT("gemm_ws_rqs");
   NFK_REQUIRE(kmma_last >= 1 && kmma_last <= 4, "gemm_ws_rqs: kmma_last must be 1..4");
   NFK_REQUIRE(arith >= NFK_ARITH_EXACT && arith <= NFK_ARITH_FAST, "gemm_ws_rqs: bad arith %d", arith);
   NFK_REQUIRE(B > 0.f, "gemm_ws_rqs: tail bound must be positive");
@@ -1155,6 +1189,9 @@ int nfk_gemm_ws_rqs(const void* a_img, const void* w_img, const float* bias, con
   a.x = x;
   a.logdet = logdet;
   a.accumulate = accumulate;
+  a.fmt = fmt;
+  a.dbg_params = dbg_params;
+  a.dbg_bins = reinterpret_cast<signed char*>(dbg_bins);
   a.c = make_rqs_consts(8, B);
   cudaStream_t st = (cudaStream_t)stream;
   const bool inv = inverse != 0;
@@ -1205,8 +1242,10 @@ int nfk_gemm_ws_rqs_bwd(const void* a_img, const void* w_img, const float* bias,
 }
 
 int nfk_pack_w_img(const float* W, int64_t ld, int n_src_rows, int n_src_cols, void* img, int KB,
-                   const int32_t* tile_blocks, int n_tiles, int transposed, int pad_rows, int pad_k, void* stream) {
+                   const int32_t* tile_blocks, int n_tiles, int transposed, int pad_rows, int pad_k, int fmt,
+                   void* stream) {
   NFK_REQUIRE(n_src_rows > 0 && n_src_cols > 0 && ld >= n_src_cols && KB > 0, "pack_w_img: bad shape");
+  NFK_REQUIRE_FMT("pack_w_img");
   NFK_REQUIRE(tile_blocks && n_tiles >= 1 && n_tiles <= WS_MAX_TILES, "pack_w_img: 1..%d N tiles", WS_MAX_TILES);
   NFK_REQUIRE(W && img && (reinterpret_cast<uintptr_t>(img) & 15) == 0, "pack_w_img: bad pointer");
   PackWArgs a{};
@@ -1220,6 +1259,7 @@ int nfk_pack_w_img(const float* W, int64_t ld, int n_src_rows, int n_src_cols, v
   a.transposed = transposed;
   a.pad_rows = pad_rows;
   a.pad_k = pad_k;
+  a.fmt = fmt;
   long long total = 0;
   for (int t = 0; t < n_tiles; ++t) {
     NFK_REQUIRE(tile_blocks[t] >= 1 && tile_blocks[t] <= 4, "pack_w_img: N tile of %d blocks", tile_blocks[t]);

@@ -62,6 +62,8 @@ struct FusedArgs {
   long long n_tiles;
   int cond_first;         // 1: conditioning column is column 0 of each pair (mask = [0])
   int accumulate;
+  float* dbg_params;      // optional [N][32][24]: the raw spline parameters (accumulator + b3) each element saw
+  signed char* dbg_bins;  // optional [N][32]: the bin each element used (-1 = identity tail)
   long long* trace;       // optional [17][32] clock64 stamps of CTA 0, tile 2: control warp, then the 16 epilogue warps (tools/trace_fused.py)
   RqsConsts c;
 };
@@ -342,8 +344,17 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
         o.y = (a.cond_first ? xc.y : xc.x) + __uint_as_float(v[0] ^ v[7] ^ v[15] ^ v[22]);
         o.lad = __uint_as_float(v[1] ^ v[9] ^ v[17]);
 #else
-        const RqsOut o = rqs_element<MODE, 8, INVERSE, true>(RegParams{v, sB3 + f * FU_PC},
-                                                              a.cond_first ? xc.y : xc.x, a.c);
+        // FAST decides the bin lazily on the exact chain next to a knot (FIXBINS), so in every arithmetic the
+        // bin is the one nf/utils.py:20-25 finds on the parameters this kernel computed
+        const RqsOut o = rqs_element<MODE, 8, INVERSE, true, true>(RegParams{v, sB3 + f * FU_PC},
+                                                                    a.cond_first ? xc.y : xc.x, a.c);
+        if (a.dbg_params) {            // test hook (uniform branch): what this element computed from
+          const size_t e = ((size_t)tile * FU_ROWS + row) * FU_NF + f;
+#pragma unroll
+          for (int i = 0; i < FU_PC; ++i)
+            a.dbg_params[e * FU_PC + i] = i < 23 ? __uint_as_float(v[i]) + sB3[f * FU_PC + i] : 0.f;
+          if (a.dbg_bins) a.dbg_bins[e] = (signed char)o.bin;
+        }
 #endif
         *pr = make_float2(a.cond_first ? xc.x : xc.y, o.y);  // (conditioning, transformed): Q5
         lad_acc += o.lad;
@@ -408,7 +419,8 @@ int nfk_nsf_fused_rows_per_tile(void) { return FU_ROWS; }
 
 int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w1_img, const void* w2_img,
                         const void* w3_img, const float* b1, const float* b2, const float* b3, int64_t N,
-                        int mask_col, float B, int inverse, int accumulate, int arith, void* stream) {
+                        int mask_col, float B, int inverse, int accumulate, int arith, float* dbg_params,
+                        int8_t* dbg_bins, void* stream) {
   NFK_REQUIRE(N >= 0 && N % FU_ROWS == 0, "nsf_pairs_fused: N must be a multiple of %d (got %lld)", FU_ROWS,
               (long long)N);
   NFK_REQUIRE(mask_col == 0 || mask_col == 1, "nsf_pairs_fused: mask column must be 0 or 1");
@@ -435,6 +447,8 @@ int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w
   a.n_tiles = N / FU_ROWS;
   a.cond_first = (mask_col == 0);
   a.accumulate = accumulate;
+  a.dbg_params = dbg_params;
+  a.dbg_bins = reinterpret_cast<signed char*>(dbg_bins);
   a.trace = g_fused_trace;
   a.c = make_rqs_consts(8, B);
   cudaStream_t st = (cudaStream_t)stream;

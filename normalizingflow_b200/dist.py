@@ -32,31 +32,46 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
-def bind_to_gpu_numa_node(local_rank: int) -> Optional[str]:
+def bind_to_gpu_numa_node(local_rank: int) -> str:
     """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that pinned host
     buffers allocated afterwards (first touch) and the copy-issuing thread are local to the GPU's
     PCIe root: with 8 ranks streaming host batches, cross-socket traffic is what caps the
-    end-to-end rate.  Best effort: returns a one-line description, or None when the topology
-    cannot be read (then nothing is changed)."""
+    end-to-end rate.  Best effort; always returns a one-line description: what was bound, or
+    ``"unbound: <why>"`` when nothing was changed (single-node VM, topology unreadable, ...)."""
     try:
         import pynvml
+    except Exception as e:                                      # noqa: BLE001
+        return f"unbound: pynvml not importable ({type(e).__name__})"
+    try:
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(_physical_index(local_rank))
         bus = pynvml.nvmlDeviceGetPciInfo(h).busId
         bus = bus.decode() if isinstance(bus, bytes) else bus
         bdf = bus.lower()[-12:]                                  # 0000:1b:00.0
+    except Exception as e:                                      # noqa: BLE001
+        return f"unbound: NVML query failed ({type(e).__name__}: {e})"
+    try:
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
-        if node < 0:
-            return None
+    except Exception as e:                                      # noqa: BLE001
+        return f"unbound: /sys/bus/pci/devices/{bdf}/numa_node unreadable ({type(e).__name__})"
+    try:
+        n_nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+    except OSError:
+        n_nodes = 0
+    if node < 0:
+        return f"unbound: GPU {local_rank} ({bdf}) reports numa_node={node} (no affinity exposed; host has {n_nodes} NUMA node(s))"
+    try:
         cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
         allowed = os.sched_getaffinity(0)
         cpus = sorted(set(cpus) & allowed)
         if not cpus:
-            return None
+            return f"unbound: no allowed CPU on NUMA node {node} of GPU {local_rank} ({bdf})"
+        if n_nodes <= 1:
+            return f"unbound: single NUMA node host (GPU {local_rank} {bdf} -> node {node}, {len(cpus)} CPUs): nothing to bind"
         os.sched_setaffinity(0, cpus)
         return f"GPU {local_rank} ({bdf}) -> NUMA node {node}, {len(cpus)} CPUs"
-    except Exception:                                           # noqa: BLE001 - best effort by design
-        return None
+    except Exception as e:                                      # noqa: BLE001 - best effort by design
+        return f"unbound: {type(e).__name__}: {e}"
 
 
 def _physical_index(local_rank: int) -> int:
@@ -93,6 +108,8 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> N
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+    from . import _lib                      # .data writes do not bump Parameter._version
+    _lib.invalidate_caches()
 
 
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], average: bool = True, group=None) -> int:

@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import torch
 
+from . import _lib
+
 
 def _warmup(fn, n=3):
     s = torch.cuda.Stream()
@@ -71,4 +73,7 @@ class GraphedTrainStep:
         for s, t in zip(self.static_in, inputs):
             s.copy_(t)
         self.graph.replay()
+        # the replayed optimizer step rewrote the parameters without touching their version counters:
+        # weight images / chunk graphs cached outside this graph are stale from here on
+        _lib.invalidate_caches()
         return self.static_loss

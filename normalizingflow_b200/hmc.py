@@ -21,7 +21,7 @@ import math
 import torch
 from torch.distributions import MultivariateNormal
 
-from . import _ops
+from . import _lib, _ops
 
 
 class HMC:
@@ -128,7 +128,15 @@ class FlowSimulation:
         self.d = self.position.shape[1]
         self.dim = dim if dim is not None else 1
         self.nparticles = nparticles if nparticles is not None else self.d // self.dim
-        self.inv_mass = 1.0 / float(mass)
+        if isinstance(mass, torch.Tensor):
+            if mass.numel() != 1 and not bool((mass == mass.flatten()[0]).all()):
+                raise ValueError("FlowSimulation integrates one scalar mass for all coordinates; per-particle "
+                                 "masses (HMC(mass=tensor)) must all be equal")
+            mass = float(mass.flatten()[0])
+        self.mass = float(mass)
+        if self.mass <= 0.0:
+            raise ValueError("mass must be positive")
+        self.inv_mass = 1.0 / self.mass
         self.velocity = torch.zeros_like(self.position)
         self.grad_evals = 0
         self.tensor_core_grad = True      # bf16-conditioner models: hand-written forward+backward path
@@ -143,7 +151,11 @@ class FlowSimulation:
         self.position = position.to(self.device, torch.float32).reshape(self.n_chains, -1).contiguous().clone()
 
     def set_velocity(self, velocity):
-        self.velocity = velocity.to(self.device, torch.float32).reshape(self.n_chains, -1).contiguous().clone()
+        """``velocity`` is what HMC.generate_v draws: v ~ N(0, 1/(m beta)) (hmc.py:24-27).  The kick / drift
+        kernels integrate the MOMENTUM p = m v (kick p += dt/2 F, drift q += dt p / m), so the velocity is
+        converted here; with the default unit mass the two coincide."""
+        v = velocity.to(self.device, torch.float32).reshape(self.n_chains, -1).contiguous().clone()
+        self.velocity = v * self.mass if self.mass != 1.0 else v
 
     def potential(self, x):
         return -self.model.evaluate(x)
@@ -192,7 +204,8 @@ class FlowSimulation:
         from . import _wide
         if not _wide.flow_grad_eligible(self.model):
             return None
-        key = (path_len, dt, self.n_chains, tuple(p._version for p in self.model.parameters()))
+        key = (path_len, dt, self.n_chains, _lib.param_epoch(),
+               tuple((p._version, p.data_ptr()) for p in self.model.parameters()))
         entry = self._graphs.get(key)
         if entry is None:
             self._graphs.clear()
@@ -229,10 +242,13 @@ class FlowSimulation:
             out = self._graph_trajectory(int(path_len), float(dt))
             if out is not None:
                 return out
-        q, p = self.position, self.velocity       # unit-mass convention: p is the velocity
+        # integrate on copies: HMC keeps references to the position it last accepted (hmc.py:36, :58),
+        # so advancing self.position in place would turn every rejection into an acceptance
+        q, p = self.position.clone(), self.velocity.clone()
         pot, force = self.potential_and_force(q)
         for _ in range(path_len):
             _ops.leapfrog_kick_drift(q, p, force, dt, self.inv_mass)      # p += dt/2 F ; q += dt p / m
             pot, force = self.potential_and_force(q)
             _ops.leapfrog_kick(p, force, dt)                               # p += dt/2 F(q_new)
+        self.position, self.velocity = q, p
         return q, pot

@@ -8,17 +8,21 @@
 Differences that do not change results: under ``torch.no_grad()`` each layer accumulates its
 log-det into the running [N] buffer inside its kernel (no separate add pass); consecutive
 ``Planar`` layers run as one fused stack kernel; a ``GaussianPrior`` is evaluated by the
-log-prob reduction kernel.  Any other prior object with ``.sample((n,))`` / ``.log_prob(x)``
-(e.g. torch.distributions.MultivariateNormal) is used as is.
+log-prob reduction kernel, and so is the prior the reference itself builds,
+``MultivariateNormal(0, vars*I)`` (applications/src/setup.py:25-30): a zero-mean scaled-identity
+``MultivariateNormal`` is recognised once and its ``log_prob`` routed to the same kernel (its ``sample`` stays
+torch's, so seeds reproduce the reference's latents).  Any other prior object with ``.sample((n,))`` /
+``.log_prob(x)`` is used as is.
 """
 from __future__ import annotations
 
 import math
+import warnings
 
 import torch
 import torch.nn as nn
 
-from . import _ops
+from . import _lib, _ops
 from .flows import Planar, PlanarStack
 
 
@@ -46,6 +50,20 @@ class GaussianPrior:
         return out.reshape(x.shape[:-1])
 
 
+def _scaled_identity_var(prior):
+    """var when ``prior`` is a zero-mean MultivariateNormal with covariance var*I (what the reference's
+    hot configs construct, setup.py:25-30), else None.  One host read per prior object."""
+    if not isinstance(prior, torch.distributions.MultivariateNormal):
+        return None
+    loc, tril = prior.loc, prior._unbroadcasted_scale_tril
+    if loc.dim() != 1 or tril.dim() != 2:
+        return None
+    diag = torch.diagonal(tril)
+    if bool((loc != 0).any()) or bool((tril - torch.diag(diag) != 0).any()) or bool((diag != diag[0]).any()):
+        return None
+    return float(diag[0]) ** 2
+
+
 class NormalizingFlowModel(nn.Module):
 
     def __init__(self, prior, flows, device="cpu", fuse_planar=True):
@@ -54,6 +72,29 @@ class NormalizingFlowModel(nn.Module):
         self.prior = prior
         self.flows = nn.ModuleList(flows)
         self.fuse_planar = fuse_planar
+        self._prior_var_cache = None
+
+    def _prior_var(self):
+        """Variance of an isotropic zero-mean Gaussian prior (GaussianPrior or a scaled-identity
+        MultivariateNormal), else None."""
+        prior = self.prior
+        if isinstance(prior, GaussianPrior):
+            return prior.var
+        c = self._prior_var_cache
+        if c is None or c[0] is not prior:
+            c = self._prior_var_cache = (prior, _scaled_identity_var(prior))
+        return c[1]
+
+    def prior_log_prob(self, z, add=None, add_sign=1.0):
+        """prior.log_prob(z) (+ add_sign * add) — nf/models.py:19-20, :34, :39.  Isotropic Gaussian priors
+        run on the log-prob reduction kernel with the addition folded in (no-grad calls)."""
+        var = self._prior_var()
+        if var is not None and z.is_cuda and z.dim() == 2 and not (torch.is_grad_enabled() and z.requires_grad):
+            return _ops.gauss_logprob(z, var, add=add, add_sign=add_sign)
+        if var is not None and z.is_cuda and z.dim() == 2 and add is None:
+            return _ops.GaussLogprobFn.apply(z, var)
+        lp = self.prior.log_prob(z)
+        return lp if add is None else lp + add_sign * add
 
     # runs of consecutive Planar layers collapse into one fused launch
     def _forward_plan(self):
@@ -80,7 +121,7 @@ class NormalizingFlowModel(nn.Module):
             else:
                 x, ld = flow.forward(x)
                 log_det = log_det + ld
-        z, prior_logprob = x, self.prior.log_prob(x)
+        z, prior_logprob = x, self.prior_log_prob(x)
         return z, prior_logprob, log_det
 
     def inverse(self, z):
@@ -100,14 +141,26 @@ class NormalizingFlowModel(nn.Module):
         with torch.no_grad():
             z = self.prior.sample((n_samples,))
             x, log_det = self.inverse(z)
-            log_px = self.prior.log_prob(z) - log_det
+            log_px = self.prior_log_prob(z, add=log_det, add_sign=-1.0)          # models.py:34
         return x.data, log_px.data, z.data
 
     def evaluate(self, x):
         with torch.no_grad():
-            z, prior_logprob, log_det = self.forward(x)
-            log_px = prior_logprob + log_det
+            log_px = self._log_px(x)
         return log_px.data
+
+    def _log_px(self, x):
+        """log p(x) = prior.log_prob(f(x)) + log_det (models.py:37-39) with the sum folded into the
+        log-prob reduction kernel."""
+        m, _ = x.shape
+        log_det = torch.zeros(m, dtype=torch.float32, device=x.device)
+        for flow in self._forward_plan():
+            if hasattr(flow, "_nfk_step"):
+                x, log_det = flow._nfk_step(x, log_det, False)
+            else:
+                x, ld = flow.forward(x)
+                log_det = log_det + ld
+        return self.prior_log_prob(x, add=log_det, add_sign=1.0)
 
 
     # ------------------------------------------------------------------------------------
@@ -120,19 +173,23 @@ class NormalizingFlowModel(nn.Module):
         """Copy streams and rotating device buffers, kept across calls: the next call's first
         host->device copy then overlaps the previous call's last kernels and device->host copy."""
         key = (str(dev), rows, d)
-        pipe = getattr(self, "_pipe", None)
-        if pipe is None or pipe["key"] != key:
+        pipes = self.__dict__.setdefault("_pipes", {})
+        pipe = pipes.get(key)
+        if pipe is None:
+            if len(pipes) >= 4:                  # bound the device memory held by rotating buffers
+                self.host_sync()
+                pipes.clear()
             nbuf = 3
-            pipe = dict(key=key, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), nbuf=nbuf, it=0,
-                        bufs=[torch.empty((rows, d), dtype=torch.float32, device=dev) for _ in range(nbuf)],
-                        free=[None] * nbuf)
-            self._pipe = pipe
+            pipe = pipes[key] = dict(key=key, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), nbuf=nbuf,
+                                     it=0, free=[None] * nbuf,
+                                     bufs=[torch.empty((rows, d), dtype=torch.float32, device=dev)
+                                           for _ in range(nbuf)])
         return pipe
 
     def _param_version(self):
         """Changes whenever a parameter is replaced or written in place (optimizer step, load_state_dict):
         captured chunk graphs hold pointers to weight images packed from one parameter version."""
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (_lib.param_epoch(),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _stream_rows(self, host_in, fn, outs, chunk_rows, wait=True, tag=None):
         """``tag`` names the computation (``fn``) for the chunk-graph cache: with a tag, the kernels of a
@@ -189,8 +246,10 @@ class NormalizingFlowModel(nn.Module):
                         slot["drained"] = torch.cuda.Event()
                         slot["drained"].record(s_out)
         if wait:
-            # results are valid once the CURRENT stream is synchronised (as for any non_blocking copy)
+            # the returned host tensors are read by the CPU, not by a stream: block the host until the
+            # device->host copies have landed (and keep the current stream ordered after them)
             cur.wait_stream(s_out)
+            s_out.synchronize()
         return outs
 
     host_graphs = True          # set False to run every chunk eagerly
@@ -207,27 +266,31 @@ class NormalizingFlowModel(nn.Module):
                 out = fn(xin)
             cur.wait_stream(side)
             return dict(graph=graph, out=tuple(out), drained=None)
-        except Exception:       # e.g. a layer that synchronises; keep the eager path
+        except Exception as e:       # e.g. a layer that synchronises; keep the eager path
             torch.cuda.synchronize(xin.device)
+            if not getattr(self, "_warned_eager", False):
+                self._warned_eager = True
+                warnings.warn("normalizingflow_b200: CUDA-graph capture of a host-pipeline chunk failed "
+                              f"({type(e).__name__}: {e}); chunks run eagerly (host-dispatch-bound, slower)",
+                              RuntimeWarning, stacklevel=2)
             return False
 
     def host_sync(self):
         """Block the host until every evaluate_host / inverse_host result has landed (needed before
         reading results of calls made with ``wait=False``)."""
-        pipe = getattr(self, "_pipe", None)
-        if pipe is not None:
+        for pipe in self.__dict__.get("_pipes", {}).values():
             pipe["s_out"].synchronize()
 
     def evaluate_host(self, x_host, out=None, chunk_rows=131072, wait=True):
         """log p(x) for a batch in host memory -> host tensor [N] (pinned when allocated here).
-        ``wait=False`` does not order the current stream after the device->host copies, so
-        back-to-back calls overlap completely; call ``host_sync()`` before reading the results."""
+        ``wait=True`` (default): the result is complete in host memory when the call returns.
+        ``wait=False`` returns while copies are in flight, so back-to-back calls overlap completely;
+        call ``host_sync()`` before reading any result."""
         if out is None:
             out = torch.empty(x_host.shape[0], dtype=torch.float32).pin_memory()
 
         def fn(x):
-            z, prior_logprob, log_det = self.forward(x)
-            return (prior_logprob + log_det,)
+            return (self._log_px(x),)
         self._stream_rows(x_host, fn, (out,), chunk_rows, wait, tag="evaluate")
         return out
 
@@ -241,6 +304,6 @@ class NormalizingFlowModel(nn.Module):
 
         def fn(z):
             x, log_det = self.inverse(z)
-            return x, self.prior.log_prob(z) - log_det
+            return x, self.prior_log_prob(z, add=log_det, add_sign=-1.0)
         self._stream_rows(z_host, fn, (out_x, out_log_px), chunk_rows, wait, tag="inverse")
         return out_x, out_log_px

@@ -25,35 +25,43 @@ def pair_mode(request):
     _lib.lib.nfk_set_gemm_ws_pair_mode(-1)
 
 
-def _layer(w, b, kb):
+def _layer(w, b, kb, fmt=0):
     W = _wide()
     n_out, k_in = w.shape
     tiles = W.plan_tiles(W.blocks(n_out))
-    w_img, bp = W.weight_image(w.cuda(), b.cuda(), kb, tiles)
-    return dict(w=w_img, b=bp, KB=kb, kmma_last=(k_in - 64 * (kb - 1) + 15) // 16, tiles=tiles, n_out=n_out)
+    w_img, bp = W.weight_image(w.cuda(), b.cuda(), kb, tiles, fmt)
+    return dict(w=w_img, b=bp, KB=kb, kmma_last=(k_in - 64 * (kb - 1) + 15) // 16, tiles=tiles, n_out=n_out, fmt=fmt)
+
+
+FMT_DTYPE = {0: torch.bfloat16, 1: torch.float16}
 
 
 @pytest.mark.parametrize("M,K,N,act,f32", [(128, 64, 64, 1, False), (1, 32, 800, 1, False), (300, 800, 800, 1, False),
                                            (1000, 800, 736, 0, True), (129, 76, 874, 0, True),
                                            (20000, 800, 1748, 0, True), (40000, 832, 832, 1, False),
                                            (257, 16, 100, 0, True)])
-def test_gemm_ws_matches_fp64(M, K, N, act, f32):
+@pytest.mark.parametrize("fmt", [0, 1], ids=["bf16", "fp16"])
+def test_gemm_ws_matches_fp64(M, K, N, act, f32, fmt):
     W = _wide()
+    dt = FMT_DTYPE[fmt]
     from normalizingflow_b200._lib import i32_array
     g = torch.Generator().manual_seed(M + K + N)
     x = torch.randn(M, K, generator=g)
     w = torch.randn(N, K, generator=g) / K ** 0.5
     b = torch.randn(N, generator=g)
     kb = W.blocks(K)
-    a_img = W.pack_input(x.cuda(), K, 1, [0], kb)
-    # the packed image round-trips to the bf16-rounded input
+    a_img = W.pack_input(x.cuda(), K, 1, [0], kb, fmt)
+    # the packed image round-trips to the input rounded to the image format
     back = W.image_to_rows(a_img, M, K).float().cpu()
-    assert torch.equal(back, x.to(torch.bfloat16).float())
-    lay = _layer(w, b, kb)
+    assert torch.equal(back, x.to(dt).float())
+    # the device packer (nfk_pack_w_img) and the host packer build the same weight image
+    tiles0 = W.plan_tiles(W.blocks(N))
+    assert torch.equal(W.pack_weight(w.cuda(), kb, tiles0, fmt=fmt).cpu(), W.weight_image(w, b, kb, tiles0, fmt)[0])
+    lay = _layer(w, b, kb, fmt)
     lay["tiles_c"] = i32_array(lay["tiles"])
     y = W.gemm(a_img, lay, M, act, f32)
     torch.cuda.synchronize()
-    ref = torch.nn.functional.linear(x.to(torch.bfloat16).double(), w.to(torch.bfloat16).double(), b.double())
+    ref = torch.nn.functional.linear(x.to(dt).double(), w.to(dt).double(), b.double())
     if act:
         ref = torch.tanh(ref)
     if f32:
@@ -63,26 +71,32 @@ def test_gemm_ws_matches_fp64(M, K, N, act, f32):
         # padding columns of the image are exact zeros (they are the next layer's K padding)
         full = W.image_to_rows(y, M, sum(lay["tiles"]) * 64).float().cpu()
         assert torch.count_nonzero(full[:, N:]) == 0
-    tol = 2e-3 if (f32 and not act) else 1e-2
+    tol = 2e-3 if (f32 and not act) else (1e-2 if fmt == 0 else 2e-3)
     assert rel_err(got, ref) <= tol, rel_err(got, ref)
 
 
-def test_wide_mlp3_matches_bf16_chain():
+def test_wide_mlp3_matches_16bit_chain():
     """FCNN 32 -> 800 -> 800 -> 736 through the three wide GEMMs vs an fp64 evaluation that rounds
-    the operands to bf16 at the same places."""
+    the operands to the inference image format (fp16) at the same places."""
     W = _wide()
     from normalizingflow_b200 import flows
     torch.manual_seed(0)
     net = flows.FCNN(32, 736, 800, precision="bf16").cuda()
     x = torch.randn(3000, 64, generator=torch.Generator().manual_seed(5))
     y = W.mlp3(net, x.cuda(), 32, 2, [1]).cpu()
-    bf = lambda t: t.to(torch.bfloat16).double()
+    bf = lambda t: t.to(FMT_DTYPE[W.INFER_FMT]).double()
     l0, l2, l4 = net.network[0], net.network[2], net.network[4]
     xc = bf(x.reshape(-1, 32, 2)[:, :, 1])
     h1 = bf(torch.tanh(xc @ bf(l0.weight.cpu()).T + l0.bias.double().cpu()).float())
     h2 = bf(torch.tanh(h1 @ bf(l2.weight.cpu()).T + l2.bias.double().cpu()).float())
     ref = h2 @ bf(l4.weight.cpu()).T + l4.bias.double().cpu()
-    assert rel_err(y, ref) <= 1e-2, rel_err(y, ref)
+    assert rel_err(y, ref) <= 2e-3, rel_err(y, ref)
+    # and against the plain fp32 MLP: the north star's 1e-2 class for the 16-bit conditioner GEMMs
+    f32 = lambda t: t.double().cpu()
+    xc32 = x.reshape(-1, 32, 2)[:, :, 1].double()
+    r32 = torch.tanh(torch.tanh(xc32 @ f32(l0.weight).T + f32(l0.bias)) @ f32(l2.weight).T + f32(l2.bias)) \
+        @ f32(l4.weight).T + f32(l4.bias)
+    assert rel_err(y, r32) <= 2e-3, rel_err(y, r32)
 
 
 @pytest.mark.parametrize("inverse", [False, True])
@@ -135,8 +149,9 @@ def test_rqs_epilogue_lj38_geometry(inverse, mask):
 
 @pytest.mark.parametrize("inverse", [False, True])
 def test_nsf_layer_h800_vs_oracle(inverse):
-    """Whole NSF_CL layer at the class-default hidden width: wide bf16 conditioner + spline kernel
-    vs the fp32 oracle (1e-2 class of the bf16 conditioner path)."""
+    """Whole NSF_CL layer at the class-default hidden width: wide 16-bit conditioner (fp16 operand images on
+    the inference forward) with the spline epilogue vs the fp32 oracle: the north star's 1e-2 for BOTH z
+    and log_det (a sum of 32 per-feature terms)."""
     from normalizingflow_b200 import flows
     from oracle import nf_oracle as O
     torch.manual_seed(1)
@@ -148,8 +163,8 @@ def test_nsf_layer_h800_vs_oracle(inverse):
     with torch.no_grad():
         out, ld = (lay.inverse if inverse else lay.forward)(x.cuda())
     ro, rld = O.nsf_cl(x, sd, 32, 2, [1], 8, 3.0, inverse)[:2]
-    assert rel_err(out.cpu(), ro) <= 1e-2
-    assert rel_err(ld.cpu(), rld) <= 2e-2
+    assert rel_err(out.cpu(), ro) <= 1e-2, rel_err(out.cpu(), ro)
+    assert rel_err(ld.cpu(), rld) <= 1e-2, rel_err(ld.cpu(), rld)
 
 
 @pytest.mark.parametrize("N", [0, 1, 127, 129, 300])

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     # every declared function has a ctypes signature and vice versa
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert _lib.MISSING == []
-    assert _lib.lib.nfk_abi_version() == 1
+    assert _lib.lib.nfk_abi_version() == 2
     assert _lib.lib.nfk_nsf_fused_rows_per_tile() == 128
 
 
@@ -208,16 +208,22 @@ def test_wide_path_tile_plan_and_operand_images():
     # argument errors are caught on the host (NFK_EINVAL), before any launch
     L = _lib.lib
     tiles_c = (ctypes.c_int32 * 1)(5)
-    assert L.nfk_gemm_ws(None, None, None, None, 128, 1, 4, tiles_c, 1, 1, 0, 0, 0, None, None) == _lib.NFK_EINVAL
+    assert L.nfk_gemm_ws(None, None, None, None, 128, 1, 4, tiles_c, 1, 1, 0, 0, 0, None, 0, None) == _lib.NFK_EINVAL
     tiles_c = (ctypes.c_int32 * 1)(4)
-    assert L.nfk_gemm_ws(None, None, None, None, 128, 1, 7, tiles_c, 1, 1, 0, 0, 0, None, None) == _lib.NFK_EINVAL
-    assert L.nfk_gemm_ws(None, None, None, None, 128, 1, 4, tiles_c, 1, 2, 0, 0, 0, None, None) == _lib.NFK_EINVAL
-    assert L.nfk_gemm_ws(None, None, None, None, 0, 1, 4, tiles_c, 1, 1, 0, 0, 0, None, None) == 0
+    assert L.nfk_gemm_ws(None, None, None, None, 128, 1, 7, tiles_c, 1, 1, 0, 0, 0, None, 0, None) == _lib.NFK_EINVAL
+    assert L.nfk_gemm_ws(None, None, None, None, 128, 1, 4, tiles_c, 1, 2, 0, 0, 0, None, 0, None) == _lib.NFK_EINVAL
+    assert L.nfk_gemm_ws(None, None, None, None, 0, 1, 4, tiles_c, 1, 1, 0, 0, 0, None, 1, None) == 0
+    # image format: only NFK_IMG_BF16 / NFK_IMG_F16; the tanh-backward epilogue reads bf16 images only
+    assert L.nfk_gemm_ws(None, None, None, None, 128, 1, 4, tiles_c, 1, 1, 0, 0, 0, None, 2, None) == _lib.NFK_EINVAL
+    assert L.nfk_gemm_ws(None, None, None, None, 128, 1, 4, tiles_c, 1, 2, 0, 0, 0, tiles_c, 1, None) == _lib.NFK_EINVAL
+    # fp16 weight image on the host packer saturates instead of overflowing to inf
+    img16, _ = _wide.weight_image(torch.tensor([[1e6, -1e6, 0.5]]), None, 1, [1], _wide.F16)
+    assert img16.dtype == torch.float16 and float(img16.float().abs().max()) == 65504.0
     mask = (ctypes.c_int32 * 1)(3)
-    rc = L.nfk_gemm_ws_rqs(None, None, None, None, None, None, 128, 13, 2, 32, 2, mask, 1, 3.0, 0, 0, 2, None)
+    rc = L.nfk_gemm_ws_rqs(None, None, None, None, None, None, 128, 13, 2, 32, 2, mask, 1, 3.0, 0, 0, 2, 0, None, None, None)
     assert rc == _lib.NFK_EINVAL and b"mask" in L.nfk_last_error()
     mask = (ctypes.c_int32 * 1)(1)
-    rc = L.nfk_gemm_ws_rqs(None, None, None, None, None, None, 128, 13, 2, 200, 2, mask, 1, 3.0, 0, 0, 2, None)
+    rc = L.nfk_gemm_ws_rqs(None, None, None, None, None, None, 128, 13, 2, 200, 2, mask, 1, 3.0, 0, 0, 2, 1, None, None, None)
     assert rc == _lib.NFK_EINVAL and b"exceed" in L.nfk_last_error()
     assert L.nfk_gemm_ws_rqs_bwd(None, None, None, None, None, None, 1.0, None, None, 0, 13, 2, 32, 2, mask, 1, 3.0,
                                  0, None) == 0
