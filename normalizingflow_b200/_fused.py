@@ -73,9 +73,12 @@ def run_debug(layer, x, inverse):
     kernel computed for every element (accumulator + b3) and the bin it used.  N must be a multiple of 128."""
     dev = require_cuda(x)
     x = f32c(x)
+    n_real = x.shape[0]
+    if n_real % ROWS:                       # a partial last tile is zero-padded, as in run()
+        xp = torch.zeros(((n_real + ROWS - 1) // ROWS * ROWS, 64), dtype=torch.float32, device=dev)
+        xp[:n_real] = x
+        x = xp
     N = x.shape[0]
-    if N % ROWS:
-        raise ValueError(f"run_debug needs a multiple of {ROWS} rows")
     pk = packed(layer)
     out = torch.empty((N, 64), dtype=torch.float32, device=dev)
     logdet = torch.empty((N,), dtype=torch.float32, device=dev)
@@ -85,7 +88,7 @@ def run_debug(layer, x, inverse):
         call("nfk_nsf_pairs_fused", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
              ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), N, layer._mask[0], float(layer.B), int(bool(inverse)), 0,
              _ops._arith(layer.arith), ptr(params), ptr(bins), stream_ptr(dev))
-    return out, logdet, params[:, :, :23].contiguous(), bins
+    return out[:n_real], logdet[:n_real], params[:n_real, :, :23].contiguous(), bins[:n_real]
 
 
 def run(layer, x, inverse, logdet=None):

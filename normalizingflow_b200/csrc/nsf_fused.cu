@@ -85,7 +85,9 @@ __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar) {
 // feature-in-chunk = warp / 4); warp 16 is the control warp: it issues every tcgen05.mma and
 // every TMA bulk copy and never waits on arithmetic, so tensor work and weight streaming run
 // ahead of the epilogues.  All hand-offs are mbarriers; there is no CTA-wide barrier in the loop.
-template <int MODE, bool INVERSE>
+// DBG: test-hook instantiation that also writes the raw parameters and bins of every element (the production
+// instantiation carries none of that code: even a never-taken uniform branch cost 1-2 % of the launch).
+template <int MODE, bool INVERSE, bool DBG = false>
 __global__ void __launch_bounds__(FU_THREADS, 1)
 nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -346,15 +348,22 @@ nsf_pairs_fused_kernel(const __grid_constant__ FusedArgs a) {
 #else
         // FAST decides the bin lazily on the exact chain next to a knot (FIXBINS), so in every arithmetic the
         // bin is the one nf/utils.py:20-25 finds on the parameters this kernel computed
+#ifdef NFK_ABLATE_NOFIX       // timing experiment only: without the lazy exact-bin decision
+        const RqsOut o = rqs_element<MODE, 8, INVERSE, true, false>(RegParams{v, sB3 + f * FU_PC},
+                                                                     a.cond_first ? xc.y : xc.x, a.c);
+#else
         const RqsOut o = rqs_element<MODE, 8, INVERSE, true, true>(RegParams{v, sB3 + f * FU_PC},
                                                                     a.cond_first ? xc.y : xc.x, a.c);
-        if (a.dbg_params) {            // test hook (uniform branch): what this element computed from
+#endif
+#ifndef NFK_ABLATE_NODBG
+        if constexpr (DBG) {           // test hook: what this element computed from
           const size_t e = ((size_t)tile * FU_ROWS + row) * FU_NF + f;
 #pragma unroll
           for (int i = 0; i < FU_PC; ++i)
             a.dbg_params[e * FU_PC + i] = i < 23 ? __uint_as_float(v[i]) + sB3[f * FU_PC + i] : 0.f;
-          if (a.dbg_bins) a.dbg_bins[e] = (signed char)o.bin;
+          a.dbg_bins[e] = (signed char)o.bin;
         }
+#endif
 #endif
         *pr = make_float2(a.cond_first ? xc.x : xc.y, o.y);  // (conditioning, transformed): Q5
         lad_acc += o.lad;
@@ -386,9 +395,9 @@ static_assert(FU_SMEM <= 227 * 1024, "fused layer kernel exceeds the 227 KB shar
 
 RqsConsts make_rqs_consts(int K, float B);   // rqs_coupling.cu
 
-template <int MODE, bool INVERSE>
+template <int MODE, bool INVERSE, bool DBG = false>
 static int launch_fused(const FusedArgs& a, cudaStream_t st) {
-  auto kern = nsf_pairs_fused_kernel<MODE, INVERSE>;
+  auto kern = nsf_pairs_fused_kernel<MODE, INVERSE, DBG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM);
   if (e != cudaSuccess) {
     set_error("nsf_fused: cannot set %zu B dynamic shared memory: %s", FU_SMEM, cudaGetErrorString(e));
@@ -453,6 +462,14 @@ int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w
   a.c = make_rqs_consts(8, B);
   cudaStream_t st = (cudaStream_t)stream;
   const bool inv = inverse != 0;
+  if (dbg_params || dbg_bins) {
+    NFK_REQUIRE(dbg_params && dbg_bins, "nsf_pairs_fused: dbg_params and dbg_bins go together");
+    if (arith == NFK_ARITH_EXACT)
+      return inv ? launch_fused<NFK_ARITH_EXACT, true, true>(a, st) : launch_fused<NFK_ARITH_EXACT, false, true>(a, st);
+    if (arith == NFK_ARITH_HYBRID)
+      return inv ? launch_fused<NFK_ARITH_HYBRID, true, true>(a, st) : launch_fused<NFK_ARITH_HYBRID, false, true>(a, st);
+    return inv ? launch_fused<NFK_ARITH_FAST, true, true>(a, st) : launch_fused<NFK_ARITH_FAST, false, true>(a, st);
+  }
   if (arith == NFK_ARITH_EXACT)
     return inv ? launch_fused<NFK_ARITH_EXACT, true>(a, st) : launch_fused<NFK_ARITH_EXACT, false>(a, st);
   if (arith == NFK_ARITH_HYBRID)

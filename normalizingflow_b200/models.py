@@ -50,18 +50,33 @@ class GaussianPrior:
         return out.reshape(x.shape[:-1])
 
 
-def _scaled_identity_var(prior):
+def _scaled_identity_var(prior, why=None):
     """var when ``prior`` is a zero-mean MultivariateNormal with covariance var*I (what the reference's
-    hot configs construct, setup.py:25-30), else None.  One host read per prior object."""
-    if not isinstance(prior, torch.distributions.MultivariateNormal):
+    hot configs construct, setup.py:25-30), else None.  One host read per prior object.  The Cholesky
+    factor torch computed is accepted as sigma*I when its off-diagonal and the spread of its diagonal are
+    below 1e-6 of sigma (a device factorisation may differ from the exact sqrt in the last bit)."""
+    def no(msg):
+        if why is not None:
+            why.append(msg)
         return None
+    if not isinstance(prior, torch.distributions.MultivariateNormal):
+        return no(f"not a MultivariateNormal: {type(prior).__name__}")
     loc, tril = prior.loc, prior._unbroadcasted_scale_tril
     if loc.dim() != 1 or tril.dim() != 2:
-        return None
-    diag = torch.diagonal(tril)
-    if bool((loc != 0).any()) or bool((tril - torch.diag(diag) != 0).any()) or bool((diag != diag[0]).any()):
-        return None
-    return float(diag[0]) ** 2
+        return no(f"batched prior: loc {tuple(loc.shape)}, scale_tril {tuple(tril.shape)}")
+    diag = torch.diagonal(tril).double()
+    sigma = float(diag.mean())
+    off = float((tril.double() - torch.diag(diag)).abs().max())
+    spread = float((diag - sigma).abs().max())
+    mean = float(loc.abs().max())
+    if not (sigma > 0.0) or mean != 0.0 or off > 1e-6 * sigma or spread > 1e-6 * sigma:
+        return no(f"not a zero-mean scaled identity: |loc| {mean:.3g}, off-diagonal {off:.3g}, diagonal spread "
+                  f"{spread:.3g}, sigma {sigma:.6g}")
+    # prefer the caller's own covariance entry when it is available (exact var, not sigma^2 re-rounded)
+    cov = prior.__dict__.get("covariance_matrix")
+    if cov is not None and cov.dim() == 2:
+        return float(cov[0, 0])
+    return sigma * sigma
 
 
 class NormalizingFlowModel(nn.Module):
@@ -80,7 +95,7 @@ class NormalizingFlowModel(nn.Module):
         prior = self.prior
         if isinstance(prior, GaussianPrior):
             return prior.var
-        c = self._prior_var_cache
+        c = getattr(self, "_prior_var_cache", None)
         if c is None or c[0] is not prior:
             c = self._prior_var_cache = (prior, _scaled_identity_var(prior))
         return c[1]
@@ -252,14 +267,68 @@ class NormalizingFlowModel(nn.Module):
             s_out.synchronize()
         return outs
 
+    def _stream_generated(self, n, fn, outs, chunk_rows, wait=True, tag=None):
+        """Like _stream_rows for work that has no host input: ``fn(rows)`` produces ``rows`` result rows on the
+        device (e.g. draws latents and pushes them through the flow); results go to the host tensors
+        ``outs`` chunk by chunk, the device->host copy of chunk i overlapping the kernels of chunk i+1."""
+        dev = next(self.parameters()).device
+        cur = torch.cuda.current_stream(dev)
+        rows_full = min(chunk_rows, n)
+        pipe = self._host_pipe(dev, rows_full, 0)
+        s_out, nbuf = pipe["s_out"], pipe["nbuf"]
+        # a user-supplied generator is not registered with the capture: run eagerly then
+        use_graphs = (tag is not None and self.host_graphs and not torch.cuda.is_current_stream_capturing()
+                      and getattr(self.prior, "generator", None) is None)
+        if use_graphs:
+            ver = self._param_version()
+            if pipe.get("ver") != ver:
+                pipe["ver"], pipe["graphs"] = ver, {}
+        pending = pipe.setdefault("pending", [None] * nbuf)
+        with torch.no_grad():
+            for a in range(0, n, chunk_rows):
+                b = min(n, a + chunk_rows)
+                k = pipe["it"] % nbuf
+                pipe["it"] += 1
+                slot = None
+                if use_graphs and b - a == rows_full:
+                    slot = pipe["graphs"].get((tag, k))
+                    if slot is None:
+                        slot = self._capture_chunk(fn, rows_full, cur)
+                        pipe["graphs"][(tag, k)] = slot
+                    if slot:
+                        if slot["drained"] is not None:
+                            cur.wait_event(slot["drained"])
+                        slot["graph"].replay()
+                        res = slot["out"]
+                if not slot:
+                    res = fn(b - a)
+                done = torch.cuda.Event()
+                done.record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(done)
+                    for r, o in zip(res, outs):
+                        if o is None:
+                            continue
+                        o[a:b].copy_(r, non_blocking=True)
+                        if not slot:
+                            r.record_stream(s_out)
+                    if slot:
+                        slot["drained"] = torch.cuda.Event()
+                        slot["drained"].record(s_out)
+        if wait:
+            cur.wait_stream(s_out)
+            s_out.synchronize()
+        return outs
+
     host_graphs = True          # set False to run every chunk eagerly
 
     def _capture_chunk(self, fn, xin, cur):
         """fn(xin) captured as a CUDA graph on a side stream (one eager call first: weight images are
         packed lazily).  Returns False when capture is not possible, and the chunk then runs eagerly."""
+        dev = xin.device if isinstance(xin, torch.Tensor) else next(self.parameters()).device
         try:
             fn(xin)
-            side = torch.cuda.Stream(xin.device)
+            side = torch.cuda.Stream(dev)
             side.wait_stream(cur)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
@@ -267,7 +336,7 @@ class NormalizingFlowModel(nn.Module):
             cur.wait_stream(side)
             return dict(graph=graph, out=tuple(out), drained=None)
         except Exception as e:       # e.g. a layer that synchronises; keep the eager path
-            torch.cuda.synchronize(xin.device)
+            torch.cuda.synchronize(dev)
             if not getattr(self, "_warned_eager", False):
                 self._warned_eager = True
                 warnings.warn("normalizingflow_b200: CUDA-graph capture of a host-pipeline chunk failed "
@@ -307,3 +376,28 @@ class NormalizingFlowModel(nn.Module):
             return x, self.prior_log_prob(z, add=log_det, add_sign=-1.0)
         self._stream_rows(z_host, fn, (out_x, out_log_px), chunk_rows, wait, tag="inverse")
         return out_x, out_log_px
+
+    def sample_host(self, n_samples, out_x=None, out_log_px=None, out_z=None, return_z=True, chunk_rows=131072,
+                    wait=True):
+        """``sample(n)`` (nf/models.py:31-35) delivered to host memory: the latents are drawn ON THE DEVICE by
+        ``prior.sample`` as the reference does, pushed through the inverse flow in row chunks, and
+        (x, log_px[, z]) land in (pinned) host tensors while the next chunk computes.  No host->device
+        traffic at all; ``return_z=False`` skips the copy of z."""
+        d = getattr(self.prior, "dim", None)
+        if d is None:
+            ev = getattr(self.prior, "event_shape", None)
+            d = int(ev[-1]) if ev else int(self.prior.sample((1,)).shape[-1])
+        if out_x is None:
+            out_x = torch.empty((n_samples, d), dtype=torch.float32).pin_memory()
+        if out_log_px is None:
+            out_log_px = torch.empty(n_samples, dtype=torch.float32).pin_memory()
+        if return_z and out_z is None:
+            out_z = torch.empty((n_samples, d), dtype=torch.float32).pin_memory()
+
+        def fn(rows):
+            z = self.prior.sample((rows,))
+            x, log_det = self.inverse(z)
+            return x, self.prior_log_prob(z, add=log_det, add_sign=-1.0), z
+        self._stream_generated(n_samples, fn, (out_x, out_log_px, out_z if return_z else None), chunk_rows, wait,
+                               tag="sample_z" if return_z else "sample")
+        return (out_x, out_log_px, out_z) if return_z else (out_x, out_log_px)

@@ -65,3 +65,31 @@ def test_graphed_train_step_tracks_eager_training(precision):
     assert losses_g[-1] < losses_g[0]
     for pe, pg in zip(me.parameters(), mg.parameters()):
         assert rel_err(pg, pe.detach().double().cpu()) <= 5e-3
+
+
+def test_eager_evaluation_after_graphed_steps_sees_the_new_weights():
+    """A replayed GraphedTrainStep rewrites the parameters without bumping their version counters; the
+    weight-image caches (fused / wide) must still be refreshed (parameter epoch, _lib.invalidate_caches):
+    eager evaluate() after graphed steps equals a fresh deep copy of the trained model."""
+    from normalizingflow_b200.graphs import GraphedTrainStep
+    m = _model("bf16")
+    x = torch.randn(640, 64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6))
+    with torch.no_grad():
+        before = m.evaluate(x).clone()          # fills the inference-side weight-image caches
+
+    def loss(xx):
+        z, plp, ld = m(xx)
+        return -torch.mean(plp + ld)
+    opt = torch.optim.Adam(m.parameters(), lr=5e-3, capturable=True)
+    step = GraphedTrainStep(loss, opt, x, warmup=1)
+    for _ in range(3):
+        step(x)
+    with torch.no_grad():
+        after = m.evaluate(x)
+        fresh = copy.deepcopy(m)
+        for mod in fresh.modules():             # a copy with no caches at all
+            for k in [k for k in mod.__dict__ if k.endswith("_cache") or k == "_ar_tables"]:
+                mod.__dict__.pop(k)
+        ref = fresh.evaluate(x)
+    assert torch.equal(after, ref)
+    assert float((after - before).abs().max()) > 1e-3

@@ -150,3 +150,58 @@ def test_layer_backward_matches_autograd(inverse, size, dim, mask, H):
     err = (gin - gref).abs() / (1.0 + gref.abs())
     assert float(err.median()) <= 2e-3, float(err.median())
     assert float((err > 3e-2).float().mean()) <= 5e-3, float((err > 3e-2).float().mean())
+
+
+def test_single_chain_eager_rejection_restores_the_position():
+    """n_chains = 1 on the eager integrator (fp32 conditioner): HMC keeps references to the position it
+    last accepted (nf/hmc.py:36, :58), so the integrator must not advance that tensor in place -- a
+    rejected move leaves position and potential exactly where they were."""
+    from normalizingflow_b200.hmc import HMC, FlowSimulation
+    m = _model()
+    q0 = torch.randn(1, 64, generator=torch.Generator().manual_seed(3)) * 0.3
+    sim = FlowSimulation(m, n_chains=1, nparticles=32, dim=2, init_pos=q0)
+    sim.tensor_core_grad = False
+    # the integrator works on copies: a reference taken before the step still holds the old position
+    held = sim.get_position()
+    snapshot = held.clone()
+    sim.set_velocity(torch.randn(1, 64, generator=torch.Generator().manual_seed(4)))
+    q1, _ = sim.integration_step(path_len=3, dt=0.2)
+    assert torch.equal(held, snapshot) and not torch.equal(q1, snapshot)
+    assert sim.get_position() is q1
+    sim.set_position(snapshot)
+    # through the driver: starting near the mode with full-temperature velocities most moves go uphill
+    # and are rejected (the reference's acceptance rule ignores the kinetic energy, Q12)
+    h = HMC(sim, path_len=3, dt=0.2, dim=2, beta=1.0)
+    torch.manual_seed(0)
+    pos, pot, logp, acc = h.hmc(epochs=10)
+    assert pos.shape == (10, 64) and 0.0 <= acc <= 1.0
+    n_rej = 0
+    for i in range(1, 10):
+        same_pos, same_pot = torch.equal(pos[i], pos[i - 1]), float(pot[i]) == float(pot[i - 1])
+        assert same_pos == same_pot, (i, same_pos, same_pot)      # a recorded position moves only when accepted
+        n_rej += int(same_pos)
+    assert n_rej >= 1, "test needs at least one rejection to be meaningful"
+    assert torch.equal(pos[0].cpu(), snapshot.flatten().cpu())
+    # the simulation's own state equals HMC's accepted state
+    assert torch.equal(sim.get_position().flatten().cpu(), torch.as_tensor(h.position).flatten().cpu())
+
+
+def test_mass_enters_the_dynamics_once():
+    """FlowSimulation(mass=m): HMC hands over velocities v ~ N(0, 1/(m beta)); the integrator must reproduce
+    velocity Verlet  q += dt v + dt^2/(2m) F ...  -- i.e. a trajectory with mass m and velocity v equals the
+    unit-mass trajectory with velocity v and forces F/m."""
+    from normalizingflow_b200.hmc import FlowSimulation
+    m = _model()
+    C, mass = 64, 4.0
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    q0 = torch.randn(C, 64, device="cuda", generator=gen) * 0.5
+    v0 = torch.randn(C, 64, device="cuda", generator=gen) * 0.5
+    sim = FlowSimulation(m, n_chains=C, init_pos=q0, mass=mass)
+    sim.set_velocity(v0)
+    dt = 0.05
+    U, F = sim.potential_and_force(q0)
+    q1, _ = sim.integration_step(path_len=1, dt=dt)
+    expect = q0 + dt * v0 + 0.5 * dt * dt * F / mass
+    assert float((q1 - expect).abs().max()) < 1e-5
+    with pytest.raises(ValueError):
+        FlowSimulation(m, n_chains=C, init_pos=q0, mass=torch.tensor([1.0, 2.0]))

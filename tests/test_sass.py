@@ -38,7 +38,7 @@ def _count(sass, mnemonic):
     return len(re.findall(r"\s" + re.escape(mnemonic) + r"[\s.;]", sass))
 
 
-FUSED = "_ZN3nfk22nsf_pairs_fused_kernelILi2ELb0EEEvNS_9FusedArgsE"
+FUSED = "_ZN3nfk22nsf_pairs_fused_kernelILi2ELb0ELb0EEEvNS_9FusedArgsE"      # FAST, forward, production (no debug hook)
 PAIRS = "_ZN3nfk18rqs_coupling_pairsILi2ELi8ELb0EEEvNS_12CouplingArgsE"
 
 
@@ -53,6 +53,7 @@ def test_only_sm100a_code_and_no_spills_in_the_hot_kernels():
     assert len(hot) >= 20
     # (the lazy exact-bin path of the FAST spline epilogue costs one gemm_ws instantiation two spilled
     # registers on its cold side: tolerated up to 16 bytes, nothing in the fused layer kernel)
+    hot = [k for k in hot if not re.search(r"nsf_pairs_fused_kernelILi\dELb[01]ELb1E", k)]      # debug-hook instantiations: tests only
     spilled = {k: v for k, v in res.items() if k in hot and (v["LOCAL"] or v["STACK"] > (16 if "gemm_ws_kernelILi2E" in k else 0))}
     assert not spilled, spilled
     # the fused layer kernel shares sub-partition 0 with its control warp: 5 warps -> at most 96 registers
@@ -69,8 +70,11 @@ def test_fused_layer_kernel_instruction_mix():
     assert "F2FP.SATFINITE.F16" in s                  # fp16 operands, saturating conversion of the inputs
     # one spline element: 43 MUFU operations (profiles/fused_analysis_r01.md): 32 ex2 of the double softmaxes
     # + 2 x (ex2, lg2) of the double softplus + 6 rcp + 1 lg2
+    # ... plus, statically, the cold side of the lazy exact-bin decision (one exact knot chain: 16 expf = 16
+    # EX2 and the reciprocal refinements of its two softmaxes), taken by ~1e-4 of the elements
     mufu = _count(s, "MUFU.EX2") + _count(s, "MUFU.LG2") + _count(s, "MUFU.RCP")
-    assert 43 <= mufu <= 46, mufu
+    assert 43 <= mufu <= 82, mufu
+    assert _count(s, "MUFU.EX2") <= 34 + 16 and _count(s, "MUFU.LG2") == 3
 
 
 def test_standalone_pairs_kernel_uses_tma_ring_and_packed_math():
