@@ -26,9 +26,12 @@ __all__ = ["FCNN", "RealNVP", "NSF_AR", "NSF_CL", "Planar", "Radial", "PlanarSta
 class FCNN(nn.Module):
     """Linear-Tanh-Linear-Tanh-Linear conditioner (nf/flows.py:20-35).
 
-    ``precision``: "fp32" = CUDA-core fp32 GEMMs (parity mode, matches the reference's addmm
-    to fp32 round-off); "bf16" = tcgen05 tensor-core GEMMs with bf16 operands and fp32
-    accumulation (throughput mode, 1e-2 parity class).
+    ``precision``: "fp32" = fp32-class GEMMs (3xTF32 on the tensor cores for inference, CUDA-core
+    kernels under autograd; parity mode, matches the reference's addmm to fp32 round-off);
+    "bf16" = tcgen05 tensor-core GEMMs with 16-bit operands and fp32 accumulation (throughput mode,
+    1e-2 parity class: fp16 operands on the inference forward, bf16 on the gradient paths);
+    "fp32x3" = as "fp32", and eligible NSF_CL layers run the split-operand fused layer kernel
+    (fp16 hi + lo operands, three tensor-core MMAs per product: fp32-class accuracy in one launch).
     """
 
     def __init__(self, in_dim, out_dim, hidden_dim, precision="fp32"):
@@ -48,7 +51,7 @@ class FCNN(nn.Module):
         if self.precision == "bf16":
             from . import _bf16
             return _bf16.mlp3(self, x)
-        if self.precision != "fp32":
+        if self.precision not in ("fp32", "fp32x3"):
             raise ValueError(f"unknown conditioner precision {self.precision!r}")
         if not torch.is_grad_enabled():
             # inference: the three GEMMs on the tensor cores with fp32-class accuracy (3xTF32,
