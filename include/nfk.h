@@ -210,6 +210,23 @@ int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w
                         int accumulate, int arith, float* dbg_params /*nullable*/,
                         int8_t* dbg_bins /*nullable*/, void* stream);
 
+/* Second generation of the fused layer kernel (csrc/nsf_fused2.cu), same contract as nfk_nsf_pairs_fused:
+ * the layer's phases run on three overlapping sets of warps (spline warps / hidden-layer warps one tile
+ * ahead / MMA + TMA warps, registers redistributed with setmaxnreg), W2 and W3 stream through one ring.
+ * split == 0: fp16 operands; images as for nfk_nsf_pairs_fused (w2_img = two 128 x 64 K blocks, w3_img = 8
+ *   chunks of [2 K blocks][96 x 64]).
+ * split != 0: fp32-class conditioner -- every operand is an fp16 pair hi + lo (lo = fp16(v - hi)), every product
+ *   three tensor-core MMAs hi*hi + lo*hi + hi*lo with fp32 accumulation: w1_img [128 x 64] carries hi in K
+ *   columns 0..31 and lo in 32..63; w2_img = [kb0 hi][kb0 lo][kb1 hi][kb1 lo] (16 KB blocks); w3_img = per
+ *   chunk [hi 24 KB][lo 24 KB].  With NFK_ARITH_HYBRID / EXACT this is the strict-parity configuration
+ *   (z, log_det to the fp32 gate, bins = the exact search) in ONE launch per layer pass.
+ * Replaces NSF_CL.forward/inverse (nf/flows.py:227-253). */
+int nfk_nsf_pairs_fused2(const float* x, float* out, float* logdet, const void* w1_img,
+                         const void* w2_img, const void* w3_img, const float* b1, const float* b2,
+                         const float* b3, int64_t N, int mask_col, float B, int inverse,
+                         int accumulate, int arith, int split, float* dbg_params /*nullable*/,
+                         int8_t* dbg_bins /*nullable*/, void* stream);
+
 /* ---- wide conditioner path (hidden width > 128; the class default is 800, nf/flows.py:216):
  * persistent warp-specialised tcgen05 GEMM  Y = act(A W^T + b)  over operands stored in HBM as
  * *shared-memory images*: 128-row x 64-column blocks of 16-bit elements (16 KB; `fmt` = NFK_IMG_BF16 or

@@ -14,9 +14,16 @@ ROWS = 128
 HP, K1P, NF, PC, CF = 128, 64, 32, 24, 4
 
 
+# Which kernel generation runs the layer: 2 = csrc/nsf_fused2.cu (three overlapping warp sets), 1 = csrc/nsf_fused.cu.
+# The split-operand (fp32-class, precision "fp32x3") configuration exists in generation 2 only.
+GENERATION = 2 if _lib.have("nfk_nsf_pairs_fused2") else 1
+
+
 def eligible(layer) -> bool:
+    prec = getattr(layer.psi, "precision", None)
     return (layer.size == 32 and layer.dim == 2 and len(layer._mask) == 1 and layer.K == 8
-            and getattr(layer.psi, "precision", None) == "bf16" and _lib.have("nfk_nsf_pairs_fused")
+            and (prec == "bf16" or (prec == "fp32x3" and _lib.have("nfk_nsf_pairs_fused2")))
+            and _lib.have("nfk_nsf_pairs_fused")
             and hasattr(layer.psi, "network") and layer.psi.network[0].out_features <= HP
             and layer.psi.network[0].in_features == 32)
 
@@ -33,7 +40,72 @@ def _swizzle_image(mat):
     return blk[:, r, src, :].contiguous()
 
 
+def _hi_lo(w):
+    """fp32 -> (hi, lo) fp16 pair with hi + lo = w to ~22 bits (lo = fp16(w - hi))."""
+    w = w.detach().float().clamp(-65504.0, 65504.0)
+    hi = w.to(torch.float16)
+    lo = (w - hi.float()).to(torch.float16)
+    return hi, lo
+
+
+def packed_split(layer):
+    """Operand images of the split-operand (fp32-class) kernel: see nfk_nsf_pairs_fused2 in include/nfk.h."""
+    net = layer.psi.network
+    l0, l2, l4 = net[0], net[2], net[4]
+    key = (_lib.param_epoch(),) + tuple((l.weight._version, l.weight.data_ptr(), l.bias._version)
+                                        for l in (l0, l2, l4))
+    cache = getattr(layer, "_fused_split_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    dev = l0.weight.device
+    H = l0.out_features
+    f16 = torch.float16
+    h1, o1 = _hi_lo(l0.weight)
+    w1 = torch.zeros((HP, K1P), dtype=f16, device=dev)
+    w1[:H, :32] = h1                                   # K columns 0..31: hi, 32..63: lo
+    w1[:H, 32:64] = o1
+    h2, o2 = _hi_lo(l2.weight)
+    w2h = torch.zeros((HP, HP), dtype=f16, device=dev)
+    w2l = torch.zeros((HP, HP), dtype=f16, device=dev)
+    w2h[:H, :H], w2l[:H, :H] = h2, o2
+    i2h, i2l = _swizzle_image(w2h), _swizzle_image(w2l)                       # [2 K blocks, 128, 8, 8] each
+    w2 = torch.stack([i2h[0], i2l[0], i2h[1], i2l[1]]).contiguous()           # consumption order of the ring
+    h3, o3 = _hi_lo(l4.weight)
+    w3h = torch.zeros((NF, PC, HP), dtype=f16, device=dev)
+    w3l = torch.zeros((NF, PC, HP), dtype=f16, device=dev)
+    w3h[:, :23, :H], w3l[:, :23, :H] = h3.reshape(NF, 23, H), o3.reshape(NF, 23, H)
+    w3h, w3l = w3h.reshape(NF // CF, CF * PC, HP), w3l.reshape(NF // CF, CF * PC, HP)
+    w3 = torch.stack([torch.stack([_swizzle_image(w3h[c]), _swizzle_image(w3l[c])]) for c in range(NF // CF)]).contiguous()
+    b1 = torch.zeros(HP, dtype=torch.float32, device=dev)
+    b1[:H] = l0.bias.detach().float()
+    b2 = torch.zeros(HP, dtype=torch.float32, device=dev)
+    b2[:H] = l2.bias.detach().float()
+    b3 = torch.zeros((NF, PC), dtype=torch.float32, device=dev)
+    b3[:, :23] = l4.bias.detach().float().reshape(NF, 23)
+    pk = dict(w1=_swizzle_image(w1), w2=w2, w3=w3, b1=b1, b2=b2, b3=b3.reshape(-1).contiguous())
+    layer._fused_split_cache = (key, pk)
+    return pk
+
+
+def _launch(layer, pk, x, out, logdet, n, inverse, accumulate, split, dbg_p=None, dbg_b=None):
+    dev = x.device
+    if GENERATION == 2 or split:
+        call("nfk_nsf_pairs_fused2", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
+             ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), n, layer._mask[0], float(layer.B), int(bool(inverse)),
+             int(accumulate), _ops._arith(layer.arith), int(split), ptr(dbg_p), ptr(dbg_b), stream_ptr(dev))
+    else:
+        call("nfk_nsf_pairs_fused", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
+             ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), n, layer._mask[0], float(layer.B), int(bool(inverse)),
+             int(accumulate), _ops._arith(layer.arith), ptr(dbg_p), ptr(dbg_b), stream_ptr(dev))
+
+
+def _is_split(layer) -> bool:
+    return getattr(layer.psi, "precision", None) == "fp32x3"
+
+
 def packed(layer):
+    if _is_split(layer):
+        return packed_split(layer)
     net = layer.psi.network
     l0, l2, l4 = net[0], net[2], net[4]
     key = (_lib.param_epoch(),) + tuple((l.weight._version, l.weight.data_ptr(), l.bias._version)
@@ -85,9 +157,7 @@ def run_debug(layer, x, inverse):
     params = torch.empty((N, NF, PC), dtype=torch.float32, device=dev)
     bins = torch.empty((N, NF), dtype=torch.int8, device=dev)
     with torch.cuda.device(dev):
-        call("nfk_nsf_pairs_fused", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
-             ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), N, layer._mask[0], float(layer.B), int(bool(inverse)), 0,
-             _ops._arith(layer.arith), ptr(params), ptr(bins), stream_ptr(dev))
+        _launch(layer, pk, x, out, logdet, N, inverse, False, _is_split(layer), params, bins)
     return out[:n_real], logdet[:n_real], params[:n_real, :, :23].contiguous(), bins[:n_real]
 
 
@@ -106,10 +176,8 @@ def run(layer, x, inverse, logdet=None):
     if n_main:
         with torch.cuda.device(dev):
             tm = _ops.KERNEL_TIMER
-            ev = tm.start("nsf_pairs_fused", dev) if tm is not None else None
-            call("nfk_nsf_pairs_fused", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
-                 ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), n_main, layer._mask[0], float(layer.B),
-                 int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), ptr(None), ptr(None), stream_ptr(dev))
+            ev = tm.start("nsf_pairs_fused3x" if _is_split(layer) else "nsf_pairs_fused", dev) if tm is not None else None
+            _launch(layer, pk, x, out, logdet, n_main, inverse, accumulate, _is_split(layer))
             if ev is not None:
                 tm.stop(ev, dev)
     if n_main < N:
@@ -123,9 +191,7 @@ def run(layer, x, inverse, logdet=None):
         if accumulate:
             lp[:nt] = logdet[n_main:]
         with torch.cuda.device(dev):
-            call("nfk_nsf_pairs_fused", ptr(xp), ptr(op), ptr(lp), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
-                 ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), ROWS, layer._mask[0], float(layer.B),
-                 int(bool(inverse)), int(accumulate), _ops._arith(layer.arith), ptr(None), ptr(None), stream_ptr(dev))
+            _launch(layer, pk, xp, op, lp, ROWS, inverse, accumulate, _is_split(layer))
         out[n_main:] = op[:nt]
         logdet[n_main:] = lp[:nt]
     return out, logdet
