@@ -505,7 +505,7 @@ def run_native(a):
     secondary = []
     if not a.no_secondary and a.hidden == 128 and cond == "bf16" and not a.no_fused:
         specs2 = [("cfg2_h800_class_default", 800, "bf16", "fast", "tensor-pipe-bound regime (42.09 TFLOP per 2^20-row step)")]
-        if _lib.have("nfk_nsf_pairs_fused3x"):
+        if _lib.have("nfk_nsf_pairs_fused2"):
             specs2.append(("cfg2_h128_fp32_class_fused", 128, "fp32x3", "hybrid",
                            "strict parity: split-operand (fp32-class) conditioner GEMMs + HYBRID spline (exact bin search) in ONE kernel per layer pass"))
         specs2.append(("cfg2_h128_strict_fp32_unfused", 128, "fp32", "hybrid",

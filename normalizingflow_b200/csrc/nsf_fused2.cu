@@ -102,19 +102,42 @@ __device__ __forceinline__ void split_f16x2_sat(float a, float b, uint32_t& hi, 
   split_f16x2(a, b, hi, lo);
 }
 
-// 24 raw parameters of one feature held in registers: value = accumulator + bias
-struct RegParams2 {
+// tanh for the split-operand (fp32-class) configuration: MUFU.TANH carries ~2^-11 relative error, which would
+// throw away what the hi + lo operands buy; 1 - 2 / (1 + e^(2x)) on ex2.approx + rcp.approx is good to ~3e-7
+// absolute everywhere (saturates correctly: e^(2x) = inf -> 1, 0 -> -1) at two MUFU operations.
+__device__ __forceinline__ float tanh_2mufu(float x) {
+  const float t = ex2_approx(x * (2.f * LOG2E));
+  return fmaf(-2.f, rcp_approx(1.f + t), 1.f);
+}
+
+// 24 raw parameters of one feature held in registers, bias already added in place (add_bias24)
+struct RegVals {
+  static constexpr bool in_registers = true;
   const uint32_t* v;
-  const float* b;
-  __device__ __forceinline__ float operator()(int i) const { return __uint_as_float(v[i]) + b[i]; }
+  __device__ __forceinline__ float operator()(int i) const { return __uint_as_float(v[i]); }
   __device__ __forceinline__ float dyn(int base, int i) const {
     uint32_t r = v[16];
 #pragma unroll
     for (int j = 1; j < 7; ++j)
       if (i == j) r = v[16 + j];
-    return __uint_as_float(r) + b[16 + i];
+    return __uint_as_float(r);
   }
 };
+// v[0..23] += b[0..23]: six 16-byte shared-memory loads (every lane reads the same address: broadcast) and
+// twelve packed fp32x2 adds instead of 24 scalar loads + 24 scalar adds per element
+__device__ __forceinline__ void add_bias24(uint32_t* v, const float* b) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float4 bb = *reinterpret_cast<const float4*>(b + 4 * i);
+    float lo, hi;
+    unpk2(add2(pk2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), pk2(bb.x, bb.y)), lo, hi);
+    v[4 * i] = __float_as_uint(lo);
+    v[4 * i + 1] = __float_as_uint(hi);
+    unpk2(add2(pk2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), pk2(bb.z, bb.w)), lo, hi);
+    v[4 * i + 2] = __float_as_uint(lo);
+    v[4 * i + 3] = __float_as_uint(hi);
+  }
+}
 
 // Per-tile order of the MMA warp's work and of the ring pieces (both warps walk the same list):
 //   chunk 0 .. S1, [GEMM1 of the next tile], chunk S1+1 .. S2, [GEMM2 of the next tile: W2 pieces], chunk S2+1 .. 7
@@ -356,7 +379,10 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
         for (int t = 0; t < 2; ++t) {
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = tanh_approx(__uint_as_float(v[t * 8 + j]) + bias[part * 16 + t * 8 + j]);
+          for (int j = 0; j < 8; ++j) {
+            const float pre = __uint_as_float(v[t * 8 + j]) + bias[part * 16 + t * 8 + j];
+            f[j] = SPLIT ? tanh_2mufu(pre) : tanh_approx(pre);
+          }
           const int ch = (part & 3) * 2 + t;
           if (SPLIT) {
             uint4 uh, ul;
@@ -474,13 +500,13 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
         if (lane == 0) mbar_arrive(&bar_d3e[g & 1]);           // the accumulator may be overwritten
         float2* pr = reinterpret_cast<float2*>(xs + row * F2_XLD + 2 * f);
         const float2 xc = *pr;
-        const RqsOut o = rqs_element<MODE, 8, INVERSE, true, true>(RegParams2{v, sB3 + f * F2_PC},
-                                                                    a.cond_first ? xc.y : xc.x, a.c);
+        add_bias24(v, sB3 + f * F2_PC);
+        const RqsOut o = rqs_element<MODE, 8, INVERSE, true, true>(RegVals{v}, a.cond_first ? xc.y : xc.x, a.c);
         if constexpr (DBG) {
           const size_t e = ((size_t)tile * F2_ROWS + row) * F2_NF + f;
 #pragma unroll
           for (int i = 0; i < F2_PC; ++i)
-            a.dbg_params[e * F2_PC + i] = i < 23 ? __uint_as_float(v[i]) + sB3[f * F2_PC + i] : 0.f;
+            a.dbg_params[e * F2_PC + i] = i < 23 ? __uint_as_float(v[i]) : 0.f;
           a.dbg_bins[e] = (signed char)o.bin;
         }
         *pr = make_float2(a.cond_first ? xc.x : xc.y, o.y);  // (conditioning, transformed): Q5

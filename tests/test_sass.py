@@ -54,6 +54,7 @@ def test_only_sm100a_code_and_no_spills_in_the_hot_kernels():
     # (the lazy exact-bin path of the FAST spline epilogue costs one gemm_ws instantiation two spilled
     # registers on its cold side: tolerated up to 16 bytes, nothing in the fused layer kernel)
     hot = [k for k in hot if not re.search(r"nsf_pairs_fused_kernelILi\dELb[01]ELb1E", k)]      # debug-hook instantiations: tests only
+    hot += [k for k in res if re.search(r"nsf_fused2_kernelILi[12]ELb[01]ELb[01]ELb0E", k)]       # production FAST / HYBRID, both operand modes
     spilled = {k: v for k, v in res.items() if k in hot and (v["LOCAL"] or v["STACK"] > (16 if "gemm_ws_kernelILi2E" in k else 0))}
     assert not spilled, spilled
     # the fused layer kernel shares sub-partition 0 with its control warp: 5 warps -> at most 96 registers
@@ -75,6 +76,30 @@ def test_fused_layer_kernel_instruction_mix():
     mufu = _count(s, "MUFU.EX2") + _count(s, "MUFU.LG2") + _count(s, "MUFU.RCP")
     assert 43 <= mufu <= 82, mufu
     assert _count(s, "MUFU.EX2") <= 34 + 16 and _count(s, "MUFU.LG2") == 3
+
+
+FUSED2 = "_ZN3nfk17nsf_fused2_kernelILi2ELb0ELb0ELb0EEEvNS_10Fused2ArgsE"        # FAST, forward, fp16 operands, production
+FUSED2_SPLIT = "_ZN3nfk17nsf_fused2_kernelILi1ELb0ELb1ELb0EEEvNS_10Fused2ArgsE"  # HYBRID, forward, split operands
+
+
+def test_second_generation_fused_kernel():
+    """csrc/nsf_fused2.cu: warp-specialised roles with per-warpgroup register budgets (setmaxnreg), tcgen05 MMAs,
+    TMA bulk ring, TMEM loads, packed fp32x2 bias adds / knot chains, 16-byte bias loads; launch allocation of
+    80 registers and no spill in the production instantiations."""
+    res = _usage()
+    assert res[FUSED2]["REG"] == 80 and res[FUSED2]["STACK"] == 0 and res[FUSED2]["LOCAL"] == 0, res[FUSED2]
+    s = _sass(FUSED2)
+    assert _count(s, "USETMAXREG") == 3               # spline warps grow, hidden and MMA/TMA warpgroups shrink
+    assert _count(s, "UTCHMMA") >= 14                 # GEMM1 (2) + GEMM2 piece (4) + one GEMM3 chunk (8), prologue copies
+    assert _count(s, "UBLKCP") >= 4 and _count(s, "LDTM") >= 3
+    assert _count(s, "MUFU.TANH") in (16, 32)         # hidden epilogue: 16 columns per step (two call sites)
+    assert _count(s, "FADD2") >= 20 and _count(s, "FFMA2") >= 20
+    assert _count(s, "LDS.128") >= 6                  # b3 as six 16-byte broadcast loads per element
+    assert _count(s, "MUFU.LG2") == 3
+    sp = _sass(FUSED2_SPLIT)
+    assert _count(sp, "MUFU.TANH") == 0               # fp32-class tanh: ex2 + rcp
+    assert _count(sp, "UTCHMMA") >= 3 * 14 - 4        # three MMAs per product (hi*hi + lo*hi + hi*lo)
+    assert "F2FP" in sp and "HADD2.F32" in sp         # hi / lo operand split in the epilogues
 
 
 def test_standalone_pairs_kernel_uses_tma_ring_and_packed_math():

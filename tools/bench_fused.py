@@ -12,11 +12,12 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--hidden", type=int, default=128)
     ap.add_argument("--modes", nargs="*", default=["hybrid", "fast", "exact"])
+    ap.add_argument("--split", action="store_true", help="split-operand (fp32-class) kernel: conditioner precision fp32x3")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     layer = NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=a.hidden, mask=[1])
-    layer.psi.precision = "bf16"
+    layer.psi.precision = "fp32x3" if a.split else "bf16"
     layer = layer.to(dev)
     x = torch.randn(a.rows, 64, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
     ld = torch.zeros(a.rows, device=dev)
