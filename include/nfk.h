@@ -132,6 +132,13 @@ int nfk_planar_prepare(const float* w, const float* u, float* uhat, float* wuhat
 int nfk_planar_stack(const float* x, const float* w, const float* uhat, const float* wuhat,
                      const float* b, float* out, float* logdet, int64_t N, int d, int L,
                      int accumulate, void* stream);
+/* The same stack at the HBM rate for d = 128, L <= 32 (csrc/planar_mma.cu): the stack is rewritten as two
+ * small dense products around a per-row scalar recurrence over the Gram matrix gram[l][m] = w_l . uhat_m
+ * ([L, L], from nfk_planar_gram), products on the tensor cores with fp16 hi + lo operand pairs (fp32-class). */
+int nfk_planar_gram(const float* w, const float* uhat, float* gram, int d, int L, void* stream);
+int nfk_planar_stack_mma(const float* x, const float* w, const float* uhat, const float* gram,
+                         const float* b, float* out, float* logdet, int64_t N, int d, int L,
+                         int accumulate, void* stream);
 /* backward: recomputes the forward layer by layer; grad_w/grad_uhat [L,d], grad_b/grad_wuhat
  * [L] are ACCUMULATED with atomics into zero-initialised buffers (the chain from uhat, wuhat to
  * u, w is parameter-sized and stays in the host wrapper). */

@@ -47,6 +47,8 @@ SIGNATURES = {
                                             c_int, _P, _P, c_int64, c_int, c_int, _P]),
     "nfk_planar_prepare": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
     "nfk_planar_stack": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "nfk_planar_gram": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "nfk_planar_stack_mma": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "nfk_planar_stack_bwd": (c_int, [_P] * 12 + [c_int64, c_int, c_int, _P]),
     "nfk_rqs_coupling_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P]),
     "nfk_radial_sumsq": (c_int, [_P, _P, _P, c_int64, c_int, _P]),

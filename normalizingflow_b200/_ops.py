@@ -334,14 +334,31 @@ def planar_stack(x, w, u, b, logdet=None):
     L, d = w.shape
     N = x.shape[0]
     uhat, wuhat = planar_prepare(w, u)
-    out = torch.empty_like(x)
     accumulate = logdet is not None
     if not accumulate:
         logdet = torch.empty((N,), dtype=torch.float32, device=dev)
+    if d == 128 and PLANAR_MMA and _lib.have("nfk_planar_stack_mma") and x.data_ptr() % 8 == 0:
+        # Gram-matrix form on the tensor cores (csrc/planar_mma.cu), 32 layers per launch
+        cur = x
+        with torch.cuda.device(dev):
+            for l0 in range(0, L, 32):
+                l1 = min(L, l0 + 32)
+                wl, ul, bl = w[l0:l1].contiguous(), uhat[l0:l1].contiguous(), b[l0:l1].contiguous()
+                gram = torch.empty((l1 - l0, l1 - l0), dtype=torch.float32, device=dev)
+                call("nfk_planar_gram", ptr(wl), ptr(ul), ptr(gram), d, l1 - l0, stream_ptr(dev))
+                out = torch.empty_like(x)
+                call("nfk_planar_stack_mma", ptr(cur), ptr(wl), ptr(ul), ptr(gram), ptr(bl), ptr(out), ptr(logdet), N, d,
+                     l1 - l0, int(accumulate or l0 > 0), stream_ptr(dev))
+                cur = out
+        return cur, logdet
+    out = torch.empty_like(x)
     with torch.cuda.device(dev):
         call("nfk_planar_stack", ptr(x), ptr(w), ptr(uhat), ptr(wuhat), ptr(b), ptr(out), ptr(logdet), N, d, L,
              int(accumulate), stream_ptr(dev))
     return out, logdet
+
+
+PLANAR_MMA = True        # False: the per-layer register-resident kernel for every shape (cross-check)
 
 
 def radial(x, x0, log_alpha, beta, per_sample=False, logdet=None):

@@ -358,3 +358,38 @@ def test_bf16_fcnn_backward_runs_on_the_tensor_core_kernels():
             scale = float(c.abs().max()) + 1e-12
             assert float((a - c).abs().max()) <= 2e-2 * scale, (n_in, H, n_out, float((a - c).abs().max()) / scale)
             assert float((a - b).abs().max()) <= 2e-2 * scale
+
+
+@pytest.mark.parametrize("L", [1, 5, 32, 40])
+@pytest.mark.parametrize("N", [1, 17, 1000])
+def test_planar_stack_gram_form_matches_the_sequential_reference(L, N):
+    """d = 128 stacks run in the Gram-matrix form on the tensor cores (csrc/planar_mma.cu; 32 layers per launch,
+    fp16 hi + lo operands): against the oracle's layer-by-layer chain (nf/flows_1.py:42-60) in fp32 and fp64, and
+    against the per-layer register kernel."""
+    ops, _, _, _ = _mods()
+    from oracle import nf_oracle as O
+    gen = torch.Generator().manual_seed(100 * L + N)
+    d = 128
+    w = (torch.rand(L, d, generator=gen) * 2 - 1) / d ** 0.5 * 3.0          # 3x the default init scale
+    u = (torch.rand(L, d, generator=gen) * 2 - 1) / d ** 0.5 * 3.0
+    b = (torch.rand(L, generator=gen) * 2 - 1)
+    x = torch.randn(N, d, generator=gen) * 1.5
+    z32, ld32 = x, torch.zeros(N)
+    z64, ld64 = x.double(), torch.zeros(N, dtype=torch.float64)
+    for l in range(L):
+        z32, l32 = O.planar(z32, w[l], u[l], b[l:l + 1])
+        ld32 = ld32 + l32
+        z64, l64 = O.planar(z64, w[l].double(), u[l].double(), b[l:l + 1].double())
+        ld64 = ld64 + l64
+    z, ld = ops.planar_stack(x.cuda(), w.cuda(), u.cuda(), b.cuda())
+    assert rel_err(z, z64) <= 1e-5 and rel_err(ld, ld64) <= 1e-5, (rel_err(z, z64), rel_err(ld, ld64))
+    assert rel_err(z, z32) <= 1e-5 and rel_err(ld, ld32) <= 1e-5, (rel_err(z, z32), rel_err(ld, ld32))
+    acc = torch.full((N,), 0.5, device="cuda")
+    z2, ld2 = ops.planar_stack(x.cuda(), w.cuda(), u.cuda(), b.cuda(), logdet=acc)
+    assert torch.equal(z2, z) and rel_err(ld2, ld64 + 0.5) <= 1e-5
+    ops.PLANAR_MMA = False
+    try:
+        zo, ldo = ops.planar_stack(x.cuda(), w.cuda(), u.cuda(), b.cuda())
+    finally:
+        ops.PLANAR_MMA = True
+    assert rel_err(z, zo.cpu()) <= 1e-5 and rel_err(ld, ldo.cpu()) <= 1e-5
