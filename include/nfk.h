@@ -158,6 +158,19 @@ int nfk_radial(const float* x, const float* x0, const float* log_alpha, const fl
                const float* sumsq, float* out, float* logdet, int64_t N, int d, int per_sample,
                int accumulate, void* stream);
 
+/* A run of L PER-SAMPLE radial layers in one pass (csrc/radial_stack.cu): x0 [L,d], log_alpha [L], beta [L];
+ * out [N,d], logdet [N] (+)= sum over the layers.  d in {32, 64, 128, 256}. */
+int nfk_radial_stack(const float* x, const float* x0, const float* log_alpha, const float* beta,
+                     float* out, float* logdet, int64_t N, int d, int L, int accumulate, void* stream);
+/* Batch-global mode, one fused pass: when x0 != NULL applies the layer (out = x + beta h (x - x0) with
+ * h = 1 / (alpha + sqrt(sumsq[0])), logdet[0] (+)= the layer's single log-det) and, when x0_next != NULL,
+ * accumulates sum (value - x0_next)^2 of what it just wrote (of x itself when x0 == NULL) into the zeroed
+ * device scalar sumsq_next -- the second pass of layer l is the first pass of layer l+1.  Across ranks the
+ * caller all-reduces sumsq_next between launches.  d must be a multiple of 4 that divides 1024. */
+int nfk_radial_global(const float* x, const float* x0, const float* log_alpha, const float* beta,
+                      const float* sumsq, const float* x0_next, float* sumsq_next, float* out,
+                      float* logdet, int64_t N, int d, int accumulate, void* stream);
+
 /* backward of the radial layer: grad_x [N,d]; grad_x0 [d], grad_log_alpha [1], grad_beta [1] are
  * ACCUMULATED with atomics into zero-initialised buffers.  Batch-global mode needs sumsq (as the
  * forward) and dot = sum(grad_out * (x - x0)) from nfk_radial_dot (all-reduced when sharded). */

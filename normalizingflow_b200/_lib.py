@@ -53,6 +53,8 @@ SIGNATURES = {
     "nfk_rqs_coupling_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P]),
     "nfk_radial_sumsq": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
     "nfk_radial": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "nfk_radial_stack": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "nfk_radial_global": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "nfk_radial_dot": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
     "nfk_radial_bwd": (c_int, [_P] * 12 + [c_int64, c_int, c_int, _P]),
     "nfk_gauss_logprob": (c_int, [_P, _P, c_float, _P, c_int64, c_int, c_float, _P]),

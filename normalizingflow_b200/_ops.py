@@ -384,6 +384,49 @@ def radial(x, x0, log_alpha, beta, per_sample=False, logdet=None):
     return out, logdet
 
 
+def radial_stack(x, x0, log_alpha, beta, per_sample, logdet=None):
+    """A run of L radial layers (x0 [L,d], log_alpha [L], beta [L]) without autograd.
+    per_sample: ONE pass over x for the whole run (row kept in registers).  Batch-global (the reference's
+    Frobenius norm over the whole batch, quirk Q9): one read + one write per layer -- the pass that applies layer l
+    also accumulates the sum of squares layer l+1 needs (all-reduced across ranks between launches).
+    Returns (z, logdet): logdet [N] per sample, [1] in the batch-global mode."""
+    dev = require_cuda(x, x0, log_alpha, beta, logdet)
+    x, x0, log_alpha, beta = f32c(x), f32c(x0), f32c(log_alpha.reshape(-1)), f32c(beta.reshape(-1))
+    N, d = x.shape
+    L = x0.shape[0]
+    accumulate = logdet is not None
+    if not accumulate:
+        logdet = torch.empty((N if per_sample else 1,), dtype=torch.float32, device=dev)
+    if per_sample:
+        out = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            call("nfk_radial_stack", ptr(x), ptr(x0), ptr(log_alpha), ptr(beta), ptr(out), ptr(logdet), N, d, L,
+                 int(accumulate), stream_ptr(dev))
+        return out, logdet
+    multi = torch.distributed.is_available() and torch.distributed.is_initialized()
+    sums = torch.zeros((L + 1,), dtype=torch.float32, device=dev)
+    bufs = [torch.empty_like(x), torch.empty_like(x) if L > 1 else None]
+    with torch.cuda.device(dev):
+        call("nfk_radial_global", ptr(x), ptr(None), ptr(None), ptr(None), ptr(None), ptr(x0[0]), ptr(sums[0:1]),
+             ptr(None), ptr(None), N, d, 0, stream_ptr(dev))
+        cur = x
+        for l in range(L):
+            if multi:
+                torch.distributed.all_reduce(sums[l:l + 1])
+            out = bufs[l & 1]
+            nxt = x0[l + 1] if l + 1 < L else None
+            call("nfk_radial_global", ptr(cur), ptr(x0[l]), ptr(log_alpha[l:l + 1]), ptr(beta[l:l + 1]), ptr(sums[l:l + 1]),
+                 ptr(nxt), ptr(sums[l + 1:l + 2]), ptr(out), ptr(logdet), N, d, int(accumulate or l > 0), stream_ptr(dev))
+            cur = out
+    return cur, logdet
+
+
+def radial_stack_ok(d: int, per_sample: bool) -> bool:
+    if per_sample:
+        return _lib.have("nfk_radial_stack") and d in (32, 64, 128, 256)
+    return _lib.have("nfk_radial_global") and d % 4 == 0 and 1024 % d == 0
+
+
 # --------------------------------------------------------------------------------------
 # log-prob reduction, gather, leapfrog
 # --------------------------------------------------------------------------------------

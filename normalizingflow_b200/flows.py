@@ -20,7 +20,7 @@ import torch.nn.init as init
 
 from . import _ops
 
-__all__ = ["FCNN", "RealNVP", "NSF_AR", "NSF_CL", "Planar", "Radial", "PlanarStack"]
+__all__ = ["FCNN", "RealNVP", "NSF_AR", "NSF_CL", "Planar", "Radial", "PlanarStack", "RadialStack"]
 
 
 class FCNN(nn.Module):
@@ -332,3 +332,29 @@ class Radial(nn.Module):
 
     def inverse(self, z):
         raise NotImplementedError("Radial flow has no inverse in the reference.")
+
+
+class RadialStack(nn.Module):
+    """Fuses a run of consecutive ``Radial`` layers of the same mode (built by NormalizingFlowModel; parameters
+    stay owned by the layers).  Without autograd: per-sample runs are ONE pass over the batch, batch-global
+    runs (the reference's behaviour) one read + one write per layer; with autograd each layer runs through its
+    own ``RadialFn``."""
+
+    def __init__(self, layers):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+        self.per_sample = bool(layers[0].per_sample)
+
+    def forward(self, x):
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        d = x.shape[1]
+        if needs_grad or not _ops.radial_stack_ok(d, self.per_sample) or x.dtype != torch.float32:
+            ld = None
+            for l in self.layers:
+                x, l_ld = l.forward(x)
+                ld = l_ld if ld is None else ld + l_ld
+            return x, ld
+        x0 = torch.stack([l.x0.detach() for l in self.layers])
+        la = torch.cat([l.log_alpha.detach().reshape(1) for l in self.layers])
+        be = torch.cat([l.beta.detach().reshape(1) for l in self.layers])
+        return _ops.radial_stack(x, x0, la, be, self.per_sample)

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, _ops
-from .flows import Planar, PlanarStack
+from .flows import Planar, PlanarStack, Radial, RadialStack
 
 
 class GaussianPrior:
@@ -111,19 +111,28 @@ class NormalizingFlowModel(nn.Module):
         lp = self.prior.log_prob(z)
         return lp if add is None else lp + add_sign * add
 
-    # runs of consecutive Planar layers collapse into one fused launch
+    # runs of consecutive Planar layers, and of consecutive Radial layers of one mode, collapse into fused launches
     def _forward_plan(self):
         plan, run = [], []
+
+        def flush():
+            if run:
+                if len(run) == 1:
+                    plan.append(run[0])
+                else:
+                    plan.append(PlanarStack(list(run)) if type(run[0]) is Planar else RadialStack(list(run)))
+                run.clear()
         for f in self.flows:
-            if self.fuse_planar and type(f) is Planar:
+            fusable = self.fuse_planar and type(f) in (Planar, Radial)
+            if fusable and run and (type(run[0]) is not type(f)
+                                    or (type(f) is Radial and bool(f.per_sample) != bool(run[0].per_sample))):
+                flush()
+            if fusable:
                 run.append(f)
                 continue
-            if run:
-                plan.append(PlanarStack(run) if len(run) > 1 else run[0])
-                run = []
+            flush()
             plan.append(f)
-        if run:
-            plan.append(PlanarStack(run) if len(run) > 1 else run[0])
+        flush()
         return plan
 
     def forward(self, x):

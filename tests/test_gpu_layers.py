@@ -393,3 +393,34 @@ def test_planar_stack_gram_form_matches_the_sequential_reference(L, N):
     finally:
         ops.PLANAR_MMA = True
     assert rel_err(z, zo.cpu()) <= 1e-5 and rel_err(ld, ldo.cpu()) <= 1e-5
+
+
+@pytest.mark.parametrize("per_sample", [True, False], ids=["per_sample", "batch_global"])
+@pytest.mark.parametrize("d,L,N", [(128, 32, 1000), (64, 3, 17), (32, 1, 1), (256, 5, 300)])
+def test_radial_stack_matches_the_layer_by_layer_reference(per_sample, d, L, N):
+    """Fused runs of radial layers (csrc/radial_stack.cu) against the oracle's layer-by-layer chain
+    (nf/flows_1.py:85-97: batch-global Frobenius norm, quirk Q9, and the per-sample variant) and against the
+    per-layer kernels; through NormalizingFlowModel, which builds the fused run."""
+    _, _, flows, models = _mods()
+    from oracle import nf_oracle as O
+    dev = torch.device("cuda")
+    torch.manual_seed(7 * d + L)
+    layers = [flows.Radial(d, per_sample=per_sample) for _ in range(L)]
+    m = models.NormalizingFlowModel(models.GaussianPrior(d, device=dev), layers, device=dev).to(dev)
+    x = torch.randn(N, d, generator=torch.Generator().manual_seed(N)) * 1.3
+    z64 = x.double()
+    ld64 = torch.zeros(N if per_sample else 1, dtype=torch.float64)
+    for l in layers:
+        z64, l64 = O.radial(z64, l.x0.detach().cpu().double(), l.log_alpha.detach().cpu().double(),
+                            l.beta.detach().cpu().double(), per_sample=per_sample)
+        ld64 = ld64 + l64
+    with torch.no_grad():
+        plan = m._forward_plan()
+        assert (len(plan) == 1 and type(plan[0]).__name__ == "RadialStack") or L == 1
+        z, plp, ld = m.forward(x.to(dev))
+        m.fuse_planar = False
+        z1, _, ld1 = m.forward(x.to(dev))                       # per-layer kernels
+    assert rel_err(z, z64) <= 1e-5, rel_err(z, z64)
+    ref_ld = ld64 if per_sample else ld64.expand(N)
+    assert rel_err(ld, ref_ld) <= 2e-5, rel_err(ld, ref_ld)
+    assert rel_err(z, z1.cpu()) <= 1e-5 and rel_err(ld, ld1.cpu()) <= 2e-5

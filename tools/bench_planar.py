@@ -38,3 +38,18 @@ for mma in (True, False):
                       "frac_of_hbm_stack_fused_floor": (2 * d * 4 + 4) * N / (ms * 1e-3) / 1e9 / hbm,
                       "GBps_vs_per_layer_bytes": L * (2 * d * 4 + 8) * N / (ms * 1e-3) / 1e9}))
 _ops.PLANAR_MMA = True
+
+# ---- radial: per-layer launches vs the fused runs
+from normalizingflow_b200 import flows, models
+for per_sample in (True, False):
+    layers = [flows.Radial(d, per_sample=per_sample) for _ in range(L)]
+    m = models.NormalizingFlowModel(models.GaussianPrior(d, device=dev), layers, device=dev).to(dev)
+    for fuse in (True, False):
+        m.fuse_planar = fuse
+        with torch.no_grad():
+            ms = timeit(lambda: m.forward(x), iters=5)
+        passes = (1 if (fuse and per_sample) else (L + 0.5 if fuse else (L if per_sample else 1.5 * L)))
+        print(json.dumps({"kernel": f"32 x Radial(128, per_sample={per_sample}) " + ("fused run" if fuse else "per-layer launches"),
+                          "ms": ms, "ms_per_layer": ms / L, "samples_per_s": N / ms * 1e3,
+                          "frac_of_hbm_own_traffic": passes * 2 * d * 4 * N / (ms * 1e-3) / 1e9 / hbm,
+                          "GBps_vs_per_layer_bytes": L * (2 * d * 4 + 8) * N / (ms * 1e-3) / 1e9}))
