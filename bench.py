@@ -228,14 +228,25 @@ def build_flow(hidden, cond, arith, fused, dev, sd):
     return model.to(dev)
 
 
-def time_device(model, x, z, steps, warmup, dev, world, local, rank, with_clocks=True):
-    """(ms per step [max over ranks], per-kernel CUDA-event sums, libnfk launches, clocks) of `steps` fwd+inv passes."""
+def time_device(model, x, z, steps, warmup, dev, world, local, rank, with_clocks=True, graphed=False):
+    """(ms per step [max over ranks], per-kernel CUDA-event sums, libnfk launches, clocks) of `steps` fwd+inv passes.
+    graphed: the step is captured once with graphs.GraphedCallable (public API) and replayed as ONE CUDA graph -- the
+    per-kernel event timer is then empty, the launch count is what one replay contains."""
     from normalizingflow_b200 import _lib, _ops
 
-    def step():
+    def eager_step():
         with torch.no_grad():
-            model.forward(x)
-            model.inverse(z)
+            a = model.forward(x)
+            b = model.inverse(z)
+        return a + b
+    step, per_replay = eager_step, None
+    if graphed:
+        from normalizingflow_b200.graphs import GraphedCallable
+        l0 = _lib.launch_count()
+        eager_step()
+        per_replay = _lib.launch_count() - l0
+        g = GraphedCallable(lambda xx, zz: eager_step(), x, z)
+        step = g.graph.replay
     for _ in range(max(3, warmup)):
         step()
     _barrier(world)
@@ -251,7 +262,7 @@ def time_device(model, x, z, steps, warmup, dev, world, local, rank, with_clocks
     e1.record()
     _barrier(world)
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
+    launches = (_lib.launch_count() - launches0) if per_replay is None else per_replay * steps
     _ops.KERNEL_TIMER = None
     ksum = timer.summary()
     clk = clocks.stop() if clocks is not None else None
@@ -371,11 +382,11 @@ def train_block(a, sd, dev, world, rank):
             ev[2].record()
         opt.step()
         return nb
-    for _ in range(2):
+    for _ in range(4):
         step()
     _barrier(world)
     l0 = _lib.launch_count()
-    t_ar, nbytes, steps = 0.0, 0, 3
+    t_ar, nbytes, steps = 0.0, 0, 5
     ev[0].record()
     for _ in range(steps):
         nbytes = step(True)
@@ -383,8 +394,19 @@ def train_block(a, sd, dev, world, rank):
         torch.cuda.synchronize()
         t_ar += ev[1].elapsed_time(ev[2])
     ms = ev[0].elapsed_time(ev[3]) / steps
-    ms, ar = max_over_ranks([ms, t_ar / steps], dev, world)
     launches = (_lib.launch_count() - l0) / steps
+    # the all-reduce alone: ranks aligned by a barrier, ten back-to-back reductions of the same bucket (inside a
+    # step the measured interval also contains the wait for the slowest rank to reach the collective)
+    ar_only = 0.0
+    if world > 1:
+        _barrier(world)
+        ev[1].record()
+        for _ in range(10):
+            bucket.allreduce()
+        ev[2].record()
+        torch.cuda.synchronize()
+        ar_only = ev[1].elapsed_time(ev[2]) / 10
+    ms, ar, ar_only = max_over_ranks([ms, t_ar / steps, ar_only], dev, world)
     flat = torch.cat([p.detach().reshape(-1) for p in params])
     ident, rel = True, None
     if world > 1:
@@ -408,7 +430,9 @@ def train_block(a, sd, dev, world, rank):
             rel = float((g_dist - g_one).abs().max() / g_one.abs().max().clamp_min(1e-30))
     out = {"what": f"forward-KL training step of the cfg-2 flow (H={a.hidden}, bf16 tensor-core forward+backward), {rows} rows/GPU, "
                    "Adam, one in-place NCCL all-reduce of the flat fp32 gradient bucket per step",
-           "ms_per_step": ms, "train_samples_per_s": world * rows / (ms * 1e-3), "allreduce_ms": ar,
+           "ms_per_step": ms, "train_samples_per_s": world * rows / (ms * 1e-3),
+           "allreduce_ms_in_step_incl_rank_skew": ar, "allreduce_ms_alone": ar_only,
+           "allreduce_GBps_alone": (nbytes / (ar_only * 1e-3) / 1e9) if ar_only else None,
            "allreduce_bytes": nbytes, "grad_elements": int(flat.numel()), "libnfk_launches_per_step": launches,
            "replicas_bit_identical_after_steps": ident, "sharded_vs_single_process_gradient_rel_err": rel}
     del model, opt, bucket, x
@@ -486,7 +510,11 @@ def run_native(a):
     if not strong and world > 1 and not a.no_strong:
         r0, r1 = shard_rows(a.batch, rank, world)
         xs_, zs_ = x[: r1 - r0], z[: r1 - r0]
-        s_ms, s_ksum, _, _, s_tot = time_device(model, xs_, zs_, a.steps, a.warmup, dev, world, local, rank, with_clocks=False)
+        # the per-GPU share is small (2^20 / N rows: ~90 us per layer launch at N = 8), so the step is replayed as one
+        # CUDA graph (graphs.GraphedCallable), as the host-buffer pipeline does for its chunks
+        s_ms, _, _, _, s_tot = time_device(model, xs_, zs_, a.steps, a.warmup, dev, world, local, rank, with_clocks=False,
+                                           graphed=True)
+        _, s_ksum, _, _, _ = time_device(model, xs_, zs_, 3, 1, dev, world, local, rank, with_clocks=False)
         kn, (nl, kms) = max(s_ksum.items(), key=lambda kv: kv[1][1])
         strong_blk = {"scaling": "strong", "global_batch": a.batch, "rows_per_gpu": r1 - r0, "ms_per_step": s_ms,
                       "value": a.batch / (s_ms * 1e-3), "unit": UNIT,
@@ -494,6 +522,8 @@ def run_native(a):
                       "efficiency": (a.batch / (s_ms * 1e-3)) / value,
                       "one_gpu_value_same_run": value / world,
                       "dominant_kernel_avg_launch_ms": kms / max(1, nl),
+                      "how": "one CUDA-graph replay per step (16 layer launches + log-prob reduction), consecutive layer "
+                             "kernels chained by programmatic dependent launch",
                       "note": "every rank runs its contiguous 1/N of the 2^20-row batch, no data-path collective; "
                               "one_gpu_value is this run's weak-scaling per-GPU rate on the full 2^20 rows"}
         if not a.no_e2e:

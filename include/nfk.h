@@ -241,6 +241,10 @@ int nfk_nsf_pairs_fused(const float* x, float* out, float* logdet, const void* w
  *   chunk [hi 24 KB][lo 24 KB].  With NFK_ARITH_HYBRID / EXACT this is the strict-parity configuration
  *   (z, log_det to the fp32 gate, bins = the exact search) in ONE launch per layer pass.
  * Replaces NSF_CL.forward/inverse (nf/flows.py:227-253). */
+/* consecutive launches of nfk_nsf_pairs_fused2 on one stream overlap their prologue with the previous launch's tail
+ * (programmatic dependent launch; the kernel waits for its predecessor before its first global access).
+ * on = 0 restores plain stream order.  Process-global; for tuning and tests. */
+int nfk_set_fused2_pdl(int on);
 int nfk_nsf_pairs_fused2(const float* x, float* out, float* logdet, const void* w1_img,
                          const void* w2_img, const void* w3_img, const float* b1, const float* b2,
                          const float* b3, int64_t N, int mask_col, float B, int inverse,

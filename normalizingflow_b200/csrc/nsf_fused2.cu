@@ -198,6 +198,12 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
     mbar_init(bar_d12, 1);
     fence_barrier_init();
   }
+  // Programmatic dependent launch: this grid may have been scheduled while the previous kernel of the stream
+  // (the previous layer) was still draining -- its CTAs start on each SM as soon as that SM's CTA exits, with
+  // barrier init and TMEM allocation already done.  Nothing in global memory is touched before this wait; the
+  // trigger lets the NEXT layer's grid do the same behind this one.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
   for (int i = tid; i < F2_HP; i += F2_THREADS) {
     sB1[i] = a.b1[i];
     sB2[i] = a.b2[i];
@@ -543,6 +549,8 @@ static_assert(F2_SMEM <= 227 * 1024, "fused layer kernel (v2) exceeds the 227 KB
 
 RqsConsts make_rqs_consts(int K, float B);   // rqs_coupling.cu
 
+static int g_fused2_pdl = 1;      // programmatic dependent launch of consecutive layers (nfk_set_fused2_pdl; tuning / tests)
+
 template <int MODE, bool INVERSE, bool SPLIT, bool DBG>
 static int launch_fused2(const Fused2Args& a, cudaStream_t st) {
   auto kern = nsf_fused2_kernel<MODE, INVERSE, SPLIT, DBG>;
@@ -553,7 +561,21 @@ static int launch_fused2(const Fused2Args& a, cudaStream_t st) {
   }
   const long long cap = sm_count();
   const long long grid = a.n_tiles < cap ? a.n_tiles : cap;
-  kern<<<(unsigned)grid, F2_THREADS, F2_SMEM, st>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(F2_THREADS);
+  cfg.dynamicSmemBytes = F2_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see griddepcontrol.wait in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = g_fused2_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, a);
+  if (e != cudaSuccess) {
+    set_error("nsf_fused2: launch failed: %s", cudaGetErrorString(e));
+    return NFK_ECUDA;
+  }
   count_launch();
   return check_launch("nsf_fused2");
 }
@@ -570,6 +592,11 @@ static int dispatch_fused2(const Fused2Args& a, int arith, bool inv, cudaStream_
 }  // namespace nfk
 
 using namespace nfk;
+
+extern "C" int nfk_set_fused2_pdl(int on) {
+  g_fused2_pdl = on ? 1 : 0;
+  return NFK_OK;
+}
 
 extern "C" int nfk_nsf_pairs_fused2(const float* x, float* out, float* logdet, const void* w1_img, const void* w2_img,
                                     const void* w3_img, const float* b1, const float* b2, const float* b3, int64_t N,
