@@ -493,7 +493,7 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
       float lad_acc = 0.f;
 #pragma unroll 1
       for (int c = 0; c < F2_NCHUNK; ++c, ++g) {
-        mbar_wait(&bar_d3f[g & 1], (g >> 1) & 1);
+        mbar_wait_idle(&bar_d3f[g & 1], (g >> 1) & 1, 200);   // suspended probe: a waiting warp leaves the issue port to the other three
         tc_fence_after();
         const int f = c * F2_CF + slice;
         uint32_t v[24];
