@@ -251,6 +251,22 @@ int nfk_nsf_pairs_fused2(const float* x, float* out, float* logdet, const void* 
                          int accumulate, int arith, int split, float* dbg_params /*nullable*/,
                          int8_t* dbg_bins /*nullable*/, void* stream);
 
+/* Gradient of one fused layer w.r.t. its input in ONE launch (csrc/nsf_fused_bwd.cu; hidden <= 128, size 32, dim 2,
+ * K 8): recomputes the conditioner with the forward kernel's fp16 operands (same parameters and bins, bit for bit),
+ * runs the spline adjoint per element in registers, the three dgrad GEMMs (bf16 operands) and the tanh backward on
+ * chip.  x, grad_out, grad_x [N, 64] (grad_out in the layer's OUTPUT column order: conditioning, transformed);
+ * grad_logdet [N] or NULL (grad_logdet_const for every row: 1 for log-prob gradients).  w1/w2/w3_img, b1..b3 as for
+ * nfk_nsf_pairs_fused2 (split = 0); transposed bf16 images: w3t_img [4][3][128 x 64] (pair of chunks p, K block:
+ * n = hidden unit, k = 24-per-feature padded parameter index within the pair), w2t_img [2][128 x 64] (n = input unit,
+ * k = output unit), w1t_img [2][32 x 64] (n = conditioning feature, k = hidden unit), all K-major SWIZZLE_128B.
+ * Replaces autograd through NSF_CL.forward / inverse (nf/flows.py:227-253) for dL/dx, as the flow-preconditioned HMC
+ * force evaluation needs it (nf/hmc.py:34-41, applications/src/systems.py:308-311). */
+int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, const float* grad_logdet,
+                            float grad_logdet_const, float* grad_x, const void* w1_img, const void* w2_img,
+                            const void* w3_img, const void* w3t_img, const void* w2t_img,
+                            const void* w1t_img, const float* b1, const float* b2, const float* b3,
+                            int64_t N, int mask_col, float B, int inverse, void* stream);
+
 /* ---- wide conditioner path (hidden width > 128; the class default is 800, nf/flows.py:216):
  * persistent warp-specialised tcgen05 GEMM  Y = act(A W^T + b)  over operands stored in HBM as
  * *shared-memory images*: 128-row x 64-column blocks of 16-bit elements (16 KB; `fmt` = NFK_IMG_BF16 or

@@ -195,3 +195,89 @@ def run(layer, x, inverse, logdet=None):
         out[n_main:] = op[:nt]
         logdet[n_main:] = lp[:nt]
     return out, logdet
+
+
+# ---------------------------------------------------------------------------------------------
+# dL/dx of a fused layer in one launch (csrc/nsf_fused_bwd.cu): the HMC force path for hidden <= 128
+# ---------------------------------------------------------------------------------------------
+def bwd_eligible(layer) -> bool:
+    return (_lib.have("nfk_nsf_pairs_fused_bwd") and GENERATION == 2 and eligible(layer)
+            and getattr(layer.psi, "precision", None) == "bf16")
+
+
+def packed_bwd(layer):
+    """Transposed bf16 dgrad operands (W3^T per pair of chunks, W2^T, W1^T) in the K-major SWIZZLE_128B image layout."""
+    net = layer.psi.network
+    l0, l2, l4 = net[0], net[2], net[4]
+    key = (_lib.param_epoch(),) + tuple((l.weight._version, l.weight.data_ptr()) for l in (l0, l2, l4))
+    cache = getattr(layer, "_fused_bwd_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    dev = l0.weight.device
+    H = l0.out_features
+    bf = torch.bfloat16
+    w3p = torch.zeros((NF, PC, HP), dtype=bf, device=dev)
+    w3p[:, :23, :H] = l4.weight.detach().to(bf).reshape(NF, 23, H)
+    w3t = torch.stack([_swizzle_image(w3p[8 * p:8 * p + 8].reshape(8 * PC, HP).t().contiguous())
+                       for p in range(NF // 8)]).contiguous()                    # [4, 3, 128, 8, 8]
+    w2p = torch.zeros((HP, HP), dtype=bf, device=dev)
+    w2p[:H, :H] = l2.weight.detach().to(bf)
+    w2t = _swizzle_image(w2p.t().contiguous())                                      # [2, 128, 8, 8]
+    w1p = torch.zeros((HP, 32), dtype=bf, device=dev)
+    w1p[:H, :] = l0.weight.detach().to(bf)
+    w1t = _swizzle_image(w1p.t().contiguous())                                      # [2, 32, 8, 8]
+    pk = dict(w3t=w3t, w2t=w2t, w1t=w1t)
+    layer._fused_bwd_cache = (key, pk)
+    return pk
+
+
+def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=False):
+    """dL/dx [N, 64] of one bwd_eligible layer from the layer input x, dL/d(out) and dL/d(log_det) (a per-row tensor, or a
+    constant for every row).  A partial last tile is zero-padded."""
+    dev = require_cuda(x, g_out, g_logdet)
+    x, g_out = f32c(x), f32c(g_out)
+    N = x.shape[0]
+    pk, pb = packed(layer), packed_bwd(layer)
+    n_pad = (N + ROWS - 1) // ROWS * ROWS
+    if n_pad != N:
+        xp = torch.zeros((n_pad, 64), dtype=torch.float32, device=dev)
+        xp[:N] = x
+        gp = torch.zeros((n_pad, 64), dtype=torch.float32, device=dev)
+        gp[:N] = g_out
+        x, g_out = xp, gp
+        if g_logdet is not None:
+            glp = torch.zeros((n_pad,), dtype=torch.float32, device=dev)
+            glp[:N] = g_logdet
+            g_logdet = glp
+    g_in = torch.empty((n_pad, 64), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        tm = _ops.KERNEL_TIMER
+        ev = tm.start("nsf_pairs_fused_bwd", dev) if tm is not None else None
+        call("nfk_nsf_pairs_fused_bwd", ptr(x), ptr(g_out), ptr(f32c(g_logdet)) if g_logdet is not None else ptr(None),
+             float(g_logdet_const), ptr(g_in), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]), ptr(pb["w3t"]), ptr(pb["w2t"]),
+             ptr(pb["w1t"]), ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), n_pad, layer._mask[0], float(layer.B),
+             int(bool(inverse)), stream_ptr(dev))
+        if ev is not None:
+            tm.stop(ev, dev)
+    return g_in[:N]
+
+
+def flow_logp_and_grad(model, x):
+    """log p(x) [N] and d log p / dx [N, d] through a flow whose layers are all bwd_eligible, under an isotropic Gaussian
+    prior: 8 forward launches (keeping each layer's input) + 8 backward launches + the log-prob reduction; None when the
+    model does not qualify."""
+    from .flows import NSF_CL
+    var = model._prior_var() if hasattr(model, "_prior_var") else None
+    if var is None or len(model.flows) == 0 or not all(isinstance(f, NSF_CL) and f.fused and bwd_eligible(f) for f in model.flows):
+        return None
+    h = f32c(x.detach())
+    logdet = torch.zeros(h.shape[0], dtype=torch.float32, device=h.device)
+    inputs = []
+    for f in model.flows:
+        inputs.append(h)
+        h, logdet = run(f, h, False, logdet)
+    logp = _ops.gauss_logprob(h, var, add=logdet, add_sign=1.0)
+    g = h * (-1.0 / var)
+    for f, xin in zip(reversed(model.flows), reversed(inputs)):
+        g = layer_backward(f, xin, g, None, 1.0, False)
+    return logp, g

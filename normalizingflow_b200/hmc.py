@@ -140,6 +140,7 @@ class FlowSimulation:
         self.velocity = torch.zeros_like(self.position)
         self.grad_evals = 0
         self.tensor_core_grad = True      # bf16-conditioner models: hand-written forward+backward path
+        self.fused_grad = True            # ... through the one-launch-per-layer kernels when hidden width <= 128
         self.use_graph = True             # replay whole trajectories as one CUDA graph on that path
         self._graphs = {}
 
@@ -165,11 +166,16 @@ class FlowSimulation:
 
     def potential_and_force(self, q):
         """U(q) [C] and F(q) = -grad U = grad log p [C, d] — one forward + one backward through the flow."""
-        from . import _wide
-        fast = _wide.flow_logp_and_grad(self.model, q) if self.tensor_core_grad else None
+        from . import _fused, _wide
+        fast = None
+        if self.tensor_core_grad:
+            # hidden width <= 128: one forward and one backward launch per layer (csrc/nsf_fused2.cu,
+            # csrc/nsf_fused_bwd.cu); wider conditioners: the forward keeps the hidden activations, backward =
+            # spline adjoint as a GEMM epilogue + dgrad GEMMs on the tensor cores (csrc/gemm_ws.cu); no autograd graph
+            fast = _fused.flow_logp_and_grad(self.model, q) if self.fused_grad else None
+            if fast is None:
+                fast = _wide.flow_logp_and_grad(self.model, q)
         if fast is not None:
-            # forward keeps the hidden activations, backward = spline adjoint as a GEMM epilogue +
-            # dgrad GEMMs on the tensor cores (csrc/gemm_ws.cu); no autograd graph
             logp, force = fast
             self.grad_evals += 1
             return -logp, force
@@ -198,13 +204,13 @@ class FlowSimulation:
         return pot
 
     def _graph_trajectory(self, path_len, dt):
-        """The leapfrog trajectory (path_len + 1 log-prob+grad evaluations, ~75 launches each) is a
+        """The leapfrog trajectory (path_len + 1 log-prob+grad evaluations: 18 launches each at hidden width <= 128, ~75 on the wide path) is a
         fixed launch sequence on fixed buffers: capture it once per (path_len, dt, parameter
         version) and replay it, so the GPU is never waiting on the host."""
         from . import _wide
         if not _wide.flow_grad_eligible(self.model):
             return None
-        key = (path_len, dt, self.n_chains, _lib.param_epoch(),
+        key = (path_len, dt, self.n_chains, self.fused_grad, _lib.param_epoch(),
                tuple((p._version, p.data_ptr()) for p in self.model.parameters()))
         entry = self._graphs.get(key)
         if entry is None:

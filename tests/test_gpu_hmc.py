@@ -152,6 +152,79 @@ def test_layer_backward_matches_autograd(inverse, size, dim, mask, H):
     assert float((err > 3e-2).float().mean()) <= 5e-3, float((err > 3e-2).float().mean())
 
 
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("mask,H,N", [(0, 128, 1024), (1, 128, 1024), (1, 64, 900), (0, 16, 130)])
+def test_fused_layer_backward_matches_fp32_autograd(inverse, mask, H, N):
+    """ONE launch per layer (csrc/nsf_fused_bwd.cu: conditioner recomputed with the forward kernel's fp16 operands,
+    spline adjoint in registers, three dgrad GEMMs on chip) vs autograd through the fp32 parity path of the same
+    layer, for L = sum(out * r) + sum(logdet * s).  d logdet / dx jumps across knots (the spline is C1), so the
+    bulk is gated, not the maximum; a partial last tile is padded."""
+    from normalizingflow_b200 import _fused, flows
+    torch.manual_seed(7)
+    lay = flows.NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=H, mask=[mask]).cuda()
+    with torch.no_grad():
+        lay.psi.network[4].weight.mul_(3.0)
+    gen = torch.Generator().manual_seed(11)
+    x = (1.2 * torch.randn(N, 64, generator=gen)).cuda()
+    r = torch.randn(N, 64, generator=gen).cuda()
+    s = torch.randn(N, generator=gen).cuda()
+    lay.fused = False
+    lay.psi.precision = "fp32"
+    xg = x.clone().requires_grad_()
+    out, ld = (lay.inverse if inverse else lay.forward)(xg)
+    (gref,) = torch.autograd.grad((out * r).sum() + (ld * s).sum(), [xg])
+    lay.psi.precision = "bf16"
+    lay.fused = True
+    assert _fused.bwd_eligible(lay)
+    with torch.no_grad():
+        gin = _fused.layer_backward(lay, x, r, s, 1.0, inverse)
+        g_const = _fused.layer_backward(lay, x, r, None, 1.0, inverse)
+        g_ones = _fused.layer_backward(lay, x, r, torch.ones_like(s), 0.0, inverse)
+    assert gin.shape == (N, 64) and torch.isfinite(gin).all()
+    err = (gin - gref).abs() / (1.0 + gref.abs())
+    assert float(err.median()) <= 2e-3, float(err.median())
+    assert float((err > 3e-2).float().mean()) <= 1e-2, float((err > 3e-2).float().mean())
+    assert torch.equal(g_const, g_ones)                 # constant d logdet == a tensor of that constant
+    # rows are independent: the first 128 rows alone give the same gradient bit for bit
+    with torch.no_grad():
+        g_head = _fused.layer_backward(lay, x[:128], r[:128], s[:128], 1.0, inverse)
+    assert torch.equal(g_head, gin[:128])
+
+
+def test_fused_force_path_is_used_and_matches_the_wide_path_and_the_oracle():
+    """8-layer flow (H = 16 golden weights, bf16-class conditioner): FlowSimulation takes the one-launch-per-layer
+    path (17 + 1 launches per evaluation); it agrees with the wide multi-launch path and with torch autograd
+    through the fp32 oracle in the 1e-2 class."""
+    from normalizingflow_b200 import _fused, _lib
+    from normalizingflow_b200.hmc import FlowSimulation
+    from oracle import nf_oracle as O
+    m = _model(precision="bf16")
+    g = golden("models.npz")
+    x = T(g["nsf.x"])
+    assert _fused.flow_logp_and_grad(m, x.cuda()) is not None
+    sim = FlowSimulation(m, n_chains=x.shape[0], init_pos=x)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    U, F = sim.potential_and_force(sim.get_position())
+    torch.cuda.synchronize()
+    n_launch = _lib.launch_count() - n0
+    assert n_launch <= 20, n_launch
+    sim.fused_grad = False
+    U2, F2 = sim.potential_and_force(sim.get_position())
+    scale = float(F2.abs().max())
+    assert rel_err(U, U2.double().cpu()) <= 5e-3
+    assert float((F - F2).abs().median()) <= 5e-3 * scale
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    specs = [dict(type="NSF_CL", size=32, dim=2, K=8, B=3.0, mask=[i % 2]) for i in range(8)]
+    xr = x.clone().requires_grad_()
+    z, plp, ld = O.flow_forward(specs, sd, xr)
+    (gref,) = torch.autograd.grad((plp + ld).sum(), xr)
+    assert rel_err(-U, (plp + ld).detach()) <= 1e-2
+    err = (F.cpu() - gref).abs() / (1.0 + gref.abs())
+    assert float(err.median()) <= 2e-3, float(err.median())
+    assert float((err > 3e-2).float().mean()) <= 3e-2, float((err > 3e-2).float().mean())
+
+
 def test_single_chain_eager_rejection_restores_the_position():
     """n_chains = 1 on the eager integrator (fp32 conditioner): HMC keeps references to the position it
     last accepted (nf/hmc.py:36, :58), so the integrator must not advance that tensor in place -- a
