@@ -252,16 +252,20 @@ int nfk_nsf_pairs_fused2(const float* x, float* out, float* logdet, const void* 
                          int8_t* dbg_bins /*nullable*/, void* stream);
 
 /* Gradient of one fused layer w.r.t. its input in ONE launch (csrc/nsf_fused_bwd.cu; hidden <= 128, size 32, dim 2,
- * K 8): recomputes the conditioner with the forward kernel's fp16 operands (same parameters and bins, bit for bit),
- * runs the spline adjoint per element in registers, the three dgrad GEMMs (bf16 operands) and the tanh backward on
- * chip.  x, grad_out, grad_x [N, 64] (grad_out in the layer's OUTPUT column order: conditioning, transformed);
- * grad_logdet [N] or NULL (grad_logdet_const for every row: 1 for log-prob gradients).  w1/w2/w3_img, b1..b3 as for
- * nfk_nsf_pairs_fused2 (split = 0); transposed bf16 images: w3t_img [4][3][128 x 64] (pair of chunks p, K block:
- * n = hidden unit, k = 24-per-feature padded parameter index within the pair), w2t_img [2][128 x 64] (n = input unit,
- * k = output unit), w1t_img [2][32 x 64] (n = conditioning feature, k = hidden unit), all K-major SWIZZLE_128B.
+ * K 8): recomputes the conditioner with the forward kernel's fp16 operands (same parameters, bit for bit), runs the
+ * spline adjoint per element in registers, the three dgrad GEMMs (bf16 operands) and the tanh backward on chip.
+ * x, grad_out, grad_x [N, 64]; dL/d(out) = grad_out_scale * grad_out in the layer's OUTPUT column order
+ * (conditioning, transformed) -- pass z and -1/var to start from an isotropic Gaussian prior; grad_logdet [N] or
+ * NULL (grad_logdet_const for every row: 1 for log-prob gradients).  N a multiple of 128.
+ * Operand images (all K-major SWIZZLE_128B, built by normalizingflow_b200/_fused.py:packed_bwd): w1_img, w2_img,
+ * b1, b2 as for nfk_nsf_pairs_fused2 (split = 0); w3_img and b3 likewise but with every feature's 24 rows in the
+ * order (w0, h0, w1, h1, ..., w7, h7, d0 .. d6, 0) so that a width / height logit pair lands in adjacent
+ * accumulator columns; transposed bf16 images: w3t_img [4][3][128 x 64] (pair of chunks p, K block: n = hidden
+ * unit, k = parameter index within the pair, same order), w2t_img [2][128 x 64] (n = input unit, k = output unit),
+ * w1t_img [2][32 x 64] (n = conditioning feature, k = hidden unit).
  * Replaces autograd through NSF_CL.forward / inverse (nf/flows.py:227-253) for dL/dx, as the flow-preconditioned HMC
  * force evaluation needs it (nf/hmc.py:34-41, applications/src/systems.py:308-311). */
-int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, const float* grad_logdet,
+int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, float grad_out_scale, const float* grad_logdet,
                             float grad_logdet_const, float* grad_x, const void* w1_img, const void* w2_img,
                             const void* w3_img, const void* w3t_img, const void* w2t_img,
                             const void* w1t_img, const float* b1, const float* b2, const float* b3,

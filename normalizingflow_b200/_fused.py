@@ -205,20 +205,33 @@ def bwd_eligible(layer) -> bool:
             and getattr(layer.psi, "precision", None) == "bf16")
 
 
+# order of a feature's 24 parameter rows in the backward kernel's W3 images: width / height logits interleaved
+_BWD_ROW_ORDER = [i // 2 + 8 * (i % 2) for i in range(16)] + list(range(16, 24))
+
+
 def packed_bwd(layer):
-    """Transposed bf16 dgrad operands (W3^T per pair of chunks, W2^T, W1^T) in the K-major SWIZZLE_128B image layout."""
+    """Operand images of the one-launch backward (see nfk_nsf_pairs_fused_bwd in include/nfk.h): the forward W3 / b3
+    with permuted rows (fp16) and the transposed bf16 dgrad operands W3^T per pair of chunks, W2^T, W1^T."""
     net = layer.psi.network
     l0, l2, l4 = net[0], net[2], net[4]
-    key = (_lib.param_epoch(),) + tuple((l.weight._version, l.weight.data_ptr()) for l in (l0, l2, l4))
+    key = (_lib.param_epoch(),) + tuple((l.weight._version, l.weight.data_ptr(), l.bias._version) for l in (l0, l2, l4))
     cache = getattr(layer, "_fused_bwd_cache", None)
     if cache is not None and cache[0] == key:
         return cache[1]
     dev = l0.weight.device
     H = l0.out_features
-    bf = torch.bfloat16
-    w3p = torch.zeros((NF, PC, HP), dtype=bf, device=dev)
-    w3p[:, :23, :H] = l4.weight.detach().to(bf).reshape(NF, 23, H)
-    w3t = torch.stack([_swizzle_image(w3p[8 * p:8 * p + 8].reshape(8 * PC, HP).t().contiguous())
+    bf, f16 = torch.bfloat16, torch.float16
+    order = torch.tensor(_BWD_ROW_ORDER, device=dev)
+    w3p = torch.zeros((NF, PC, HP), dtype=torch.float32, device=dev)
+    w3p[:, :23, :H] = l4.weight.detach().float().reshape(NF, 23, H)
+    w3p = w3p[:, order, :]                                                          # [32, 24, 128], rows permuted
+    w3f = w3p.clamp(-65504.0, 65504.0).to(f16).reshape(NF // CF, CF * PC, HP)
+    w3 = torch.stack([_swizzle_image(w3f[c]) for c in range(NF // CF)]).contiguous()
+    b3 = torch.zeros((NF, PC), dtype=torch.float32, device=dev)
+    b3[:, :23] = l4.bias.detach().float().reshape(NF, 23)
+    b3 = b3[:, order].reshape(-1).contiguous()
+    w3b = w3p.to(bf)
+    w3t = torch.stack([_swizzle_image(w3b[8 * p:8 * p + 8].reshape(8 * PC, HP).t().contiguous())
                        for p in range(NF // 8)]).contiguous()                    # [4, 3, 128, 8, 8]
     w2p = torch.zeros((HP, HP), dtype=bf, device=dev)
     w2p[:H, :H] = l2.weight.detach().to(bf)
@@ -226,14 +239,14 @@ def packed_bwd(layer):
     w1p = torch.zeros((HP, 32), dtype=bf, device=dev)
     w1p[:H, :] = l0.weight.detach().to(bf)
     w1t = _swizzle_image(w1p.t().contiguous())                                      # [2, 32, 8, 8]
-    pk = dict(w3t=w3t, w2t=w2t, w1t=w1t)
+    pk = dict(w3=w3, b3=b3, w3t=w3t, w2t=w2t, w1t=w1t)
     layer._fused_bwd_cache = (key, pk)
     return pk
 
 
-def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=False):
-    """dL/dx [N, 64] of one bwd_eligible layer from the layer input x, dL/d(out) and dL/d(log_det) (a per-row tensor, or a
-    constant for every row).  A partial last tile is zero-padded."""
+def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=False, g_out_scale=1.0):
+    """dL/dx [N, 64] of one bwd_eligible layer from the layer input x, dL/d(out) = g_out_scale * g_out and dL/d(log_det)
+    (a per-row tensor, or a constant for every row).  A partial last tile is zero-padded."""
     dev = require_cuda(x, g_out, g_logdet)
     x, g_out = f32c(x), f32c(g_out)
     N = x.shape[0]
@@ -253,10 +266,10 @@ def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=F
     with torch.cuda.device(dev):
         tm = _ops.KERNEL_TIMER
         ev = tm.start("nsf_pairs_fused_bwd", dev) if tm is not None else None
-        call("nfk_nsf_pairs_fused_bwd", ptr(x), ptr(g_out), ptr(f32c(g_logdet)) if g_logdet is not None else ptr(None),
-             float(g_logdet_const), ptr(g_in), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]), ptr(pb["w3t"]), ptr(pb["w2t"]),
-             ptr(pb["w1t"]), ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), n_pad, layer._mask[0], float(layer.B),
-             int(bool(inverse)), stream_ptr(dev))
+        call("nfk_nsf_pairs_fused_bwd", ptr(x), ptr(g_out), float(g_out_scale),
+             ptr(f32c(g_logdet)) if g_logdet is not None else ptr(None), float(g_logdet_const), ptr(g_in), ptr(pk["w1"]),
+             ptr(pk["w2"]), ptr(pb["w3"]), ptr(pb["w3t"]), ptr(pb["w2t"]), ptr(pb["w1t"]), ptr(pk["b1"]), ptr(pk["b2"]),
+             ptr(pb["b3"]), n_pad, layer._mask[0], float(layer.B), int(bool(inverse)), stream_ptr(dev))
         if ev is not None:
             tm.stop(ev, dev)
     return g_in[:N]
@@ -264,7 +277,7 @@ def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=F
 
 def flow_logp_and_grad(model, x):
     """log p(x) [N] and d log p / dx [N, d] through a flow whose layers are all bwd_eligible, under an isotropic Gaussian
-    prior: 8 forward launches (keeping each layer's input) + 8 backward launches + the log-prob reduction; None when the
+    prior: one forward launch per layer (keeping each layer's input), the log-prob reduction, one backward launch per layer; None when the
     model does not qualify."""
     from .flows import NSF_CL
     var = model._prior_var() if hasattr(model, "_prior_var") else None
@@ -277,7 +290,8 @@ def flow_logp_and_grad(model, x):
         inputs.append(h)
         h, logdet = run(f, h, False, logdet)
     logp = _ops.gauss_logprob(h, var, add=logdet, add_sign=1.0)
-    g = h * (-1.0 / var)
+    g, scale = h, -1.0 / var                                  # d log N(z; 0, var I) / dz = -z / var, applied by the first launch
     for f, xin in zip(reversed(model.flows), reversed(inputs)):
-        g = layer_backward(f, xin, g, None, 1.0, False)
+        g = layer_backward(f, xin, g, None, 1.0, False, scale)
+        scale = 1.0
     return logp, g

@@ -6,28 +6,33 @@
 //
 //   recompute   A1 = fp16(x[:, cond]) -> GEMM1 -> h1 = tanh(. + b1) -> GEMM2 -> h2 = tanh(. + b2)        (kept in shared memory)
 //   per chunk   GEMM3 chunk (4 features x 24 parameters) -> TMEM -> thread (row, feature): spline ADJOINT in
-//               registers (rqs_bwd_math.cuh): direct dL/dx of the transformed column -> HBM, dL/dparams (24 values)
-//               -> bf16 A operand G in shared memory (8 features = 192 columns = 3 K blocks per pair of chunks)
+//               registers (rqs_bwd_math.cuh, both knot chains in packed fp32x2): dL/dx of the transformed column and the
+//               pass-through gradient of the conditioning column -> HBM (one 8-byte pair), dL/dparams (24 values) ->
+//               bf16 A operand G in shared memory (8 features = 192 columns = 3 K blocks per pair of chunks)
 //   per pair    dH2 += G W3_pair        (B operand: W3 transposed, streamed through the ring; accumulates in TMEM)
 //   then        dZ2 = dH2 (1 - h2^2) -> GEMM with W2^T -> dH1 ;  dZ1 = dH1 (1 - h1^2) -> GEMM with W1^T -> dXc
-//               dL/dx[:, cond] = dL/d(out)[:, cond position] + dXc
+//               dL/dx[:, cond] += dXc                                                    (red.global.add)
 //
-// The forward GEMMs use exactly the fp16 operands and MMA order of nsf_fused2_kernel, so the recomputed
-// parameters (and therefore the bins) are the forward kernel's, bit for bit; the backward GEMMs use bf16
-// operands (gradient range).  Warp roles as in nsf_fused2.cu: warps 0..15 ADJOINT (thread = (row,
-// feature-in-chunk)), 16..19 HIDDEN (thread = row: operand builders and tanh / tanh-backward epilogues), 20 MMA,
-// 21 TMA ring; registers redistributed with setmaxnreg.  The activations x / dL/d(out) are read straight from
-// global memory by the thread that needs them (8-byte pairs; the four feature slices of a row share every
-// 32-byte sector, which L1 / L2 absorb), so shared memory holds only operands: W1 16 KB + h1 32 + h2 32 + G 48
-// + ring 72.  TMEM: D12 128 + two chunk buffers 192 + dH2 128 + dXc 32 = 480 of 512 columns.
+// The forward GEMMs use exactly the fp16 operands and MMA order of nsf_fused2_kernel (the rows of W3 permuted so
+// that a feature's width and height logits arrive interleaved), so the recomputed parameters are the forward
+// kernel's, bit for bit; the backward GEMMs use bf16 operands (gradient range).
+// Warps 0..15 WORK (thread = (row, slice): the adjoint of feature 4 c + slice in chunk c, and a quarter of every
+// hidden-layer epilogue: 32 of the 128 columns of its row), warp 16 issues every MMA, warp 17 runs the weight ring.
+// The first version of this kernel gave the hidden-layer epilogues to four dedicated warps as nsf_fused2.cu does:
+// with nothing to overlap them with (a tile's backward is one dependent chain) they cost 29 k of a tile's 69 k
+// clocks; spread over the 16 work warps they cost a quarter of that.
+// The activations x / dL/d(out) are read straight from global memory by the thread that needs them (8-byte pairs
+// one chunk ahead, the next tile's rows prefetched into L2 by the ring warp), so shared memory holds only
+// operands: W1 16 KB + h1 32 + h2 32 + G 48 + ring 72.  TMEM: D12 128 + two chunk buffers 192 + dH2 128 + dXc 32
+// = 480 of 512 columns.
 #include "rqs_bwd_math.cuh"
 #include "tc05.cuh"
 
 namespace nfk {
 
 constexpr int FB_ROWS = 128;
-constexpr int FB_ADJ_WARPS = 16, FB_HID_WARPS = 4, FB_WARP_MMA = 20, FB_WARP_TMA = 21;
-constexpr int FB_THREADS = 24 * 32;
+constexpr int FB_WORK_WARPS = 16, FB_WARP_MMA = 16, FB_WARP_TMA = 17;
+constexpr int FB_THREADS = 18 * 32;
 constexpr int FB_HP = 128, FB_NF = 32, FB_PC = 24, FB_CF = 4;
 constexpr int FB_NC = FB_CF * FB_PC;             // 96
 constexpr int FB_NCHUNK = FB_NF / FB_CF;         // 8
@@ -40,8 +45,6 @@ constexpr uint32_t FB_G_BYTES = 3 * FB_KB_BYTES;
 constexpr uint32_t FB_W3C_BYTES = 2 * FB_NC * 128;              // 24 KB
 constexpr uint32_t FB_STAGE_BYTES = FB_W3C_BYTES;
 constexpr uint32_t FB_W1T_BYTES = 32 * 128;                     // one K block of W1^T: [32 rows x 64]
-constexpr int FB_REG_LAUNCH = 80, FB_REG_ADJ = 96, FB_REG_HID = 56, FB_REG_CTRL = 40;
-static_assert(16 * FB_REG_ADJ + 4 * FB_REG_HID + 4 * FB_REG_CTRL <= 24 * FB_REG_LAUNCH, "register budgets exceed the launch pool");
 constexpr uint32_t FB_T_D12 = 0, FB_T_D3 = 128, FB_T_DH2 = 320, FB_T_DX = 448;
 
 struct FusedBwdArgs {
@@ -49,19 +52,19 @@ struct FusedBwdArgs {
   const float* gout;      // [N, 64] dL/d(layer output), reference column order (conditioning, transformed)
   const float* gld;       // [N] dL/dlogdet, or null: gld_const for every row
   float gld_const;
+  float gout_scale;       // dL/d(out) = gout_scale * gout (the prior's -1/var when gout is z itself)
   float* gin;             // [N, 64] dL/d(layer input)
-  const unsigned char* w1_img;    // forward images, as nfk_nsf_pairs_fused2 (fp16)
+  const unsigned char* w1_img;    // forward images as nfk_nsf_pairs_fused2 (fp16) ...
   const unsigned char* w2_img;
-  const unsigned char* w3_img;
-  const unsigned char* w3t_img;   // [4 pairs][3 K blocks][128 x 64] bf16: (n = hidden unit, k = padded parameter index in the pair)
+  const unsigned char* w3_img;    // ... with every feature's 24 rows in the order (w0, h0, w1, h1, ..., w7, h7, d0..d6, 0)
+  const unsigned char* w3t_img;   // [4 pairs][3 K blocks][128 x 64] bf16: (n = hidden unit, k = parameter index in the pair, same order)
   const unsigned char* w2t_img;   // [2 K blocks][128 x 64] bf16: (n = input unit, k = output unit)
   const unsigned char* w1t_img;   // [2 K blocks][32 x 64] bf16: (n = conditioning feature, k = hidden unit)
   const float* b1;
   const float* b2;
-  const float* b3;
+  const float* b3;                // [32][24] in the order of w3_img's rows
   long long n_tiles;
   int cond_first;
-  int inverse;
   RqsConsts c;
 };
 
@@ -74,20 +77,21 @@ __device__ __forceinline__ bool fb_elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-template <int N>
-__device__ __forceinline__ void fb_reg_inc() {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
-}
-template <int N>
-__device__ __forceinline__ void fb_reg_dec() {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
-}
-
 // L2 prefetch of a contiguous span (the next tile's rows of x and dL/d(out)): the per-thread 8-byte loads that follow
 // then miss L1 only
 __device__ __forceinline__ void fb_prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void fb_red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+#ifdef FB_TRACE   // tools/ubench timing experiment: clock64 of the phases of CTA 0's second tile
+__device__ long long fb_trace[256];
+#define FB_T(on, slot) do { if ((on) && (threadIdx.x & 31) == 0) fb_trace[slot] = clock64(); } while (0)
+#else
+#define FB_T(on, slot) do { } while (0)
+#endif
 
 template <bool INV>
 __global__ void __launch_bounds__(FB_THREADS, 1)
@@ -106,7 +110,7 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
   uint64_t* bar_w1 = bars;             // W1 resident                                        (1 + tx)
   uint64_t* bar_full = bars + 1;       // [3] ring piece landed                              (1 + tx)
   uint64_t* bar_empty = bars + 4;      // [3] ring piece consumed                            (1, commit)
-  uint64_t* bar_a = bars + 7;          // operand written by the hidden warps, 5 phases/tile (4 warps)
+  uint64_t* bar_a = bars + 7;          // operand written by the work warps, 5 phases/tile   (16 warps)
   uint64_t* bar_d12 = bars + 8;        // GEMM1 / GEMM2 / dH1 GEMM done, 3 phases/tile       (1, commit)
   uint64_t* bar_d3f = bars + 9;        // [2] GEMM3 chunk done                               (1, commit)
   uint64_t* bar_d3e = bars + 11;       // [2] chunk accumulator drained                      (16 warps)
@@ -128,18 +132,22 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
-    mbar_init(bar_a, FB_HID_WARPS);
+    mbar_init(bar_a, FB_WORK_WARPS);
     mbar_init(bar_d12, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_d3f[i], 1);
-      mbar_init(&bar_d3e[i], FB_ADJ_WARPS);
+      mbar_init(&bar_d3e[i], FB_WORK_WARPS);
     }
-    mbar_init(bar_gready, 2 * FB_ADJ_WARPS);
+    mbar_init(bar_gready, 2 * FB_WORK_WARPS);
     mbar_init(bar_gfree, 1);
     mbar_init(bar_dh2, 1);
     mbar_init(bar_dx, 1);
     fence_barrier_init();
   }
+  // Programmatic dependent launch (as nsf_fused2.cu): this grid may be scheduled while the previous kernel of the stream
+  // drains; nothing in global memory is touched before the wait, and the trigger lets the next launch do the same.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
   for (int i = tid; i < FB_HP; i += FB_THREADS) {
     sB1[i] = a.b1[i];
     sB2[i] = a.b2[i];
@@ -150,299 +158,239 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp >= FB_WARP_MMA) {
-    fb_reg_dec<FB_REG_CTRL>();
-    if (warp == FB_WARP_TMA) {
-      // ---------------- ring producer: pieces in the order the MMA warp consumes them
-      uint32_t s = 0, ph = 0;
-      auto put = [&](const unsigned char* src, uint32_t bytes) {
-        mbar_wait_idle(&bar_empty[s], ph ^ 1);
-        if (lane == 0) {
-          mbar_expect_tx(&bar_full[s], bytes);
-          bulk_g2s(sRing + s * FB_STAGE_BYTES, src, bytes, &bar_full[s]);
-        }
-        __syncwarp();
-        if (++s == FB_STAGES) {
-          s = 0;
-          ph ^= 1;
-        }
-      };
-      if (my_tiles && lane == 0) {
-        mbar_expect_tx(bar_w1, FB_W1_BYTES);
-        bulk_g2s(sW1, a.w1_img, FB_W1_BYTES, bar_w1);
+  if (warp == FB_WARP_TMA) {
+    // ---------------- ring producer: pieces in the order the MMA warp consumes them
+    uint32_t s = 0, ph = 0;
+    auto put = [&](const unsigned char* src, uint32_t bytes) {
+      mbar_wait_idle(&bar_empty[s], ph ^ 1);
+      if (lane == 0) {
+        mbar_expect_tx(&bar_full[s], bytes);
+        bulk_g2s(sRing + s * FB_STAGE_BYTES, src, bytes, &bar_full[s]);
       }
       __syncwarp();
-      for (unsigned it = 0; it < my_tiles; ++it) {
-        if (it + 1 < my_tiles && lane == 0) {
-          const size_t nrow = (first + (size_t)(it + 1) * stride) * FB_ROWS;
-          fb_prefetch_l2(a.x + nrow * 64, FB_ROWS * 256);
-          fb_prefetch_l2(a.gout + nrow * 64, FB_ROWS * 256);
-        }
-        put(a.w2_img, FB_KB_BYTES);
-        put(a.w2_img + FB_KB_BYTES, FB_KB_BYTES);
-#pragma unroll 1
-        for (int c = 0; c < FB_NCHUNK; ++c) {
-          put(a.w3_img + (size_t)c * FB_W3C_BYTES, FB_W3C_BYTES);
-          // the dH2 GEMM of pair p is issued after chunk 2p+2 (after the last chunk for the last pair)
-          const int p = (c >= 2 && (c & 1) == 0) ? (c >> 1) - 1 : (c == FB_NCHUNK - 1 ? FB_NPAIR - 1 : -1);
-          if (p >= 0)
-            for (int kb = 0; kb < 3; ++kb) put(a.w3t_img + ((size_t)p * 3 + kb) * FB_KB_BYTES, FB_KB_BYTES);
-        }
-        put(a.w2t_img, FB_KB_BYTES);
-        put(a.w2t_img + FB_KB_BYTES, FB_KB_BYTES);
-        put(a.w1t_img, FB_W1T_BYTES);
-        put(a.w1t_img + FB_W1T_BYTES, FB_W1T_BYTES);
+      if (++s == FB_STAGES) {
+        s = 0;
+        ph ^= 1;
       }
-    } else if (warp == FB_WARP_MMA) {
-      // ---------------- MMA issuer
-      const uint32_t id_f16_128 = make_idesc_f16(FB_ROWS, FB_HP);
-      const uint32_t id_f16_96 = make_idesc_f16(FB_ROWS, FB_NC);
-      const uint32_t id_bf16_128 = make_idesc_bf16(FB_ROWS, FB_HP);
-      const uint32_t id_bf16_32 = make_idesc_bf16(FB_ROWS, 32);
-      const uint32_t aA1 = smem_u32(sA1), aA2 = smem_u32(sA2), aG = smem_u32(sG), aW1 = smem_u32(sW1), aRing = smem_u32(sRing);
-      uint32_t s = 0, ph = 0, n_a = 0, g = 0, n_pair = 0;
-      auto ring_next = [&]() {
-        if (++s == FB_STAGES) {
-          s = 0;
-          ph ^= 1;
-        }
-      };
-      // D (+)= A[K block kb] * ring piece, 4 K slices of 16; `first` clears the accumulator on the first slice
-      auto mma_block = [&](uint32_t d, uint32_t a_base, uint32_t idesc, bool first) {
-        const uint32_t bb = aRing + s * FB_STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(d, make_desc_sw128(a_base + k * 32), make_desc_sw128(bb + k * 32), idesc, (first && k == 0) ? 0u : 1u);
-      };
-      auto dh2_gemm = [&](int p) {          // dH2 (+)= G(pair p) * W3^T(pair p): 3 K blocks of 64 gradient columns
-        mbar_wait_idle(bar_gready, n_pair & 1);
-        tc_fence_after();
+    };
+    if (my_tiles && lane == 0) {
+      mbar_expect_tx(bar_w1, FB_W1_BYTES);
+      bulk_g2s(sW1, a.w1_img, FB_W1_BYTES, bar_w1);
+    }
+    __syncwarp();
+    for (unsigned it = 0; it < my_tiles; ++it) {
+      if (it + 1 < my_tiles && lane == 0) {
+        const size_t nrow = (first + (size_t)(it + 1) * stride) * FB_ROWS;
+        fb_prefetch_l2(a.x + nrow * 64, FB_ROWS * 256);
+        fb_prefetch_l2(a.gout + nrow * 64, FB_ROWS * 256);
+      }
+      put(a.w2_img, FB_KB_BYTES);
+      put(a.w2_img + FB_KB_BYTES, FB_KB_BYTES);
 #pragma unroll 1
-        for (int kb = 0; kb < 3; ++kb) {
-          mbar_wait_idle(&bar_full[s], ph);
-          tc_fence_after();
-          if (fb_elect_one()) {
-            mma_block(tmem + FB_T_DH2, aG + kb * FB_KB_BYTES, id_bf16_128, p == 0 && kb == 0);
-            umma_commit(&bar_empty[s]);
-            if (kb == 2) {
-              umma_commit(bar_gfree);
-              if (p == FB_NPAIR - 1) umma_commit(bar_dh2);
-            }
-          }
-          __syncwarp();
-          ring_next();
-        }
-        ++n_pair;
-      };
-      if (my_tiles) mbar_wait_idle(bar_w1, 0);
-      for (unsigned it = 0; it < my_tiles; ++it) {
-        // ---- GEMM1: D12 = A1 W1^T (32 real conditioning columns: K slices 0, 1)
-        mbar_wait_idle(bar_a, n_a++ & 1);
+      for (int c = 0; c < FB_NCHUNK; ++c) {
+        put(a.w3_img + (size_t)c * FB_W3C_BYTES, FB_W3C_BYTES);
+        // the dH2 GEMM of pair p is issued after chunk 2p+2 (after the last chunk for the last pair)
+        const int p = (c >= 2 && (c & 1) == 0) ? (c >> 1) - 1 : (c == FB_NCHUNK - 1 ? FB_NPAIR - 1 : -1);
+        if (p >= 0)
+          for (int kb = 0; kb < 3; ++kb) put(a.w3t_img + ((size_t)p * 3 + kb) * FB_KB_BYTES, FB_KB_BYTES);
+      }
+      put(a.w2t_img, FB_KB_BYTES);
+      put(a.w2t_img + FB_KB_BYTES, FB_KB_BYTES);
+      put(a.w1t_img, FB_W1T_BYTES);
+      put(a.w1t_img + FB_W1T_BYTES, FB_W1T_BYTES);
+    }
+  } else if (warp == FB_WARP_MMA) {
+    // ---------------- MMA issuer
+    const uint32_t id_f16_128 = make_idesc_f16(FB_ROWS, FB_HP);
+    const uint32_t id_f16_96 = make_idesc_f16(FB_ROWS, FB_NC);
+    const uint32_t id_bf16_128 = make_idesc_bf16(FB_ROWS, FB_HP);
+    const uint32_t id_bf16_32 = make_idesc_bf16(FB_ROWS, 32);
+    const uint32_t aA1 = smem_u32(sA1), aA2 = smem_u32(sA2), aG = smem_u32(sG), aW1 = smem_u32(sW1), aRing = smem_u32(sRing);
+    uint32_t s = 0, ph = 0, n_a = 0, g = 0, n_pair = 0;
+    auto ring_next = [&]() {
+      if (++s == FB_STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
+    };
+    // D (+)= A[K block kb] * ring piece, 4 K slices of 16; `first` clears the accumulator on the first slice
+    auto mma_block = [&](uint32_t d, uint32_t a_base, uint32_t idesc, bool first) {
+      const uint32_t bb = aRing + s * FB_STAGE_BYTES;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(d, make_desc_sw128(a_base + k * 32), make_desc_sw128(bb + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+    };
+    auto dh2_gemm = [&](int p) {          // dH2 (+)= G(pair p) * W3^T(pair p): 3 K blocks of 64 gradient columns
+      mbar_wait_idle(bar_gready, n_pair & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int kb = 0; kb < 3; ++kb) {
+        mbar_wait_idle(&bar_full[s], ph);
         tc_fence_after();
         if (fb_elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_bf16(tmem + FB_T_D12, make_desc_sw128(aA1 + k * 32), make_desc_sw128(aW1 + k * 32), id_f16_128, k ? 1u : 0u);
-          umma_commit(bar_d12);
+          mma_block(tmem + FB_T_DH2, aG + kb * FB_KB_BYTES, id_bf16_128, p == 0 && kb == 0);
+          umma_commit(&bar_empty[s]);
+          if (kb == 2) {
+            umma_commit(bar_gfree);
+            if (p == FB_NPAIR - 1) umma_commit(bar_dh2);
+          }
         }
         __syncwarp();
-        // ---- GEMM2: D12 = h1 W2^T
-        mbar_wait_idle(bar_a, n_a++ & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int kb = 0; kb < 2; ++kb) {
-          mbar_wait_idle(&bar_full[s], ph);
-          tc_fence_after();
-          if (fb_elect_one()) {
-            mma_block(tmem + FB_T_D12, aA1 + kb * FB_KB_BYTES, id_f16_128, kb == 0);
-            umma_commit(&bar_empty[s]);
-            if (kb == 1) umma_commit(bar_d12);
-          }
-          __syncwarp();
-          ring_next();
-        }
-        // ---- GEMM3 chunks interleaved with the dH2 GEMMs
-        mbar_wait_idle(bar_a, n_a++ & 1);                       // h2 written
-#pragma unroll 1
-        for (int c = 0; c < FB_NCHUNK; ++c, ++g) {
-          if (g >= 2) mbar_wait_idle(&bar_d3e[g & 1], ((g >> 1) + 1) & 1);
-          mbar_wait_idle(&bar_full[s], ph);
-          tc_fence_after();
-          if (fb_elect_one()) {
-            const uint32_t d = tmem + FB_T_D3 + (g & 1) * FB_NC;
-            const uint32_t bb = aRing + s * FB_STAGE_BYTES;
+        ring_next();
+      }
+      ++n_pair;
+    };
+    if (my_tiles) mbar_wait_idle(bar_w1, 0);
+    for (unsigned it = 0; it < my_tiles; ++it) {
+      const bool tr = blockIdx.x == 0 && it == 1;
+      (void)tr;
+      // ---- GEMM1: D12 = A1 W1^T (32 real conditioning columns: K slices 0, 1)
+      mbar_wait_idle(bar_a, n_a++ & 1);
+      tc_fence_after();
+      if (fb_elect_one()) {
 #pragma unroll
-            for (int kb = 0; kb < 2; ++kb)
+        for (int k = 0; k < 2; ++k)
+          umma_bf16(tmem + FB_T_D12, make_desc_sw128(aA1 + k * 32), make_desc_sw128(aW1 + k * 32), id_f16_128, k ? 1u : 0u);
+        umma_commit(bar_d12);
+      }
+      __syncwarp();
+      FB_T(tr, 0);
+      // ---- GEMM2: D12 = h1 W2^T
+      mbar_wait_idle(bar_a, n_a++ & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int kb = 0; kb < 2; ++kb) {
+        mbar_wait_idle(&bar_full[s], ph);
+        tc_fence_after();
+        if (fb_elect_one()) {
+          mma_block(tmem + FB_T_D12, aA1 + kb * FB_KB_BYTES, id_f16_128, kb == 0);
+          umma_commit(&bar_empty[s]);
+          if (kb == 1) umma_commit(bar_d12);
+        }
+        __syncwarp();
+        ring_next();
+      }
+      FB_T(tr, 1);
+      // ---- GEMM3 chunks interleaved with the dH2 GEMMs
+      mbar_wait_idle(bar_a, n_a++ & 1);                       // h2 written
+#pragma unroll 1
+      for (int c = 0; c < FB_NCHUNK; ++c, ++g) {
+        if (g >= 2) mbar_wait_idle(&bar_d3e[g & 1], ((g >> 1) + 1) & 1);
+        mbar_wait_idle(&bar_full[s], ph);
+        tc_fence_after();
+        if (fb_elect_one()) {
+          const uint32_t d = tmem + FB_T_D3 + (g & 1) * FB_NC;
+          const uint32_t bb = aRing + s * FB_STAGE_BYTES;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d, make_desc_sw128(aA2 + kb * FB_KB_BYTES + k * 32), make_desc_sw128(bb + kb * (FB_NC * 128) + k * 32),
-                          id_f16_96, (kb | k) ? 1u : 0u);
-            umma_commit(&bar_empty[s]);
-            umma_commit(&bar_d3f[g & 1]);
-          }
-          __syncwarp();
-          ring_next();
-          if (c >= 2 && (c & 1) == 0) dh2_gemm((c >> 1) - 1);
-          if (c == FB_NCHUNK - 1) dh2_gemm(FB_NPAIR - 1);
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d, make_desc_sw128(aA2 + kb * FB_KB_BYTES + k * 32), make_desc_sw128(bb + kb * (FB_NC * 128) + k * 32),
+                        id_f16_96, (kb | k) ? 1u : 0u);
+          umma_commit(&bar_empty[s]);
+          umma_commit(&bar_d3f[g & 1]);
         }
-        // ---- dH1 = dZ2 W2 (B operand W2^T) -> D12
-        mbar_wait_idle(bar_a, n_a++ & 1);                       // dZ2 written over h2
-        tc_fence_after();
-#pragma unroll 1
-        for (int kb = 0; kb < 2; ++kb) {
-          mbar_wait_idle(&bar_full[s], ph);
-          tc_fence_after();
-          if (fb_elect_one()) {
-            mma_block(tmem + FB_T_D12, aA2 + kb * FB_KB_BYTES, id_bf16_128, kb == 0);
-            umma_commit(&bar_empty[s]);
-            if (kb == 1) umma_commit(bar_d12);
-          }
-          __syncwarp();
-          ring_next();
-        }
-        // ---- dXc = dZ1 W1 (B operand W1^T, 32 output columns)
-        mbar_wait_idle(bar_a, n_a++ & 1);                       // dZ1 written over h1
-        tc_fence_after();
-#pragma unroll 1
-        for (int kb = 0; kb < 2; ++kb) {
-          mbar_wait_idle(&bar_full[s], ph);
-          tc_fence_after();
-          if (fb_elect_one()) {
-            mma_block(tmem + FB_T_DX, aA1 + kb * FB_KB_BYTES, id_bf16_32, kb == 0);
-            umma_commit(&bar_empty[s]);
-            if (kb == 1) umma_commit(bar_dx);
-          }
-          __syncwarp();
-          ring_next();
+        __syncwarp();
+        ring_next();
+        FB_T(tr, 2 + c);
+        // pair p's dH2 GEMM goes after chunk 2p+2 has been issued (after the last chunk for the last pair)
+        const int p = (c >= 2 && (c & 1) == 0) ? (c >> 1) - 1 : (c == FB_NCHUNK - 1 ? FB_NPAIR - 1 : -1);
+        if (p >= 0) {
+          dh2_gemm(p);
+          FB_T(tr, 10 + p);
         }
       }
+      // ---- dH1 = dZ2 W2 (B operand W2^T) -> D12
+      mbar_wait_idle(bar_a, n_a++ & 1);                       // dZ2 written over h2
+      tc_fence_after();
+#pragma unroll 1
+      for (int kb = 0; kb < 2; ++kb) {
+        mbar_wait_idle(&bar_full[s], ph);
+        tc_fence_after();
+        if (fb_elect_one()) {
+          mma_block(tmem + FB_T_D12, aA2 + kb * FB_KB_BYTES, id_bf16_128, kb == 0);
+          umma_commit(&bar_empty[s]);
+          if (kb == 1) umma_commit(bar_d12);
+        }
+        __syncwarp();
+        ring_next();
+      }
+      FB_T(tr, 14);
+      // ---- dXc = dZ1 W1 (B operand W1^T, 32 output columns)
+      mbar_wait_idle(bar_a, n_a++ & 1);                       // dZ1 written over h1
+      tc_fence_after();
+#pragma unroll 1
+      for (int kb = 0; kb < 2; ++kb) {
+        mbar_wait_idle(&bar_full[s], ph);
+        tc_fence_after();
+        if (fb_elect_one()) {
+          mma_block(tmem + FB_T_DX, aA1 + kb * FB_KB_BYTES, id_bf16_32, kb == 0);
+          umma_commit(&bar_empty[s]);
+          if (kb == 1) umma_commit(bar_dx);
+        }
+        __syncwarp();
+        ring_next();
+      }
+      FB_T(tr, 15);
     }
-  } else if (warp >= FB_ADJ_WARPS) {
-    // =============================== hidden warps (one row per thread) ===============================
-    fb_reg_dec<FB_REG_HID>();
+  } else {
+    // =============================== work warps ===============================
     const int q = warp & 3;
+    const int slice = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    uint32_t n_d12 = 0;
-    auto signal = [&]() {
+    uint32_t g = 0, n_pair = 0, n_d12 = 0;
+    auto signal = [&]() {                      // this warp's part of an MMA operand is in shared memory
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a);
     };
-    // h = tanh(D12 + bias) -> fp16 operand `dst`
+    // columns [32 slice, 32 slice + 32) of this row sit in K block slice / 2, 16-byte chunks 4 (slice % 2) + 0..3
+    const uint32_t blk_off = (uint32_t)(slice >> 1) * FB_KB_BYTES + (uint32_t)row * 128;
+    const int ch0 = (slice & 1) * 4;
+    // h = tanh(D12 + bias) -> fp16 operand
     auto tanh_epilogue = [&](const float* bias, unsigned char* dstA) {
-#pragma unroll 1
-      for (int part = 0; part < 8; ++part) {
-        uint32_t v[16];
-        tmem_ld16(tmem + FB_T_D12 + lane_sel + part * 16, v);
-        tmem_ld_wait();
-        unsigned char* dst = dstA + (part >> 2) * FB_KB_BYTES + row * 128;
+      uint32_t v[32];
+      tmem_ld32(tmem + FB_T_D12 + lane_sel + slice * 32, v);
+      tmem_ld_wait();
+      unsigned char* dst = dstA + blk_off;
+      const float* bs = bias + slice * 32;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          float f[8];
+      for (int t = 0; t < 4; ++t) {
+        float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = tanh_approx(__uint_as_float(v[t * 8 + j]) + bias[part * 16 + t * 8 + j]);
-          uint4 u;
-          u.x = pack_f16x2(f[0], f[1]);
-          u.y = pack_f16x2(f[2], f[3]);
-          u.z = pack_f16x2(f[4], f[5]);
-          u.w = pack_f16x2(f[6], f[7]);
-          const int ch = (part & 3) * 2 + t;
-          *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = u;
-        }
+        for (int j = 0; j < 8; ++j) f[j] = tanh_approx(__uint_as_float(v[t * 8 + j]) + bs[t * 8 + j]);
+        uint4 u;
+        u.x = pack_f16x2(f[0], f[1]);
+        u.y = pack_f16x2(f[2], f[3]);
+        u.z = pack_f16x2(f[4], f[5]);
+        u.w = pack_f16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(dst + (((ch0 + t) ^ (row & 7)) << 4)) = u;
       }
     };
     // dZ = D[tcol] * (1 - h^2), h read from the fp16 operand `buf`, dZ written over it as bf16
     auto tanh_backward = [&](uint32_t tcol, unsigned char* buf) {
-#pragma unroll 1
-      for (int part = 0; part < 8; ++part) {
-        uint32_t v[16];
-        tmem_ld16(tmem + tcol + lane_sel + part * 16, v);
-        tmem_ld_wait();
-        unsigned char* dst = buf + (part >> 2) * FB_KB_BYTES + row * 128;
+      uint32_t v[32];
+      tmem_ld32(tmem + tcol + lane_sel + slice * 32, v);
+      tmem_ld_wait();
+      unsigned char* dst = buf + blk_off;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int ch = (part & 3) * 2 + t;
-          uint4* p = reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4));
-          const uint4 hv = *p;
-          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-          uint32_t o[4];
+      for (int t = 0; t < 4; ++t) {
+        uint4* p = reinterpret_cast<uint4*>(dst + (((ch0 + t) ^ (row & 7)) << 4));
+        const uint4 hv = *p;
+        const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+        uint32_t o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
-            const float d0 = __uint_as_float(v[t * 8 + 2 * e]) * fmaf(-h.x, h.x, 1.f);
-            const float d1 = __uint_as_float(v[t * 8 + 2 * e + 1]) * fmaf(-h.y, h.y, 1.f);
-            o[e] = pack_bf16x2(d0, d1);
-          }
-          *p = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int e = 0; e < 4; ++e) {
+          const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+          const float d0 = __uint_as_float(v[t * 8 + 2 * e]) * fmaf(-h.x, h.x, 1.f);
+          const float d1 = __uint_as_float(v[t * 8 + 2 * e + 1]) * fmaf(-h.y, h.y, 1.f);
+          o[e] = pack_bf16x2(d0, d1);
         }
+        *p = make_uint4(o[0], o[1], o[2], o[3]);
       }
     };
-    for (unsigned t = 0; t < my_tiles; ++t) {
-      const size_t tile = first + (size_t)t * stride;
-      const size_t grow = tile * FB_ROWS + row;
-      // ---- A1: conditioning columns of this row (fp16, K block 0 chunks 0..3)
-      {
-        const float2* xr = reinterpret_cast<const float2*>(a.x + grow * 64);
-        unsigned char* dst = sA1 + row * 128;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 pr = __ldg(xr + ch * 8 + j);
-            f[j] = a.cond_first ? pr.x : pr.y;
-          }
-          uint4 u;
-          u.x = pack_f16x2_sat(f[0], f[1]);
-          u.y = pack_f16x2_sat(f[2], f[3]);
-          u.z = pack_f16x2_sat(f[4], f[5]);
-          u.w = pack_f16x2_sat(f[6], f[7]);
-          *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = u;
-        }
-      }
-      signal();
-      mbar_wait_idle(bar_d12, n_d12++ & 1);
-      tc_fence_after();
-      tanh_epilogue(sB1, sA1);                                 // h1 (kept for the tanh backward)
-      signal();
-      mbar_wait_idle(bar_d12, n_d12++ & 1);
-      tc_fence_after();
-      tanh_epilogue(sB2, sA2);                                 // h2
-      signal();
-      // ---- dZ2 = dH2 (1 - h2^2), in place over h2 (every chunk GEMM has completed: bar_dh2 follows them)
-      mbar_wait_idle(bar_dh2, t & 1);
-      tc_fence_after();
-      tanh_backward(FB_T_DH2, sA2);
-      signal();
-      // ---- dZ1 = dH1 (1 - h1^2), in place over h1
-      mbar_wait_idle(bar_d12, n_d12++ & 1);
-      tc_fence_after();
-      tanh_backward(FB_T_D12, sA1);
-      signal();
-      // ---- dL/dx of the conditioning columns: the pass-through gradient + the path through the conditioner
-      mbar_wait_idle(bar_dx, t & 1);
-      tc_fence_after();
-      {
-        uint32_t v[32];
-        tmem_ld32(tmem + FB_T_DX + lane_sel, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        const float* gor = a.gout + grow * 64;
-        float* gir = a.gin + grow * 64 + (a.cond_first ? 0 : 1);
-#pragma unroll
-        for (int f = 0; f < 32; ++f) gir[2 * f] = __ldg(gor + 2 * f) + __uint_as_float(v[f]);   // out pair = (cond, transformed)
-      }
-    }
-  } else {
-    // =============================== adjoint warps ===============================
-    fb_reg_inc<FB_REG_ADJ>();
-    const int q = warp & 3;
-    const int slice = warp >> 2;
-    const int row = q * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    uint32_t g = 0, n_pair = 0;
     // x / dL/d(out) pairs are fetched one chunk ahead (across tiles too), so their latency hides behind an adjoint
     float2 xn = make_float2(0.f, 0.f), gn = xn;
     if (my_tiles) {
@@ -450,13 +398,55 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
       xn = __ldg(reinterpret_cast<const float2*>(a.x + grow0 * 64) + slice);
       gn = __ldg(reinterpret_cast<const float2*>(a.gout + grow0 * 64) + slice);
     }
+    // the 8 pairs whose conditioning columns this thread turns into the A1 operand, fetched before the previous tile's
+    // tail (the waits on its last three GEMMs hide the latency)
+    float4 a1n[4];
+    if (my_tiles) {
+      const float4* x4 = reinterpret_cast<const float4*>(a.x + ((size_t)first * FB_ROWS + row) * 64 + slice * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a1n[j] = __ldg(x4 + j);
+    }
     for (unsigned it = 0; it < my_tiles; ++it) {
       const size_t tile = first + (size_t)it * stride;
       const size_t grow = tile * FB_ROWS + row;
       const float2* xr = reinterpret_cast<const float2*>(a.x + grow * 64);
       const float2* gor = reinterpret_cast<const float2*>(a.gout + grow * 64);
-      float* gir = a.gin + grow * 64 + (a.cond_first ? 1 : 0);        // input position of the transformed column
+      float2* gir = reinterpret_cast<float2*>(a.gin + grow * 64);
+      const bool tr = blockIdx.x == 0 && it == 1 && q == 0;
+      (void)tr;
+      FB_T(tr && slice == 0, 32);
+      // ---- A1: conditioning columns of features 8 slice .. 8 slice + 7 of this row (fp16, K block 0, chunk `slice`)
+      {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 pr = a1n[j];
+          f[2 * j] = a.cond_first ? pr.x : pr.y;
+          f[2 * j + 1] = a.cond_first ? pr.z : pr.w;
+        }
+        uint4 u;
+        u.x = pack_f16x2_sat(f[0], f[1]);
+        u.y = pack_f16x2_sat(f[2], f[3]);
+        u.z = pack_f16x2_sat(f[4], f[5]);
+        u.w = pack_f16x2_sat(f[6], f[7]);
+        *reinterpret_cast<uint4*>(sA1 + row * 128 + ((slice ^ (row & 7)) << 4)) = u;
+      }
+      signal();
+      FB_T(tr && slice == 0, 33);
       const float gl = a.gld ? __ldg(a.gld + grow) : a.gld_const;
+      mbar_wait(bar_d12, n_d12++ & 1);
+      tc_fence_after();
+      FB_T(tr && slice == 0, 34);
+      tanh_epilogue(sB1, sA1);                                 // h1 (kept for the tanh backward)
+      signal();
+      FB_T(tr && slice == 0, 35);
+      mbar_wait(bar_d12, n_d12++ & 1);
+      tc_fence_after();
+      FB_T(tr && slice == 0, 36);
+      tanh_epilogue(sB2, sA2);                                 // h2
+      signal();
+      FB_T(tr && slice == 0, 37);
+      // ---- the 8 chunks: adjoint of feature 4 c + slice
 #pragma unroll 1
       for (int c = 0; c < FB_NCHUNK; ++c, ++g) {
         const int f = c * FB_CF + slice;
@@ -469,8 +459,10 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
           xn = __ldg(reinterpret_cast<const float2*>(a.x + nrow * 64) + slice);
           gn = __ldg(reinterpret_cast<const float2*>(a.gout + nrow * 64) + slice);
         }
+        FB_T(tr, 64 + slice * 32 + c * 3);
         mbar_wait(&bar_d3f[g & 1], (g >> 1) & 1);
         tc_fence_after();
+        FB_T(tr, 64 + slice * 32 + c * 3 + 1);
         uint32_t v[24];
         const uint32_t ta = tmem + FB_T_D3 + (g & 1) * FB_NC + lane_sel + slice * FB_PC;
         tmem_ld16(ta, v);
@@ -479,10 +471,15 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_d3e[g & 1]);
-        float gxv, gp[24];
-        rqs_element_bwd8_lean<INV>(RegParams{v, sB3 + f * FB_PC}, a.cond_first ? xc.y : xc.x, gc.y, gl, a.c, gxv, gp);
-        gp[23] = 0.f;
-        gir[2 * f] = gxv;
+        float gxv, gD0, gD1;
+        int bin;
+        F2 gwh[8];
+        rqs_element_bwd8_packed<INV>(PairRegParams{v, sB3 + f * FB_PC}, a.cond_first ? xc.y : xc.x, a.gout_scale * gc.y, gl,
+                                     a.c, gxv, gwh, bin, gD0, gD1);
+        // input-order pair (the conditioning column's pass-through gradient now, its path through the conditioner is
+        // added at the end of the tile)
+        const float gcond = a.gout_scale * gc.x;
+        gir[f] = a.cond_first ? make_float2(gcond, gxv) : make_float2(gxv, gcond);
         // G of this pair of chunks: feature slot fs = (c & 1) * 4 + slice, 24 columns each, bf16, swizzled K-major.
         // The first chunk of a pair must not overwrite G before the previous pair's dH2 GEMM has read it.
         if ((c & 1) == 0) {
@@ -490,20 +487,81 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
           ++n_pair;
         }
         const int fs = (c & 1) * FB_CF + slice;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          uint4 u;
-          u.x = pack_bf16x2(gp[8 * j + 0], gp[8 * j + 1]);
-          u.y = pack_bf16x2(gp[8 * j + 2], gp[8 * j + 3]);
-          u.z = pack_bf16x2(gp[8 * j + 4], gp[8 * j + 5]);
-          u.w = pack_bf16x2(gp[8 * j + 6], gp[8 * j + 7]);
+        auto chunk_ptr = [&](int j) {
           const int ch = 3 * fs + j;
-          *reinterpret_cast<uint4*>(sG + (ch >> 3) * FB_KB_BYTES + row * 128 + (((ch & 7) ^ (row & 7)) << 4)) = u;
+          return sG + (ch >> 3) * FB_KB_BYTES + row * 128 + (((ch & 7) ^ (row & 7)) << 4);
+        };
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float l0, h0, l1, h1, l2, h2, l3, h3;
+          unpk2(gwh[4 * j + 0], l0, h0);
+          unpk2(gwh[4 * j + 1], l1, h1);
+          unpk2(gwh[4 * j + 2], l2, h2);
+          unpk2(gwh[4 * j + 3], l3, h3);
+          uint4 u;
+          u.x = pack_bf16x2(l0, h0);
+          u.y = pack_bf16x2(l1, h1);
+          u.z = pack_bf16x2(l2, h2);
+          u.w = pack_bf16x2(l3, h3);
+          *reinterpret_cast<uint4*>(chunk_ptr(j)) = u;
+        }
+        {
+          // derivative logits: only slots bin - 1 and bin are non-zero -- clear the 16-byte chunk, then drop the two
+          // bf16 values at their run-time positions (same thread, same addresses: program order holds)
+          unsigned char* dch = chunk_ptr(2);
+          *reinterpret_cast<uint4*>(dch) = make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t pr = pack_bf16x2(gD0, gD1);
+          if (bin > 0) *reinterpret_cast<unsigned short*>(dch + 2 * (bin - 1)) = (unsigned short)(pr & 0xffffu);
+          if (bin < 7) *reinterpret_cast<unsigned short*>(dch + 2 * bin) = (unsigned short)(pr >> 16);
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_gready);
+        FB_T(tr, 64 + slice * 32 + c * 3 + 2);
       }
+      if (it + 1 < my_tiles) {
+        const float4* x4 = reinterpret_cast<const float4*>(a.x + ((tile + stride) * FB_ROWS + row) * 64 + slice * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a1n[j] = __ldg(x4 + j);
+      }
+      // ---- dZ2 = dH2 (1 - h2^2), in place over h2 (every chunk GEMM has completed: bar_dh2 follows them)
+      mbar_wait(bar_dh2, it & 1);
+      tc_fence_after();
+      FB_T(tr && slice == 0, 38);
+      tanh_backward(FB_T_DH2, sA2);
+      signal();
+      FB_T(tr && slice == 0, 39);
+      // ---- dZ1 = dH1 (1 - h1^2), in place over h1
+      mbar_wait(bar_d12, n_d12++ & 1);
+      tc_fence_after();
+      FB_T(tr && slice == 0, 40);
+      tanh_backward(FB_T_D12, sA1);
+      signal();
+      FB_T(tr && slice == 0, 41);
+      // ---- the conditioning columns' path through the conditioner: features 8 slice .. 8 slice + 7 of this row, added
+      // to the pass-through gradients the adjoint threads stored (the mbarrier round trips order those stores first)
+      mbar_wait(bar_dx, it & 1);
+      tc_fence_after();
+      FB_T(tr && slice == 0, 42);
+      {
+        // dXc arrives row-per-lane; a 32 x 32 transpose per TMEM lane quadrant through the (now idle) G buffer turns the
+        // adds into feature-per-lane accesses: 8 sectors per instruction instead of 32
+        uint32_t v[8];
+        tmem_ld8(tmem + FB_T_DX + lane_sel + slice * 8, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        float* sT = reinterpret_cast<float*>(sG) + q * 1024;            // [32 rows][32 features], column ^ row swizzle
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sT[lane * 32 + ((slice * 8 + j) ^ lane)] = __uint_as_float(v[j]);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+        float* gq = a.gin + (tile * FB_ROWS + q * 32) * 64 + 2 * lane + (a.cond_first ? 0 : 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = slice * 8 + j;
+          fb_red_add(gq + (size_t)r * 64, sT[r * 32 + (lane ^ r)]);
+        }
+      }
+      FB_T(tr && slice == 0, 43);
     }
   }
   tc_fence_before();
@@ -521,8 +579,14 @@ RqsConsts make_rqs_consts(int K, float B);   // rqs_coupling.cu
 
 using namespace nfk;
 
-extern "C" int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, const float* grad_logdet, float grad_logdet_const,
-                                       float* grad_x, const void* w1_img, const void* w2_img, const void* w3_img,
+#ifdef FB_TRACE
+extern "C" int nfk_fused_bwd_trace_read(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, fb_trace, sizeof(long long) * 256);
+}
+#endif
+
+extern "C" int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, float grad_out_scale, const float* grad_logdet,
+                                       float grad_logdet_const, float* grad_x, const void* w1_img, const void* w2_img, const void* w3_img,
                                        const void* w3t_img, const void* w2t_img, const void* w1t_img, const float* b1,
                                        const float* b2, const float* b3, int64_t N, int mask_col, float B, int inverse,
                                        void* stream) {
@@ -542,6 +606,7 @@ extern "C" int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, co
   a.gout = grad_out;
   a.gld = grad_logdet;
   a.gld_const = grad_logdet_const;
+  a.gout_scale = grad_out_scale;
   a.gin = grad_x;
   a.w1_img = reinterpret_cast<const unsigned char*>(w1_img);
   a.w2_img = reinterpret_cast<const unsigned char*>(w2_img);
@@ -554,7 +619,6 @@ extern "C" int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, co
   a.b3 = b3;
   a.n_tiles = N / FB_ROWS;
   a.cond_first = (mask_col == 0);
-  a.inverse = inverse;
   a.c = make_rqs_consts(8, B);
   auto kern = inverse ? nsf_fused_bwd_kernel<true> : nsf_fused_bwd_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM);
@@ -564,7 +628,21 @@ extern "C" int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, co
   }
   const long long cap = sm_count();
   const long long grid = a.n_tiles < cap ? a.n_tiles : cap;
-  kern<<<(unsigned)grid, FB_THREADS, FB_SMEM, (cudaStream_t)stream>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(FB_THREADS);
+  cfg.dynamicSmemBytes = FB_SMEM;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see griddepcontrol.wait in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, a);
+  if (e != cudaSuccess) {
+    set_error("nsf_pairs_fused_bwd: launch failed: %s", cudaGetErrorString(e));
+    return NFK_ECUDA;
+  }
   count_launch();
   return check_launch("nsf_pairs_fused_bwd");
 }

@@ -416,4 +416,172 @@ __device__ __forceinline__ void rqs_element_bwd8_lean(const P& p, float x, float
   for (int i = 0; i < K - 1; ++i) gp[2 * K + i] = (i == k - 1 ? gD0 : 0.f) + (i == k ? gD1 : 0.f);
 }
 
+// ---- the same adjoint with the two sides PACKED (width side in the low, height side in the high half of fp32x2
+// registers: FFMA2 / FADD2 / FMUL2 do both softmax chains, forward and backward, in one instruction stream).  The raw
+// parameters arrive interleaved: v[2j] = width logit j, v[2j+1] = height logit j, v[16+i] = derivative logit i (the
+// one-launch layer backward permutes the rows of its W3 image accordingly), `b` the bias in the same order.
+// Differences from rqs_element_bwd8_lean, all inside the fast-math class: knots come from the prefix sums of the
+// normalised bins (knot_j = q0 cum_j + kstep j - B), and the dot product of the second softmax's backward is taken
+// from the two selected knots (sum_{i<k} b_i and b_k) instead of a sum over the bins.
+struct PairRegParams {
+  const uint32_t* v;
+  const float* b;
+  __device__ __forceinline__ F2 wh(int j) const {
+    F2 bias;
+    bias.u = *reinterpret_cast<const unsigned long long*>(b + 2 * j);
+    return add2(pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bias);
+  }
+  __device__ __forceinline__ float dyn(int i) const {
+    uint32_t r = v[16];
+#pragma unroll
+    for (int j = 1; j < 7; ++j)
+      if (i == j) r = v[16 + j];
+    return __uint_as_float(r) + b[16 + i];
+  }
+};
+
+__device__ __forceinline__ F2 sel2(bool p, F2 a, F2 b) {
+  F2 r;
+  r.u = p ? a.u : b.u;
+  return r;
+}
+
+// Outputs: gx_out = dL/dx (direct path), gwh[i] = (dL/d width logit i, dL/d height logit i), and the derivative-logit
+// gradients as (bin, gD0, gD1): dL/d derivative logit bin-1 = gD0, dL/d derivative logit bin = gD1, all others 0.
+template <bool INV>
+__device__ __forceinline__ void rqs_element_bwd8_packed(const PairRegParams& p, float x, float gy, float gl,
+                                                        const RqsConsts& c, float& gx_out, F2* gwh, int& bin,
+                                                        float& gD0_out, float& gD1_out) {
+  constexpr int K = 8;
+  const F2 zero2 = pk2(0.f, 0.f);
+  if (!((x >= c.negB) && (x <= c.B))) {            // identity tails (utils.py:42-43)
+    gx_out = gy;
+#pragma unroll
+    for (int i = 0; i < K; ++i) gwh[i] = zero2;
+    bin = 0;
+    gD0_out = 0.f;
+    gD1_out = 0.f;
+    return;
+  }
+  F2 A[K], Bv[K];
+  // ---- both double-softmax chains
+  {
+    F2 R[K];
+    float mw, mh;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      R[j] = p.wh(j);
+      float lo, hi;
+      unpk2(R[j], lo, hi);
+      mw = j ? fmaxf(mw, lo) : lo;
+      mh = j ? fmaxf(mh, hi) : hi;
+    }
+    const F2 l2e = pk2(LOG2E, LOG2E);
+    const F2 mm = mul2(pk2(-mw, -mh), l2e);
+    F2 s = zero2;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      A[j] = ex2_2(fma2(R[j], l2e, mm));
+      s = add2(s, A[j]);
+    }
+    float sw, sh;
+    unpk2(s, sw, sh);
+    const F2 rs = pk2(rcp_approx(sw), rcp_approx(sh));
+    const F2 g0 = pk2(c.g0, c.g0);
+    const F2 nm2 = mul2(pk2(-c.g0, -c.g0), rs);            // -2B log2(e) max_j a_j
+    F2 s2 = zero2;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      A[j] = mul2(A[j], rs);
+      Bv[j] = ex2_2(fma2(A[j], g0, nm2));
+      s2 = add2(s2, Bv[j]);
+    }
+    unpk2(s2, sw, sh);
+    const F2 rs2 = pk2(rcp_approx(sw), rcp_approx(sh));
+#pragma unroll
+    for (int j = 0; j < K; ++j) Bv[j] = mul2(Bv[j], rs2);
+  }
+  // ---- knots 1..7 of both sides, the bin, its two knots on each side
+  int k = 0;
+  F2 k0 = pk2(c.negB, c.negB), k1;
+  {
+    F2 kn[K];                                            // kn[j] = knot j (j = 1..7)
+    const F2 q0 = pk2(c.q0, c.q0);
+    F2 cum = zero2;
+#pragma unroll
+    for (int j = 1; j < K; ++j) {
+      cum = add2(cum, Bv[j - 1]);
+      const float off = fmaf(c.kstep, (float)j, c.negB);
+      kn[j] = fma2(cum, q0, pk2(off, off));
+      float lo, hi;
+      unpk2(kn[j], lo, hi);
+      k += (x >= (INV ? hi : lo)) ? 1 : 0;
+    }
+    k += (x >= c.Bnudge) ? 1 : 0;
+    k = min(k, K - 1);
+    k1 = kn[1];
+#pragma unroll
+    for (int i = 1; i < K; ++i)
+      if (k == i) {
+        k0 = kn[i];
+        k1 = (i + 1 < K) ? kn[i + 1] : pk2(c.B, c.B);
+      }
+  }
+  float c0, e0, c1, e1;
+  unpk2(k0, c0, e0);
+  unpk2(k1, c1, e1);
+  // ---- derivatives at the bin's ends: d = 1e-3 + softplus(D2), D2 = softplus(raw) inside, the padded constant at the
+  // boundary; each softplus shares its exponential with the sigmoid the backward needs
+  const float dr0 = p.dyn(max(k - 1, 0)), dr1 = p.dyn(min(k, K - 2));
+  auto sp_sg = [](float v, float& sp, float& sg) {      // softplus(v), sigmoid(v) from one ex2
+    const float e = ex2_approx(fminf(v, 30.f) * LOG2E), r = rcp_approx(1.f + e);
+    sp = v > 20.f ? v : LN2 * lg2_approx(1.f + e);
+    sg = e * r;
+  };
+  float D20, D21, s_dr0, s_dr1, sp0, sp1, s_D0, s_D1;
+  sp_sg(dr0, D20, s_dr0);
+  sp_sg(dr1, D21, s_dr1);
+  if (k == 0) D20 = c.edge_c;
+  if (k == K - 1) D21 = c.edge_c;
+  sp_sg(D20, sp0, s_D0);
+  sp_sg(D21, sp1, s_D1);
+  const float d0 = c.min_d + sp0, d1 = c.min_d + sp1;
+  float gxv, gc0, gc1, ge0, ge1, gd0, gd1;
+  rq_segment_bwd<true>(INV, x, c0, c1, e0, e1, d0, d1, gy, gl, gxv, gc0, gc1, ge0, ge1, gd0, gd1);
+  gx_out = gxv;
+  // ---- adjoint of both knot chains: knot_0 and knot_K are pinned constants
+  {
+    const bool first = (k == 0), last = (k == K - 1);
+    const F2 glo = pk2(first ? 0.f : gc0, first ? 0.f : ge0);
+    const F2 ghi = pk2(last ? 0.f : gc1, last ? 0.f : ge1);
+    const F2 q0 = pk2(c.q0, c.q0);
+    const F2 Y = mul2(q0, ghi);                          // dL/d b_i for i == k
+    const F2 X = fma2(q0, glo, Y);                       //            for i <  k   (0 for i > k)
+    // dot = sum_i b_i dL/db_i = X sum_{i<k} b_i + Y b_k, the sums read off the selected knots
+    const float rq0 = rcp_approx(c.q0);
+    const float offk = fmaf(c.kstep, (float)k, c.negB);
+    const F2 cumk = mul2(add2(k0, pk2(-offk, -offk)), pk2(rq0, rq0));
+    const F2 bk = mul2(add2(add2(k1, mul2(k0, pk2(-1.f, -1.f))), pk2(-c.kstep, -c.kstep)), pk2(rq0, rq0));
+    const F2 dot = fma2(X, cumk, mul2(Y, bk));
+    const F2 twoB = pk2(c.twoB, c.twoB);
+    const F2 ndot = mul2(dot, pk2(-1.f, -1.f));
+    const F2 XD = mul2(twoB, add2(X, ndot)), YD = mul2(twoB, add2(Y, ndot)), ZD = mul2(twoB, ndot);
+    F2 dot2 = zero2;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      F2 t = mul2(Bv[i], ZD);                            // dL/d a_i   (second softmax, W1 = 2B a)
+      if (i < k) t = mul2(Bv[i], XD);
+      if (i == k) t = mul2(Bv[i], YD);
+      gwh[i] = t;
+      dot2 = fma2(A[i], t, dot2);
+    }
+    const F2 ndot2 = mul2(dot2, pk2(-1.f, -1.f));
+#pragma unroll
+    for (int i = 0; i < K; ++i) gwh[i] = mul2(A[i], add2(gwh[i], ndot2));      // first softmax
+  }
+  bin = k;
+  gD0_out = (k > 0) ? gd0 * s_D0 * s_dr0 : 0.f;
+  gD1_out = (k < K - 1) ? gd1 * s_D1 * s_dr1 : 0.f;
+}
+
 }  // namespace nfk
