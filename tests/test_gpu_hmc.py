@@ -185,6 +185,9 @@ def test_fused_layer_backward_matches_fp32_autograd(inverse, mask, H, N):
     assert float(err.median()) <= 2e-3, float(err.median())
     assert float((err > 3e-2).float().mean()) <= 1e-2, float((err > 3e-2).float().mean())
     assert torch.equal(g_const, g_ones)                 # constant d logdet == a tensor of that constant
+    with torch.no_grad():                               # dL/d(out) = scale * g_out (the prior's -1/var folded into the launch)
+        g_scaled = _fused.layer_backward(lay, x, r * 4.0, s, 1.0, inverse, g_out_scale=0.25)
+    assert torch.equal(g_scaled, gin)                   # power-of-two scale: exact
     # rows are independent: the first 128 rows alone give the same gradient bit for bit
     with torch.no_grad():
         g_head = _fused.layer_backward(lay, x[:128], r[:128], s[:128], 1.0, inverse)

@@ -116,3 +116,25 @@ def test_tensor_core_gemms_issue_tcgen05():
         fn = next(k for k in res if tag in k)
         s = _sass(fn)
         assert _count(s, "UTCHMMA") >= 1, tag
+
+
+BWD = "_ZN3nfk20nsf_fused_bwd_kernelILb0EEEvNS_12FusedBwdArgsE"
+
+
+def test_layer_backward_kernel_instruction_mix_and_resources():
+    """csrc/nsf_fused_bwd.cu: every product on the tensor cores, weights through the TMA ring, both knot chains of the
+    adjoint in packed fp32x2, the conditioning-column adds as fire-and-forget reductions; 18 warps share four
+    sub-partitions (five on two of them), so 96 registers is the ceiling, with at most a few spilled loop counters."""
+    res = _usage()
+    for k in (BWD, BWD.replace("ILb0E", "ILb1E")):
+        assert res[k]["REG"] <= 96 and res[k]["STACK"] <= 32 and res[k]["LOCAL"] == 0, (k, res[k])
+    s = _sass(BWD)
+    # GEMM1 2 + GEMM2 4 + GEMM3 chunk 8 + dH2 K block 4 + dH1 4 + dXc 4 tcgen05.mma instructions in the issue loops
+    assert _count(s, "UTCHMMA") == 26, _count(s, "UTCHMMA")
+    assert _count(s, "UBLKCP") >= 2 and _count(s, "UBLKPF") == 2      # ring + W1 bulk copies, L2 prefetch of the next tile
+    assert _count(s, "LDTM") >= 6                      # two tanh epilogues, chunk parameters (x16 + x8), two tanh backwards, dXc
+    assert _count(s, "MUFU.TANH") == 64
+    assert _count(s, "FFMA2") >= 30 and _count(s, "FMUL2") >= 30 and _count(s, "FADD2") >= 25
+    assert _count(s, "REDG") == 8                      # conditioning-column gradient adds
+    mufu = _count(s, "MUFU.EX2") + _count(s, "MUFU.LG2") + _count(s, "MUFU.RCP")
+    assert 50 <= mufu <= 64, mufu                      # 32 ex2 of the double softmaxes + 4 x (ex2, lg2 | rcp) + the segment's divisions
