@@ -88,6 +88,8 @@ def test_tensor_core_force_matches_autograd_and_oracle():
     x = T(g["nsf.x"])
     assert _wide.flow_logp_and_grad(m, x.cuda()) is not None
     sim = FlowSimulation(m, n_chains=x.shape[0], init_pos=x)
+    sim.fused_grad = False          # this test is about the wide (multi-launch, bf16-operand) path; the one-launch path at
+    #                                 hidden width <= 128 has fp16 forward operands and its own test below
     U, F = sim.potential_and_force(sim.get_position())
     sim.tensor_core_grad = False
     for f in m.flows:
