@@ -263,13 +263,21 @@ int nfk_nsf_pairs_fused2(const float* x, float* out, float* logdet, const void* 
  * accumulator columns; transposed bf16 images: w3t_img [4][3][128 x 64] (pair of chunks p, K block: n = hidden
  * unit, k = parameter index within the pair, same order), w2t_img [2][128 x 64] (n = input unit, k = output unit),
  * w1t_img [2][32 x 64] (n = conditioning feature, k = hidden unit).
+ * tile_flags_in / tile_flags_out [N / 128] int32 or NULL: per-tile dependency between consecutive launches of a chain
+ * on one stream (rows are independent).  With tile_flags_out the launch sets flag t to 1 when rows [128 t, 128 t + 128)
+ * of grad_x are complete; with tile_flags_in it does NOT wait for the previous launch as a whole (programmatic
+ * dependent launch) but starts tile t when flag t is set, and clears the flag.  The caller zeroes the flags once
+ * before the chain and must pass the producer's tile_flags_out as the consumer's tile_flags_in; the first launch of
+ * a chain passes tile_flags_in = NULL (it waits for the stream), every other input of a flagged launch must be
+ * complete before that first launch.
  * Replaces autograd through NSF_CL.forward / inverse (nf/flows.py:227-253) for dL/dx, as the flow-preconditioned HMC
  * force evaluation needs it (nf/hmc.py:34-41, applications/src/systems.py:308-311). */
 int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, float grad_out_scale, const float* grad_logdet,
                             float grad_logdet_const, float* grad_x, const void* w1_img, const void* w2_img,
                             const void* w3_img, const void* w3t_img, const void* w2t_img,
                             const void* w1t_img, const float* b1, const float* b2, const float* b3,
-                            int64_t N, int mask_col, float B, int inverse, void* stream);
+                            int64_t N, int mask_col, float B, int inverse, int32_t* tile_flags_in /*nullable*/,
+                            int32_t* tile_flags_out /*nullable*/, void* stream);
 
 /* ---- wide conditioner path (hidden width > 128; the class default is 800, nf/flows.py:216):
  * persistent warp-specialised tcgen05 GEMM  Y = act(A W^T + b)  over operands stored in HBM as

@@ -200,6 +200,10 @@ def run(layer, x, inverse, logdet=None):
 # ---------------------------------------------------------------------------------------------
 # dL/dx of a fused layer in one launch (csrc/nsf_fused_bwd.cu): the HMC force path for hidden <= 128
 # ---------------------------------------------------------------------------------------------
+# consecutive backward launches of a flow depend on each other tile by tile instead of launch by launch (tools / tests)
+TILE_CHAIN = True
+
+
 def bwd_eligible(layer) -> bool:
     return (_lib.have("nfk_nsf_pairs_fused_bwd") and GENERATION == 2 and eligible(layer)
             and getattr(layer.psi, "precision", None) == "bf16")
@@ -244,9 +248,11 @@ def packed_bwd(layer):
     return pk
 
 
-def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=False, g_out_scale=1.0):
+def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=False, g_out_scale=1.0, flags_in=None,
+                   flags_out=None, keep_padding=False):
     """dL/dx [N, 64] of one bwd_eligible layer from the layer input x, dL/d(out) = g_out_scale * g_out and dL/d(log_det)
-    (a per-row tensor, or a constant for every row).  A partial last tile is zero-padded."""
+    (a per-row tensor, or a constant for every row).  A partial last tile is zero-padded.  flags_in / flags_out
+    ([N / 128] int32): per-tile dependency between the launches of a chain, see nfk_nsf_pairs_fused_bwd in include/nfk.h."""
     dev = require_cuda(x, g_out, g_logdet)
     x, g_out = f32c(x), f32c(g_out)
     N = x.shape[0]
@@ -269,10 +275,11 @@ def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=F
         call("nfk_nsf_pairs_fused_bwd", ptr(x), ptr(g_out), float(g_out_scale),
              ptr(f32c(g_logdet)) if g_logdet is not None else ptr(None), float(g_logdet_const), ptr(g_in), ptr(pk["w1"]),
              ptr(pk["w2"]), ptr(pb["w3"]), ptr(pb["w3t"]), ptr(pb["w2t"]), ptr(pb["w1t"]), ptr(pk["b1"]), ptr(pk["b2"]),
-             ptr(pb["b3"]), n_pad, layer._mask[0], float(layer.B), int(bool(inverse)), stream_ptr(dev))
+             ptr(pb["b3"]), n_pad, layer._mask[0], float(layer.B), int(bool(inverse)), ptr(flags_in), ptr(flags_out),
+             stream_ptr(dev))
         if ev is not None:
             tm.stop(ev, dev)
-    return g_in[:N]
+    return g_in if keep_padding else g_in[:N]
 
 
 def flow_logp_and_grad(model, x):
@@ -291,7 +298,20 @@ def flow_logp_and_grad(model, x):
         h, logdet = run(f, h, False, logdet)
     logp = _ops.gauss_logprob(h, var, add=logdet, add_sign=1.0)
     g, scale = h, -1.0 / var                                  # d log N(z; 0, var I) / dz = -z / var, applied by the first launch
-    for f, xin in zip(reversed(model.flows), reversed(inputs)):
-        g = layer_backward(f, xin, g, None, 1.0, False, scale)
+    N, L = h.shape[0], len(model.flows)
+    flags = None
+    if TILE_CHAIN and N % ROWS == 0 and L > 1:
+        # per-tile dependency between consecutive backward launches (rows are independent): a launch starts on the SMs
+        # the previous one has already left instead of waiting for its last wave
+        key = (h.device, N // ROWS, L)
+        cache = getattr(model, "_fused_tile_flags", None)
+        if cache is None or cache[0] != key:
+            cache = model._fused_tile_flags = (key, torch.zeros((L, N // ROWS), dtype=torch.int32, device=h.device))
+        flags = cache[1]
+        flags.zero_()
+    for i, (f, xin) in enumerate(zip(reversed(model.flows), reversed(inputs))):
+        f_in = flags[i - 1] if (flags is not None and i > 0) else None
+        f_out = flags[i] if (flags is not None and i + 1 < L) else None
+        g = layer_backward(f, xin, g, None, 1.0, False, scale, f_in, f_out)
         scale = 1.0
     return logp, g

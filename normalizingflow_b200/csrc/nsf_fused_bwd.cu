@@ -65,8 +65,19 @@ struct FusedBwdArgs {
   const float* b3;                // [32][24] in the order of w3_img's rows
   long long n_tiles;
   int cond_first;
+  int* flag_in;           // [n_tiles] or null: tile t may start when flag_in[t] != 0 (set by the launch that produces gout)
+  int* flag_out;          // [n_tiles] or null: set to 1 when tile t of gin is complete
   RqsConsts c;
 };
+
+__device__ __forceinline__ int fb_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fb_st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ bool fb_elect_one() {
   uint32_t pred;
@@ -146,7 +157,11 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
   }
   // Programmatic dependent launch (as nsf_fused2.cu): this grid may be scheduled while the previous kernel of the stream
   // drains; nothing in global memory is touched before the wait, and the trigger lets the next launch do the same.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // With tile flags the dependency on the previous launch is per TILE (rows are independent: tile t of this layer needs
+  // only tile t of dL/d(out)), so this grid's CTAs start on the SMs the previous launch has already left -- at 65,536
+  // rows (3.46 tiles per SM) that turns the four waves of every launch into 3.5.  Everything else this kernel reads
+  // (x, the weight images) was complete before the first launch of the chain, which waits for the whole stream.
+  if (a.flag_in == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;");
   for (int i = tid; i < FB_HP; i += FB_THREADS) {
     sB1[i] = a.b1[i];
@@ -393,11 +408,7 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
     };
     // x / dL/d(out) pairs are fetched one chunk ahead (across tiles too), so their latency hides behind an adjoint
     float2 xn = make_float2(0.f, 0.f), gn = xn;
-    if (my_tiles) {
-      const size_t grow0 = (size_t)first * FB_ROWS + row;
-      xn = __ldg(reinterpret_cast<const float2*>(a.x + grow0 * 64) + slice);
-      gn = __ldg(reinterpret_cast<const float2*>(a.gout + grow0 * 64) + slice);
-    }
+    if (my_tiles) xn = __ldg(reinterpret_cast<const float2*>(a.x + ((size_t)first * FB_ROWS + row) * 64) + slice);
     // the 8 pairs whose conditioning columns this thread turns into the A1 operand, fetched before the previous tile's
     // tail (the waits on its last three GEMMs hide the latency)
     float4 a1n[4];
@@ -415,6 +426,13 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
       const bool tr = blockIdx.x == 0 && it == 1 && q == 0;
       (void)tr;
       FB_T(tr && slice == 0, 32);
+      // ---- dL/d(out) of this tile is complete (per-tile dependency on the producing launch), first pair of it
+      if (a.flag_in != nullptr) {
+        if (lane == 0)
+          while (fb_ld_acquire(a.flag_in + tile) == 0) __nanosleep(64);
+        __syncwarp();
+      }
+      gn = __ldcg(gor + slice);
       // ---- A1: conditioning columns of features 8 slice .. 8 slice + 7 of this row (fp16, K block 0, chunk `slice`)
       {
         float f[8];
@@ -453,11 +471,9 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
         const float2 xc = xn, gc = gn;
         if (c + 1 < FB_NCHUNK) {
           xn = __ldg(xr + f + FB_CF);
-          gn = __ldg(gor + f + FB_CF);
+          gn = __ldcg(gor + f + FB_CF);
         } else if (it + 1 < my_tiles) {
-          const size_t nrow = (tile + stride) * FB_ROWS + row;
-          xn = __ldg(reinterpret_cast<const float2*>(a.x + nrow * 64) + slice);
-          gn = __ldg(reinterpret_cast<const float2*>(a.gout + nrow * 64) + slice);
+          xn = __ldg(reinterpret_cast<const float2*>(a.x + ((tile + stride) * FB_ROWS + row) * 64) + slice);
         }
         FB_T(tr, 64 + slice * 32 + c * 3);
         mbar_wait(&bar_d3f[g & 1], (g >> 1) & 1);
@@ -562,6 +578,16 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
         }
       }
       FB_T(tr && slice == 0, 43);
+      if (a.flag_in != nullptr || a.flag_out != nullptr) {
+        // every work thread's stores and reductions of this tile are ordered before the flag (fence, CTA barrier of the
+        // work warps, release store); the consumed input flag returns to 0 for the next chain of launches
+        __threadfence();
+        asm volatile("bar.sync 5, 512;" ::: "memory");
+        if (tid == 0) {
+          if (a.flag_in != nullptr) a.flag_in[tile] = 0;
+          if (a.flag_out != nullptr) fb_st_release(a.flag_out + tile, 1);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -589,7 +615,7 @@ extern "C" int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, fl
                                        float grad_logdet_const, float* grad_x, const void* w1_img, const void* w2_img, const void* w3_img,
                                        const void* w3t_img, const void* w2t_img, const void* w1t_img, const float* b1,
                                        const float* b2, const float* b3, int64_t N, int mask_col, float B, int inverse,
-                                       void* stream) {
+                                       int32_t* tile_flags_in, int32_t* tile_flags_out, void* stream) {
   NFK_REQUIRE(N >= 0 && N % FB_ROWS == 0, "nsf_pairs_fused_bwd: N must be a multiple of %d (got %lld)", FB_ROWS, (long long)N);
   NFK_REQUIRE(mask_col == 0 || mask_col == 1, "nsf_pairs_fused_bwd: mask column must be 0 or 1");
   NFK_REQUIRE(B > 0.f, "nsf_pairs_fused_bwd: tail bound must be positive");
@@ -619,6 +645,8 @@ extern "C" int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, fl
   a.b3 = b3;
   a.n_tiles = N / FB_ROWS;
   a.cond_first = (mask_col == 0);
+  a.flag_in = tile_flags_in;
+  a.flag_out = tile_flags_out;
   a.c = make_rqs_consts(8, B);
   auto kern = inverse ? nsf_fused_bwd_kernel<true> : nsf_fused_bwd_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM);

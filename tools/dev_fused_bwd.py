@@ -62,6 +62,25 @@ def whole_flow(C=65536, H=128):
         b = _wide.flow_logp_and_grad(m, x)
     assert a is not None and b is not None
     torch.cuda.synchronize()
+    _fused.TILE_CHAIN = False
+    with torch.no_grad():
+        a2 = _fused.flow_logp_and_grad(m, x)
+    torch.cuda.synchronize()
+    print("tile-chained launches == launch-by-launch dependency, bitwise:", bool(torch.equal(a[1], a2[1])), flush=True)
+    for chain in (False, True):
+        _fused.TILE_CHAIN = chain
+        with torch.no_grad():
+            for _ in range(3):
+                _fused.flow_logp_and_grad(m, x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                r = _fused.flow_logp_and_grad(m, x)
+            e1.record()
+            torch.cuda.synchronize()
+        print(f"   TILE_CHAIN={chain}: {e0.elapsed_time(e1) / 20:.3f} ms per evaluation; equal to first: {bool(torch.equal(r[1], a[1]))}", flush=True)
+    _fused.TILE_CHAIN = True
     sc = float(b[1].abs().max())
     print(f"flow: logp fused vs wide max abs {float((a[0] - b[0]).abs().max()):.2e}; force max abs diff "
           f"{float((a[1] - b[1]).abs().max()):.2e} (scale {sc:.2e}), median {float((a[1] - b[1]).abs().median()):.2e}", flush=True)
