@@ -251,6 +251,19 @@ int nfk_nsf_pairs_fused2(const float* x, float* out, float* logdet, const void* 
                          int accumulate, int arith, int split, float* dbg_params /*nullable*/,
                          int8_t* dbg_bins /*nullable*/, void* stream);
 
+/* The same launch as one link of a CHAIN of layer launches over the same rows on one stream (a whole flow, forward or
+ * inverse): tile_flags_in / tile_flags_out [N / 128] int32 or NULL make the dependency between consecutive launches
+ * per 128-row tile instead of per launch (rows are independent, nf/models.py:16-18).  With tile_flags_out the launch
+ * sets flag t to 1 when rows [128 t, 128 t + 128) of out and logdet are complete; with tile_flags_in it does not wait
+ * for the previous launch as a whole but takes tile t when flag t is set, and clears it.  The caller zeroes the flags
+ * before the chain, passes each producer's tile_flags_out as the next launch's tile_flags_in, and NULL as the first
+ * launch's tile_flags_in (that launch waits for the stream); weight images and biases must be complete before it. */
+int nfk_nsf_pairs_fused2_chain(const float* x, float* out, float* logdet, const void* w1_img, const void* w2_img,
+                               const void* w3_img, const float* b1, const float* b2, const float* b3, int64_t N,
+                               int mask_col, float B, int inverse, int accumulate, int arith, int split,
+                               float* dbg_params /*nullable*/, int8_t* dbg_bins /*nullable*/,
+                               int32_t* tile_flags_in /*nullable*/, int32_t* tile_flags_out /*nullable*/, void* stream);
+
 /* Gradient of one fused layer w.r.t. its input in ONE launch (csrc/nsf_fused_bwd.cu; hidden <= 128, size 32, dim 2,
  * K 8): recomputes the conditioner with the forward kernel's fp16 operands (same parameters, bit for bit), runs the
  * spline adjoint per element in registers, the three dgrad GEMMs (bf16 operands) and the tanh backward on chip.

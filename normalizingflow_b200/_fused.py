@@ -87,9 +87,14 @@ def packed_split(layer):
     return pk
 
 
-def _launch(layer, pk, x, out, logdet, n, inverse, accumulate, split, dbg_p=None, dbg_b=None):
+def _launch(layer, pk, x, out, logdet, n, inverse, accumulate, split, dbg_p=None, dbg_b=None, flags_in=None, flags_out=None):
     dev = x.device
-    if GENERATION == 2 or split:
+    if flags_in is not None or flags_out is not None:
+        call("nfk_nsf_pairs_fused2_chain", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
+             ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), n, layer._mask[0], float(layer.B), int(bool(inverse)),
+             int(accumulate), _ops._arith(layer.arith), int(split), ptr(dbg_p), ptr(dbg_b), ptr(flags_in), ptr(flags_out),
+             stream_ptr(dev))
+    elif GENERATION == 2 or split:
         call("nfk_nsf_pairs_fused2", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
              ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), n, layer._mask[0], float(layer.B), int(bool(inverse)),
              int(accumulate), _ops._arith(layer.arith), int(split), ptr(dbg_p), ptr(dbg_b), stream_ptr(dev))
@@ -161,9 +166,10 @@ def run_debug(layer, x, inverse):
     return out[:n_real], logdet[:n_real], params[:n_real, :, :23].contiguous(), bins[:n_real]
 
 
-def run(layer, x, inverse, logdet=None):
+def run(layer, x, inverse, logdet=None, flags_in=None, flags_out=None):
     """(out, logdet) of one NSF_CL layer through the fused kernel (whole 128-row tiles; a partial last
-    tile is padded)."""
+    tile is padded).  flags_in / flags_out ([N / 128] int32, N a multiple of 128): per-tile dependency between the
+    launches of a chain, see nfk_nsf_pairs_fused2_chain in include/nfk.h."""
     dev = require_cuda(x, logdet)
     x = f32c(x)
     N = x.shape[0]
@@ -177,7 +183,7 @@ def run(layer, x, inverse, logdet=None):
         with torch.cuda.device(dev):
             tm = _ops.KERNEL_TIMER
             ev = tm.start("nsf_pairs_fused3x" if _is_split(layer) else "nsf_pairs_fused", dev) if tm is not None else None
-            _launch(layer, pk, x, out, logdet, n_main, inverse, accumulate, _is_split(layer))
+            _launch(layer, pk, x, out, logdet, n_main, inverse, accumulate, _is_split(layer), None, None, flags_in, flags_out)
             if ev is not None:
                 tm.stop(ev, dev)
     if n_main < N:
@@ -291,27 +297,27 @@ def flow_logp_and_grad(model, x):
     if var is None or len(model.flows) == 0 or not all(isinstance(f, NSF_CL) and f.fused and bwd_eligible(f) for f in model.flows):
         return None
     h = f32c(x.detach())
-    logdet = torch.zeros(h.shape[0], dtype=torch.float32, device=h.device)
-    inputs = []
-    for f in model.flows:
-        inputs.append(h)
-        h, logdet = run(f, h, False, logdet)
-    logp = _ops.gauss_logprob(h, var, add=logdet, add_sign=1.0)
-    g, scale = h, -1.0 / var                                  # d log N(z; 0, var I) / dz = -z / var, applied by the first launch
     N, L = h.shape[0], len(model.flows)
-    flags = None
-    if TILE_CHAIN and N % ROWS == 0 and L > 1:
-        # per-tile dependency between consecutive backward launches (rows are independent): a launch starts on the SMs
-        # the previous one has already left instead of waiting for its last wave
+    logdet = torch.zeros(N, dtype=torch.float32, device=h.device)
+    fw = bw = None
+    if TILE_CHAIN and N % ROWS == 0 and L > 1 and GENERATION == 2 and _lib.have("nfk_nsf_pairs_fused2_chain"):
+        # per-tile dependency between consecutive launches of the forward chain and of the backward chain (rows are
+        # independent): a launch starts on the SMs the previous one has already left instead of waiting for its last wave
         key = (h.device, N // ROWS, L)
         cache = getattr(model, "_fused_tile_flags", None)
         if cache is None or cache[0] != key:
-            cache = model._fused_tile_flags = (key, torch.zeros((L, N // ROWS), dtype=torch.int32, device=h.device))
-        flags = cache[1]
-        flags.zero_()
+            cache = model._fused_tile_flags = (key, torch.zeros((2, L, N // ROWS), dtype=torch.int32, device=h.device))
+        cache[1].zero_()
+        fw, bw = cache[1][0], cache[1][1]
+    inputs = []
+    for i, f in enumerate(model.flows):
+        inputs.append(h)
+        h, logdet = run(f, h, False, logdet, fw[i - 1] if (fw is not None and i > 0) else None,
+                        fw[i] if (fw is not None and i + 1 < L) else None)
+    logp = _ops.gauss_logprob(h, var, add=logdet, add_sign=1.0)
+    g, scale = h, -1.0 / var                                  # d log N(z; 0, var I) / dz = -z / var, applied by the first launch
     for i, (f, xin) in enumerate(zip(reversed(model.flows), reversed(inputs))):
-        f_in = flags[i - 1] if (flags is not None and i > 0) else None
-        f_out = flags[i] if (flags is not None and i + 1 < L) else None
-        g = layer_backward(f, xin, g, None, 1.0, False, scale, f_in, f_out)
+        g = layer_backward(f, xin, g, None, 1.0, False, scale, bw[i - 1] if (bw is not None and i > 0) else None,
+                           bw[i] if (bw is not None and i + 1 < L) else None)
         scale = 1.0
     return logp, g

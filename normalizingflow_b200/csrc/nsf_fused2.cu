@@ -68,8 +68,19 @@ struct Fused2Args {
   int accumulate;
   float* dbg_params;
   signed char* dbg_bins;
+  int* flag_in;                  // [n_tiles] or null: tile t of x is complete when flag_in[t] != 0 (per-tile dependency on the producing launch)
+  int* flag_out;                 // [n_tiles] or null: set to 1 when tile t of out / logdet is complete
   RqsConsts c;
 };
+
+__device__ __forceinline__ int f2_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void f2_st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ bool f2_elect_one() {
   uint32_t pred;
@@ -202,7 +213,11 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
   // (the previous layer) was still draining -- its CTAs start on each SM as soon as that SM's CTA exits, with
   // barrier init and TMEM allocation already done.  Nothing in global memory is touched before this wait; the
   // trigger lets the NEXT layer's grid do the same behind this one.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // With tile flags (a chain of layer launches over the same rows) the dependency is per TILE instead: this grid does
+  // not wait for the previous launch as a whole, its CTAs start on the SMs that launch has already left and take a
+  // tile when its flag is set (rows are independent).  Everything else read here (weight images, biases) was complete
+  // before the first launch of the chain, which waits for the stream.
+  if (a.flag_in == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;");
   for (int i = tid; i < F2_HP; i += F2_THREADS) {
     sB1[i] = a.b1[i];
@@ -476,10 +491,25 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
     auto load_rows = [&](unsigned it2) {
       const size_t tile2 = first + (size_t)it2 * stride;
       const int s = it2 & 1;
+      if (a.flag_in != nullptr) {                                        // the producing launch has finished this tile
+        if (lane == 0)
+          while (f2_ld_acquire(a.flag_in + tile2) == 0) __nanosleep(64);
+        __syncwarp();
+        fence_proxy_async();                                             // ... and the bulk copy below (async proxy) sees it
+      }
       if (lane == 0) mbar_expect_tx(&bar_x[s], 8 * F2_XROW_BYTES);       // arrive (1 of 16) + expect
       __syncwarp();
       if (lane < 8)
         bulk_g2s(sX + (s * F2_ROWS + myrow) * F2_XLD, a.x + (tile2 * F2_ROWS + myrow) * 64, F2_XROW_BYTES, &bar_x[s]);
+    };
+    // tile `t_` of out / logdet is complete: the bulk stores of the 128 row-moving lanes have been performed, every
+    // thread's writes are fenced, then one release store of the flag (tile-flag chains only)
+    auto publish = [&](size_t t_) {
+      if (lane < 8) bulk_wait_all<0>();
+      fence_proxy_async();
+      __threadfence();
+      asm volatile("bar.sync 5, 512;" ::: "memory");
+      if (tid == 0) f2_st_release(a.flag_out + t_, 1);
     };
     if (my_tiles) load_rows(0);
     if (my_tiles > 1) load_rows(1);
@@ -488,11 +518,14 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
       const size_t tile = first + (size_t)it * stride;
       float* xs = sX + (it & 1) * F2_ROWS * F2_XLD;
       float ld_old = 0.f;
-      if (lane < 8 && a.accumulate) ld_old = __ldg(a.logdet + tile * F2_ROWS + myrow);
+      if (lane < 8 && a.accumulate) ld_old = __ldcg(a.logdet + tile * F2_ROWS + myrow);
       mbar_wait(&bar_x[it & 1], (it >> 1) & 1);
       float lad_acc = 0.f;
 #pragma unroll 1
       for (int c = 0; c < F2_NCHUNK; ++c, ++g) {
+        // the previous tile's rows have long left shared memory by now: publish it (deferred so that nobody waits on
+        // the bulk stores)
+        if (c == 1 && it > 0 && a.flag_out != nullptr) publish(tile - stride);
         mbar_wait_idle(&bar_d3f[g & 1], (g >> 1) & 1, 200);   // suspended probe: a waiting warp leaves the issue port to the other three
         tc_fence_after();
         const int f = c * F2_CF + slice;
@@ -529,6 +562,7 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
         bulk_s2g(a.out + (tile * F2_ROWS + myrow) * 64, xs + myrow * F2_XLD, F2_XROW_BYTES);
         bulk_commit();
       }
+      if (a.flag_in != nullptr && tid == 0) a.flag_in[tile] = 0;      // consumed: back to 0 for the next chain of launches
       // refill this buffer with tile it + 2 as soon as the store has read it
       if (it + 2 < my_tiles) {
         if (lane < 8) bulk_wait_read<0>();
@@ -537,6 +571,7 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
       }
     }
     if (lane < 8) bulk_wait_all<0>();
+    if (my_tiles && a.flag_out != nullptr) publish(first + (size_t)(my_tiles - 1) * stride);
   }
   tc_fence_before();
   __syncthreads();
@@ -602,6 +637,15 @@ extern "C" int nfk_nsf_pairs_fused2(const float* x, float* out, float* logdet, c
                                     const void* w3_img, const float* b1, const float* b2, const float* b3, int64_t N,
                                     int mask_col, float B, int inverse, int accumulate, int arith, int split,
                                     float* dbg_params, int8_t* dbg_bins, void* stream) {
+  return nfk_nsf_pairs_fused2_chain(x, out, logdet, w1_img, w2_img, w3_img, b1, b2, b3, N, mask_col, B, inverse, accumulate,
+                                    arith, split, dbg_params, dbg_bins, nullptr, nullptr, stream);
+}
+
+extern "C" int nfk_nsf_pairs_fused2_chain(const float* x, float* out, float* logdet, const void* w1_img, const void* w2_img,
+                                          const void* w3_img, const float* b1, const float* b2, const float* b3, int64_t N,
+                                          int mask_col, float B, int inverse, int accumulate, int arith, int split,
+                                          float* dbg_params, int8_t* dbg_bins, int32_t* tile_flags_in,
+                                          int32_t* tile_flags_out, void* stream) {
   NFK_REQUIRE(N >= 0 && N % F2_ROWS == 0, "nsf_pairs_fused2: N must be a multiple of %d (got %lld)", F2_ROWS, (long long)N);
   NFK_REQUIRE(mask_col == 0 || mask_col == 1, "nsf_pairs_fused2: mask column must be 0 or 1");
   NFK_REQUIRE(arith >= NFK_ARITH_EXACT && arith <= NFK_ARITH_FAST, "nsf_pairs_fused2: bad arith %d", arith);
@@ -628,6 +672,8 @@ extern "C" int nfk_nsf_pairs_fused2(const float* x, float* out, float* logdet, c
   a.accumulate = accumulate;
   a.dbg_params = dbg_params;
   a.dbg_bins = reinterpret_cast<signed char*>(dbg_bins);
+  a.flag_in = tile_flags_in;
+  a.flag_out = tile_flags_out;
   a.c = make_rqs_consts(8, B);
   cudaStream_t st = (cudaStream_t)stream;
   const bool inv = inverse != 0;

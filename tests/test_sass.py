@@ -127,7 +127,7 @@ def test_layer_backward_kernel_instruction_mix_and_resources():
     sub-partitions (five on two of them), so 96 registers is the ceiling, with at most a few spilled loop counters."""
     res = _usage()
     for k in (BWD, BWD.replace("ILb0E", "ILb1E")):
-        assert res[k]["REG"] <= 96 and res[k]["STACK"] <= 32 and res[k]["LOCAL"] == 0, (k, res[k])
+        assert res[k]["REG"] <= 96 and res[k]["STACK"] <= 64 and res[k]["LOCAL"] == 0, (k, res[k])
     s = _sass(BWD)
     # GEMM1 2 + GEMM2 4 + GEMM3 chunk 8 + dH2 K block 4 + dH1 4 + dXc 4 tcgen05.mma instructions in the issue loops
     assert _count(s, "UTCHMMA") == 26, _count(s, "UTCHMMA")
