@@ -78,8 +78,8 @@ def test_fused_layer_kernel_instruction_mix():
     assert _count(s, "MUFU.EX2") <= 34 + 16 and _count(s, "MUFU.LG2") == 3
 
 
-FUSED2 = "_ZN3nfk17nsf_fused2_kernelILi2ELb0ELb0ELb0EEEvNS_10Fused2ArgsE"        # FAST, forward, fp16 operands, production
-FUSED2_SPLIT = "_ZN3nfk17nsf_fused2_kernelILi1ELb0ELb1ELb0EEEvNS_10Fused2ArgsE"  # HYBRID, forward, split operands
+FUSED2 = "_ZN3nfk17nsf_fused2_kernelILi2ELb0ELb0ELb0ELb0EEEvNS_10Fused2ArgsE"        # FAST, forward, fp16 operands, production
+FUSED2_SPLIT = "_ZN3nfk17nsf_fused2_kernelILi1ELb0ELb1ELb0ELb0EEEvNS_10Fused2ArgsE"  # HYBRID, forward, split operands
 
 
 def test_second_generation_fused_kernel():
