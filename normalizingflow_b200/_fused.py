@@ -288,7 +288,7 @@ def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=F
     return g_in if keep_padding else g_in[:N]
 
 
-def flow_logp_and_grad(model, x):
+def flow_logp_and_grad(model, x, need_logp=True):
     """log p(x) [N] and d log p / dx [N, d] through a flow whose layers are all bwd_eligible, under an isotropic Gaussian
     prior: one forward launch per layer (keeping each layer's input), the log-prob reduction, one backward launch per layer; None when the
     model does not qualify."""
@@ -299,6 +299,9 @@ def flow_logp_and_grad(model, x):
     h = f32c(x.detach())
     N, L = h.shape[0], len(model.flows)
     logdet = torch.zeros(N, dtype=torch.float32, device=h.device)
+    for f in model.flows:          # every operand image exists BEFORE the first launch of the chain: a flagged launch does
+        packed(f)                  # not wait for the stream, so nothing but flagged tiles may be produced inside the chain
+        packed_bwd(f)
     fw = bw = None
     if TILE_CHAIN and N % ROWS == 0 and L > 1 and GENERATION == 2 and _lib.have("nfk_nsf_pairs_fused2_chain"):
         # per-tile dependency between consecutive launches of the forward chain and of the backward chain (rows are
@@ -309,15 +312,18 @@ def flow_logp_and_grad(model, x):
             cache = model._fused_tile_flags = (key, torch.zeros((2, L, N // ROWS), dtype=torch.int32, device=h.device))
         cache[1].zero_()
         fw, bw = cache[1][0], cache[1][1]
+    # without the log-prob reduction between them (need_logp = False: a leapfrog step inside a trajectory only needs the
+    # force) the first backward launch hangs on the last forward launch tile by tile as well
+    join = fw is not None and not need_logp
     inputs = []
     for i, f in enumerate(model.flows):
         inputs.append(h)
         h, logdet = run(f, h, False, logdet, fw[i - 1] if (fw is not None and i > 0) else None,
-                        fw[i] if (fw is not None and i + 1 < L) else None)
-    logp = _ops.gauss_logprob(h, var, add=logdet, add_sign=1.0)
+                        fw[i] if (fw is not None and (i + 1 < L or join)) else None)
+    logp = _ops.gauss_logprob(h, var, add=logdet, add_sign=1.0) if need_logp else None
     g, scale = h, -1.0 / var                                  # d log N(z; 0, var I) / dz = -z / var, applied by the first launch
     for i, (f, xin) in enumerate(zip(reversed(model.flows), reversed(inputs))):
-        g = layer_backward(f, xin, g, None, 1.0, False, scale, bw[i - 1] if (bw is not None and i > 0) else None,
-                           bw[i] if (bw is not None and i + 1 < L) else None)
+        f_in = (bw[i - 1] if i > 0 else (fw[L - 1] if join else None)) if bw is not None else None
+        g = layer_backward(f, xin, g, None, 1.0, False, scale, f_in, bw[i] if (bw is not None and i + 1 < L) else None)
         scale = 1.0
     return logp, g

@@ -164,21 +164,23 @@ class FlowSimulation:
     def get_potential(self, x=None):
         return self.potential(self.position if x is None else x)
 
-    def potential_and_force(self, q):
-        """U(q) [C] and F(q) = -grad U = grad log p [C, d] — one forward + one backward through the flow."""
+    def potential_and_force(self, q, need_potential=True):
+        """U(q) [C] and F(q) = -grad U = grad log p [C, d] — one forward + one backward through the flow.  With
+        need_potential = False (the interior evaluations of a trajectory) the one-launch-per-layer path skips the
+        log-prob reduction and returns None for U."""
         from . import _fused, _wide
         fast = None
         if self.tensor_core_grad:
             # hidden width <= 128: one forward and one backward launch per layer (csrc/nsf_fused2.cu,
             # csrc/nsf_fused_bwd.cu); wider conditioners: the forward keeps the hidden activations, backward =
             # spline adjoint as a GEMM epilogue + dgrad GEMMs on the tensor cores (csrc/gemm_ws.cu); no autograd graph
-            fast = _fused.flow_logp_and_grad(self.model, q) if self.fused_grad else None
+            fast = _fused.flow_logp_and_grad(self.model, q, need_potential) if self.fused_grad else None
             if fast is None:
                 fast = _wide.flow_logp_and_grad(self.model, q)
         if fast is not None:
             logp, force = fast
             self.grad_evals += 1
-            return -logp, force
+            return (-logp if logp is not None else None), force
         params = [p for p in self.model.parameters() if p.requires_grad]
         for p in params:
             p.requires_grad_(False)              # dgrad only: no weight gradients in the leapfrog
@@ -196,10 +198,10 @@ class FlowSimulation:
 
     # ---- whole trajectory as one CUDA graph -------------------------------------------------
     def _trajectory(self, q, p, path_len, dt):
-        pot, force = self.potential_and_force(q)
-        for _ in range(path_len):
+        pot, force = self.potential_and_force(q, need_potential=(path_len == 0))
+        for i in range(path_len):
             _ops.leapfrog_kick_drift(q, p, force, dt, self.inv_mass)
-            pot, force = self.potential_and_force(q)
+            pot, force = self.potential_and_force(q, need_potential=(i == path_len - 1))   # only the end point's U is used
             _ops.leapfrog_kick(p, force, dt)
         return pot
 

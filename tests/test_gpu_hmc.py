@@ -230,6 +230,30 @@ def test_fused_force_path_is_used_and_matches_the_wide_path_and_the_oracle():
     assert float((err > 3e-2).float().mean()) <= 3e-2, float((err > 3e-2).float().mean())
 
 
+def test_tile_chained_launches_equal_launch_by_launch_dependency_bitwise():
+    """65,536 x 64 rows would be the production shape; 3 x 148 + 5 tiles are enough to have CTAs with different
+    tile counts.  With tile flags a launch starts tile t when the producing launch has finished tile t (rows are
+    independent): forces and log-probs must not change by a bit, with and without the log-prob reduction in the
+    middle of the chain, and the flags must be back at zero afterwards."""
+    from normalizingflow_b200 import _fused
+    m = _model(precision="bf16")
+    N = (3 * 148 + 5) * 128
+    x = 0.8 * torch.randn(N, 64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    try:
+        _fused.TILE_CHAIN = False
+        lp0, g0 = _fused.flow_logp_and_grad(m, x)
+        _fused.TILE_CHAIN = True
+        for _ in range(3):
+            lp1, g1 = _fused.flow_logp_and_grad(m, x)
+            lp2, g2 = _fused.flow_logp_and_grad(m, x, need_logp=False)
+            assert lp2 is None
+            assert torch.equal(lp0, lp1) and torch.equal(g0, g1) and torch.equal(g0, g2)
+        torch.cuda.synchronize()
+        assert int(m._fused_tile_flags[1].abs().sum()) == 0
+    finally:
+        _fused.TILE_CHAIN = True
+
+
 def test_single_chain_eager_rejection_restores_the_position():
     """n_chains = 1 on the eager integrator (fp32 conditioner): HMC keeps references to the position it
     last accepted (nf/hmc.py:36, :58), so the integrator must not advance that tensor in place -- a
