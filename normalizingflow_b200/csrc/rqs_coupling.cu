@@ -28,6 +28,7 @@ struct CouplingArgs {
   long long n_tiles;   // tiled kernel: number of full tiles
   long long row0;      // rows kernel: first row
   int size, dim, n_mask, n_unm, d, F_t, P, R, stages, accumulate;
+  int scratch;         // streaming kernel: per-warp log-det ring, a power of two >= F_t + 32 (floats)
   int mask[MAXDIM];
   int unm[MAXDIM];
   RqsConsts c;
@@ -146,6 +147,153 @@ rqs_coupling_tiled(const __grid_constant__ CouplingArgs a) {
     }
   }
   if (tid == 0) bulk_wait_all<0>();
+}
+
+// Generic geometry, K = 8, second generation: every WARP is its own pipeline, there is no CTA-wide barrier.
+// A warp owns groups of G consecutive rows, G = 32 / gcd(F_t, 32), so a group is a whole number of 32-element
+// blocks whose (3K-1) x 32 parameters are one contiguous, 16-byte aligned span: lane 0 streams them through the
+// warp's private TMA bulk-copy ring (S stages, S - 1 blocks ahead, across group boundaries), lane l evaluates element
+// 32 k + l of the group from shared memory at the conflict-free word stride 3K-1.  Activations are gathered straight
+// from global memory (one block ahead in a register) and outputs stored straight to it: a block's 32 elements are
+// consecutive features of at most two rows, so the 4-byte accesses of a warp fall into a handful of sectors that L1 / L2
+// merge.  Per-element log-dets go through a small ring (F_t + 32 floats, rounded up to a power of two) and each row is
+// summed, as soon as its last element is in, with exactly the association of the tiled kernel (lane-strided partial
+// sums + butterfly), so the result does not depend on where a row sits in the batch.  64 registers and 6.5 KB of shared
+// memory per warp: 32 warps per SM.
+// What it fixes (profiles/ncu_tiled_r02.json): the tiled kernel has one barrier and one single-thread TMA issue per
+// 128-304 elements and 31 % of the warp slots occupied; barrier stalls dominate it.
+constexpr int STREAM_WARPS = 4;
+constexpr int MAXCOND = 3;        // conditioning columns per dim-group the streaming kernel moves in registers
+
+template <int MODE, int KT, bool INVERSE>
+__global__ void __launch_bounds__(STREAM_WARPS * 32, 8)
+rqs_coupling_stream(const __grid_constant__ CouplingArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int P = a.P, S = a.stages, G = a.R, F_t = a.F_t, d = a.d;
+  const int dim = a.dim, n_mask = a.n_mask, n_unm = a.n_unm;
+  const int n_el = G * F_t;                 // elements of a group: a multiple of 32
+  const int n_blk = n_el >> 5;
+  const uint32_t blk_floats = 32u * (uint32_t)P;
+  const int cap = a.scratch, cmask = cap - 1;
+  const size_t per_warp = ((size_t)S * blk_floats + (size_t)cap) * 4 + 64;
+  // feature -> column tables (input column of the transformed scalar, its output column), shared by the CTA: no integer
+  // division in the element loop
+  short* xcol = reinterpret_cast<short*>(smem_raw + (size_t)STREAM_WARPS * per_warp);
+  short* ocol = xcol + F_t;
+  short* gcol = ocol + F_t;                                // first column of the feature's dim-group if it is the group's
+  //                                                          first transformed feature (that lane also moves the group's
+  //                                                          conditioning values), else -1
+  float* ring = reinterpret_cast<float*>(smem_raw + (size_t)warp * per_warp);
+  float* lads = ring + (size_t)S * blk_floats;            // ring of per-element log-dets: a row is summed as soon as it is complete
+  uint64_t* full = reinterpret_cast<uint64_t*>(lads + cap);
+  for (int f = tid; f < F_t; f += STREAM_WARPS * 32) {
+    const int sgrp = f / n_unm, j = f - sgrp * n_unm;
+    xcol[f] = (short)(sgrp * dim + a.unm[j]);
+    ocol[f] = (short)(sgrp * dim + n_mask + j);
+    gcol[f] = (short)(j == 0 ? sgrp * dim : -1);
+  }
+  if (lane == 0) {
+    for (int st = 0; st < S; ++st) mbar_init(&full[st], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const long long n_groups = a.n_tiles;
+  const long long wstride = (long long)gridDim.x * STREAM_WARPS;
+  const long long g0 = (long long)blockIdx.x * STREAM_WARPS + warp;
+  // producer cursor (lane 0): next block to request
+  long long pg = g0;
+  int pk = 0, pstage = 0;
+  auto issue = [&]() {
+    if (pg < n_groups) {
+      mbar_expect_tx(&full[pstage], blk_floats * 4u);
+      bulk_g2s(ring + (size_t)pstage * blk_floats, a.params + ((size_t)pg * n_el + (size_t)pk * 32) * P, blk_floats * 4u,
+               &full[pstage]);
+      if (++pk == n_blk) {
+        pk = 0;
+        pg += wstride;
+      }
+      if (++pstage == S) pstage = 0;
+    }
+  };
+  if (lane == 0)
+    for (int i = 0; i < S - 1; ++i) issue();
+
+  // (row, feature) of this lane's element inside its group, advanced by 32 elements per block
+  const int r_first = lane / F_t, f_first = lane - r_first * F_t;
+  auto advance = [&](int& r, int& f) {
+    f += 32;
+    while (f >= F_t) {
+      f -= F_t;
+      ++r;
+    }
+  };
+  int stage = 0;
+  uint32_t phase = 0;
+  float xn = 0.f;
+  if (g0 < n_groups) xn = __ldg(a.x + (size_t)g0 * G * d + r_first * d + xcol[f_first]);
+  for (long long g = g0; g < n_groups; g += wstride) {
+    const size_t row0 = (size_t)g * G;
+    const float* xg = a.x + row0 * d;
+    float* og = a.out + row0 * d;
+    int r = r_first, f = f_first;                                // this block's element
+    int rn = r_first, fn = f_first;                              // the next block's
+    int r_done = 0;                                              // rows of this group already summed
+    for (int k = 0; k < n_blk; ++k) {
+      const int e = (k << 5) + lane;
+      const float xin = xn;
+      // next block's activation: of this group, or the first block of the warp's next group
+      if (k + 1 < n_blk) {
+        advance(rn, fn);
+        xn = __ldg(xg + rn * d + xcol[fn]);
+      } else if (g + wstride < n_groups) {
+        xn = __ldg(a.x + (size_t)(g + wstride) * G * d + r_first * d + xcol[f_first]);
+      }
+      // conditioning values of the dim-group this element opens (flows.py:239, quirk Q5: they move to the front of the
+      // group): stored with the transformed value below, so every 32-byte sector of the output row is completed by
+      // neighbouring lanes of one block instead of being revisited at the end of the group
+      const int gc = gcol[f];
+      float cv[MAXCOND];
+      if (gc >= 0) {
+#pragma unroll
+        for (int mi = 0; mi < MAXCOND; ++mi)
+          if (mi < n_mask) cv[mi] = __ldg(xg + r * d + gc + a.mask[mi]);
+      }
+      if (lane == 0) issue();                                    // keeps S - 1 blocks in flight
+      mbar_wait(&full[stage], phase);
+      const RqsOut o = rqs_element<MODE, KT, INVERSE, true, true>(SmemPtr{ring + (size_t)stage * blk_floats + (size_t)lane * P},
+                                                                 xin, a.c);
+      og[r * d + ocol[f]] = o.y;
+      if (gc >= 0) {
+#pragma unroll
+        for (int mi = 0; mi < MAXCOND; ++mi)
+          if (mi < n_mask) og[r * d + gc + mi] = cv[mi];
+      }
+      lads[e & cmask] = o.lad;
+      if (a.bins) a.bins[row0 * F_t + e] = (int8_t)o.bin;
+      r = rn;
+      f = fn;
+      __syncwarp();                                              // every lane is done with this stage's parameters
+      if (++stage == S) {
+        stage = 0;
+        phase ^= 1;
+      }
+      // rows completed by this block: flows.py:238 with the tiled kernel's association (lane-strided partial sums over the
+      // row's features, then the butterfly), so a row's log-det does not depend on its position in the batch
+      while ((r_done + 1) * F_t <= ((k + 1) << 5)) {
+        float t = 0.f;
+        for (int ff = lane; ff < F_t; ff += 32) t += lads[(r_done * F_t + ff) & cmask];
+        t = warp_sum(t);
+        if (lane == 0) {
+          float* ldp = a.logdet + row0 + r_done;
+          *ldp = a.accumulate ? *ldp + t : t;
+        }
+        ++r_done;
+      }
+    }
+    __syncwarp();                                                // the log-det ring is free for the next group
+  }
 }
 
 // Specialised geometry of the headline workload (size = 32, dim = 2, one masked column): one warp
@@ -348,7 +496,18 @@ static RqsConsts make_consts(int K, float B) {
 
 RqsConsts make_rqs_consts(int K, float B) { return make_consts(K, B); }
 
+// tuning / comparison hooks (nfk_set_coupling_tune): threads < 0 forces the older tiled kernel for generic geometries
 static int g_tune_R = 0, g_tune_threads = 0, g_tune_stages = 0, g_tune_ctas = 0;
+
+static int stream_group_rows(int F_t) {          // rows per group of the streaming kernel: G F_t is a multiple of 32
+  int a_ = F_t, b_ = 32;
+  while (b_) {
+    const int t = a_ % b_;
+    a_ = b_;
+    b_ = t;
+  }
+  return 32 / a_;
+}
 
 template <int MODE, int KT, bool INVERSE>
 static int launch_coupling(CouplingArgs& a, long long N, cudaStream_t st) {
@@ -385,6 +544,35 @@ static int launch_coupling(CouplingArgs& a, long long N, cudaStream_t st) {
         done = n_tiles * R;
       }
     }
+  } else if (KT == 8 && aligned && g_tune_threads >= 0 && F_t <= 4064 && a.n_mask <= MAXCOND && a.d <= 32000 &&
+             N / stream_group_rows(F_t) > 0) {
+    // ---- generic geometry, K = 8: warp-autonomous streaming kernel (groups of G rows = whole 32-element blocks)
+    const int G = stream_group_rows(F_t);
+    const long long n_groups = N / G;
+    const int stages = g_tune_stages > 0 ? max(2, g_tune_stages) : 2;
+    int ring_floats = 64;
+    while (ring_floats < F_t + 32) ring_floats <<= 1;
+    a.scratch = ring_floats;
+    const size_t per_warp = ((size_t)stages * 32 * a.P + (size_t)ring_floats) * 4 + 64;
+    const size_t smem = per_warp * STREAM_WARPS + (size_t)3 * F_t * 2 + 16;
+    a.R = G;
+    a.stages = stages;
+    a.n_tiles = n_groups;
+    auto kern = rqs_coupling_stream<MODE, 8, INVERSE>;           // (K = 8 only: the branch is dead for the generic-K instantiation)
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("rqs_coupling: cannot set %zu B dynamic shared memory: %s", smem, cudaGetErrorString(e));
+      return NFK_ECUDA;
+    }
+    int ctas_per_sm = g_tune_ctas > 0 ? g_tune_ctas : (int)((227 * 1024) / (smem + 1024));
+    ctas_per_sm = max(1, min(ctas_per_sm, 2048 / (STREAM_WARPS * 32)));
+    const long long cap = (long long)sm_count() * ctas_per_sm;
+    const long long want = (n_groups + STREAM_WARPS - 1) / STREAM_WARPS;
+    const long long grid = want < cap ? want : cap;
+    kern<<<(unsigned)grid, STREAM_WARPS * 32, smem, st>>>(a);
+    count_launch();
+    if (int rc = check_launch("rqs_coupling_stream")) return rc;
+    done = n_groups * G;
   } else if (aligned) {
     // ---- generic geometry: one element per thread per tile.  Rows per tile: a multiple of 4 (every
     // tile stays 16-byte aligned), as FEW as fill a 128-thread CTA.  Small tiles mean many co-resident
