@@ -138,3 +138,16 @@ def test_layer_backward_kernel_instruction_mix_and_resources():
     assert _count(s, "REDG") == 8                      # conditioning-column gradient adds
     mufu = _count(s, "MUFU.EX2") + _count(s, "MUFU.LG2") + _count(s, "MUFU.RCP")
     assert 50 <= mufu <= 64, mufu                      # 32 ex2 of the double softmaxes + 4 x (ex2, lg2 | rcp) + the segment's divisions
+
+
+def test_streaming_spline_kernel_runs_32_warps_per_sm():
+    """csrc/rqs_coupling.cu, rqs_coupling_stream: 64 registers (eight 128-thread CTAs per SM), at most two spilled words,
+    parameters through TMA bulk copies, no CTA-wide barrier inside the element loop (one after the prologue)."""
+    res = _usage()
+    ks = [k for k in res if "rqs_coupling_stream" in k]
+    assert len(ks) == 6, ks                       # 3 arithmetics x 2 directions, K = 8 only
+    for k in ks:
+        assert res[k]["REG"] <= 64 and res[k]["STACK"] <= 16 and res[k]["LOCAL"] == 0, (k, res[k])
+    s = _sass("_ZN3nfk19rqs_coupling_streamILi2ELi8ELb0EEEvNS_12CouplingArgsE")
+    assert _count(s, "UBLKCP") >= 1
+    assert _count(s, "BAR.SYNC") + _count(s, "BAR") <= 2, _count(s, "BAR")
