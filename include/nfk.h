@@ -292,6 +292,22 @@ int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, float grad_ou
                             int64_t N, int mask_col, float B, int inverse, int32_t* tile_flags_in /*nullable*/,
                             int32_t* tile_flags_out /*nullable*/, void* stream);
 
+/* The same launch with the leapfrog update folded in (the launch that completes the force, i.e. the layer nearest the
+ * data; reference applications/src/systems.py:331-336 drives kick / drift as separate tensor operations): after
+ * grad_x (= the force F when the chain started from the prior's score) of a row is complete,
+ *   momentum += kick * F ;  position += drift * momentum   (drift = 0: kick only)
+ * for the same row.  momentum, position [N, 64]; position may be x itself (a tile's reads of x are over by then).
+ * With tile_flags_out the flag also covers momentum and position, so the first forward launch of the next
+ * evaluation can hang on it (nfk_nsf_pairs_fused2_chain with that flag array as tile_flags_in). */
+int nfk_nsf_pairs_fused_bwd_leapfrog(const float* x, const float* grad_out, float grad_out_scale,
+                                     const float* grad_logdet, float grad_logdet_const, float* grad_x,
+                                     const void* w1_img, const void* w2_img, const void* w3_img,
+                                     const void* w3t_img, const void* w2t_img, const void* w1t_img,
+                                     const float* b1, const float* b2, const float* b3, int64_t N, int mask_col,
+                                     float B, int inverse, int32_t* tile_flags_in /*nullable*/,
+                                     int32_t* tile_flags_out /*nullable*/, float* momentum /*nullable*/,
+                                     float* position /*nullable*/, float kick, float drift, void* stream);
+
 /* ---- wide conditioner path (hidden width > 128; the class default is 800, nf/flows.py:216):
  * persistent warp-specialised tcgen05 GEMM  Y = act(A W^T + b)  over operands stored in HBM as
  * *shared-memory images*: 128-row x 64-column blocks of 16-bit elements (16 KB; `fmt` = NFK_IMG_BF16 or

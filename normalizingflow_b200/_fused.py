@@ -208,6 +208,10 @@ def run(layer, x, inverse, logdet=None, flags_in=None, flags_out=None):
 # ---------------------------------------------------------------------------------------------
 # consecutive backward launches of a flow depend on each other tile by tile instead of launch by launch (tools / tests)
 TILE_CHAIN = True
+# ... and consecutive evaluations of a trajectory too (the first forward launch hangs on the previous evaluation's last
+# backward launch, which has advanced the position)
+CHAIN_EVALS = False         # (off: replayed as a CUDA graph such a trajectory does not reproduce the launch-by-launch result)
+_DEBUG_NO_FLAGS = False          # tools/ubench/dbg_traj.py: leapfrog fold with launch-by-launch dependencies
 
 
 def bwd_eligible(layer) -> bool:
@@ -255,10 +259,12 @@ def packed_bwd(layer):
 
 
 def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=False, g_out_scale=1.0, flags_in=None,
-                   flags_out=None, keep_padding=False):
+                   flags_out=None, keep_padding=False, leapfrog=None):
     """dL/dx [N, 64] of one bwd_eligible layer from the layer input x, dL/d(out) = g_out_scale * g_out and dL/d(log_det)
     (a per-row tensor, or a constant for every row).  A partial last tile is zero-padded.  flags_in / flags_out
-    ([N / 128] int32): per-tile dependency between the launches of a chain, see nfk_nsf_pairs_fused_bwd in include/nfk.h."""
+    ([N / 128] int32): per-tile dependency between the launches of a chain, see nfk_nsf_pairs_fused_bwd in include/nfk.h.
+    leapfrog = (momentum, position, kick, drift): momentum += kick * dL/dx; position += drift * momentum, row by row
+    inside the same launch (nfk_nsf_pairs_fused_bwd_leapfrog; N a multiple of 128, position may be x)."""
     dev = require_cuda(x, g_out, g_logdet)
     x, g_out = f32c(x), f32c(g_out)
     N = x.shape[0]
@@ -278,52 +284,91 @@ def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=F
     with torch.cuda.device(dev):
         tm = _ops.KERNEL_TIMER
         ev = tm.start("nsf_pairs_fused_bwd", dev) if tm is not None else None
-        call("nfk_nsf_pairs_fused_bwd", ptr(x), ptr(g_out), float(g_out_scale),
-             ptr(f32c(g_logdet)) if g_logdet is not None else ptr(None), float(g_logdet_const), ptr(g_in), ptr(pk["w1"]),
-             ptr(pk["w2"]), ptr(pb["w3"]), ptr(pb["w3t"]), ptr(pb["w2t"]), ptr(pb["w1t"]), ptr(pk["b1"]), ptr(pk["b2"]),
-             ptr(pb["b3"]), n_pad, layer._mask[0], float(layer.B), int(bool(inverse)), ptr(flags_in), ptr(flags_out),
-             stream_ptr(dev))
+        if leapfrog is not None:
+            lp, lq, kick, drift = leapfrog
+            if n_pad != N or lp.shape != (N, 64) or lq.shape != (N, 64) or not (lp.is_contiguous() and lq.is_contiguous()):
+                raise ValueError("leapfrog fold needs whole 128-row tiles and contiguous [N, 64] momentum / position")
+            call("nfk_nsf_pairs_fused_bwd_leapfrog", ptr(x), ptr(g_out), float(g_out_scale),
+                 ptr(f32c(g_logdet)) if g_logdet is not None else ptr(None), float(g_logdet_const), ptr(g_in), ptr(pk["w1"]),
+                 ptr(pk["w2"]), ptr(pb["w3"]), ptr(pb["w3t"]), ptr(pb["w2t"]), ptr(pb["w1t"]), ptr(pk["b1"]), ptr(pk["b2"]),
+                 ptr(pb["b3"]), n_pad, layer._mask[0], float(layer.B), int(bool(inverse)), ptr(flags_in), ptr(flags_out),
+                 ptr(lp), ptr(lq), float(kick), float(drift), stream_ptr(dev))
+        else:
+            call("nfk_nsf_pairs_fused_bwd", ptr(x), ptr(g_out), float(g_out_scale),
+                 ptr(f32c(g_logdet)) if g_logdet is not None else ptr(None), float(g_logdet_const), ptr(g_in), ptr(pk["w1"]),
+                 ptr(pk["w2"]), ptr(pb["w3"]), ptr(pb["w3t"]), ptr(pb["w2t"]), ptr(pb["w1t"]), ptr(pk["b1"]), ptr(pk["b2"]),
+                 ptr(pb["b3"]), n_pad, layer._mask[0], float(layer.B), int(bool(inverse)), ptr(flags_in), ptr(flags_out),
+                 stream_ptr(dev))
         if ev is not None:
             tm.stop(ev, dev)
     return g_in if keep_padding else g_in[:N]
 
 
-def flow_logp_and_grad(model, x, need_logp=True):
-    """log p(x) [N] and d log p / dx [N, d] through a flow whose layers are all bwd_eligible, under an isotropic Gaussian
-    prior: one forward launch per layer (keeping each layer's input), the log-prob reduction, one backward launch per layer; None when the
-    model does not qualify."""
+def flow_eligible(model) -> bool:
+    """Every layer is a bwd_eligible NSF_CL on the fused path and the prior is an isotropic zero-mean Gaussian."""
     from .flows import NSF_CL
     var = model._prior_var() if hasattr(model, "_prior_var") else None
-    if var is None or len(model.flows) == 0 or not all(isinstance(f, NSF_CL) and f.fused and bwd_eligible(f) for f in model.flows):
+    return (var is not None and len(model.flows) > 0
+            and all(isinstance(f, NSF_CL) and f.fused and bwd_eligible(f) for f in model.flows))
+
+
+def tile_chain_ok(model, n_rows) -> bool:
+    return (TILE_CHAIN and n_rows % ROWS == 0 and len(model.flows) > 1 and GENERATION == 2
+            and _lib.have("nfk_nsf_pairs_fused2_chain"))
+
+
+def _tile_flags(model, dev, n_tiles, L):
+    """[3, L, n_tiles] int32: forward-chain flags, backward-chain flags, and (row 0 of the third plane) the flags that
+    hang the next evaluation's first forward launch on this evaluation's last backward launch."""
+    key = (dev, n_tiles, L)
+    cache = getattr(model, "_fused_tile_flags", None)
+    if cache is None or cache[0] != key:
+        cache = model._fused_tile_flags = (key, torch.zeros((3, L, n_tiles), dtype=torch.int32, device=dev))
+    return cache[1]
+
+
+def flow_logp_and_grad(model, x, need_logp=True, leapfrog=None, hang_on_previous=False, next_hangs_on_this=False,
+                       zero_flags=True):
+    """log p(x) [N] and d log p / dx [N, d] through a flow whose layers are all bwd_eligible, under an isotropic Gaussian
+    prior: one forward launch per layer (keeping each layer's input), the log-prob reduction, one backward launch per
+    layer; None when the model does not qualify.
+    leapfrog = (momentum, position, kick, drift): the last backward launch also advances momentum and position
+    (layer_backward).  hang_on_previous / next_hangs_on_this: consecutive evaluations of a trajectory form one tile-flag
+    chain (the first forward launch of an evaluation takes tile t as soon as the previous evaluation's last backward
+    launch has advanced the position of tile t); zero_flags = False keeps the flags as the previous evaluation left
+    them (all consumed), so no fill kernel interrupts the chain."""
+    if not flow_eligible(model):
         return None
+    var = model._prior_var()
     h = f32c(x.detach())
     N, L = h.shape[0], len(model.flows)
-    logdet = torch.zeros(N, dtype=torch.float32, device=h.device)
     for f in model.flows:          # every operand image exists BEFORE the first launch of the chain: a flagged launch does
         packed(f)                  # not wait for the stream, so nothing but flagged tiles may be produced inside the chain
         packed_bwd(f)
-    fw = bw = None
-    if TILE_CHAIN and N % ROWS == 0 and L > 1 and GENERATION == 2 and _lib.have("nfk_nsf_pairs_fused2_chain"):
+    fw = bw = link = None
+    if tile_chain_ok(model, N) and not _DEBUG_NO_FLAGS:
         # per-tile dependency between consecutive launches of the forward chain and of the backward chain (rows are
         # independent): a launch starts on the SMs the previous one has already left instead of waiting for its last wave
-        key = (h.device, N // ROWS, L)
-        cache = getattr(model, "_fused_tile_flags", None)
-        if cache is None or cache[0] != key:
-            cache = model._fused_tile_flags = (key, torch.zeros((2, L, N // ROWS), dtype=torch.int32, device=h.device))
-        cache[1].zero_()
-        fw, bw = cache[1][0], cache[1][1]
+        flags = _tile_flags(model, h.device, N // ROWS, L)
+        if zero_flags:
+            flags.zero_()
+        fw, bw, link = flags[0], flags[1], flags[2][0]
+    elif hang_on_previous or next_hangs_on_this:
+        raise ValueError("chained evaluations need the tile-flag path (whole 128-row tiles, TILE_CHAIN)")
     # without the log-prob reduction between them (need_logp = False: a leapfrog step inside a trajectory only needs the
     # force) the first backward launch hangs on the last forward launch tile by tile as well
     join = fw is not None and not need_logp
     inputs = []
+    logdet = None                  # the first layer writes its log-det, the others accumulate: no zero-fill launch
     for i, f in enumerate(model.flows):
         inputs.append(h)
-        h, logdet = run(f, h, False, logdet, fw[i - 1] if (fw is not None and i > 0) else None,
-                        fw[i] if (fw is not None and (i + 1 < L or join)) else None)
+        f_in = (fw[i - 1] if i > 0 else (link if hang_on_previous else None)) if fw is not None else None
+        h, logdet = run(f, h, False, logdet, f_in, fw[i] if (fw is not None and (i + 1 < L or join)) else None)
     logp = _ops.gauss_logprob(h, var, add=logdet, add_sign=1.0) if need_logp else None
     g, scale = h, -1.0 / var                                  # d log N(z; 0, var I) / dz = -z / var, applied by the first launch
     for i, (f, xin) in enumerate(zip(reversed(model.flows), reversed(inputs))):
         f_in = (bw[i - 1] if i > 0 else (fw[L - 1] if join else None)) if bw is not None else None
-        g = layer_backward(f, xin, g, None, 1.0, False, scale, f_in, bw[i] if (bw is not None and i + 1 < L) else None)
+        f_out = (bw[i] if i + 1 < L else (link if next_hangs_on_this else None)) if bw is not None else None
+        g = layer_backward(f, xin, g, None, 1.0, False, scale, f_in, f_out, leapfrog=leapfrog if i + 1 == L else None)
         scale = 1.0
     return logp, g

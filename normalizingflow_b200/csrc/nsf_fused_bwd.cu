@@ -66,7 +66,10 @@ struct FusedBwdArgs {
   long long n_tiles;
   int cond_first;
   int* flag_in;           // [n_tiles] or null: tile t may start when flag_in[t] != 0 (set by the launch that produces gout)
-  int* flag_out;          // [n_tiles] or null: set to 1 when tile t of gin is complete
+  int* flag_out;          // [n_tiles] or null: set to 1 when tile t of gin (and of lf_p / lf_q) is complete
+  float* lf_p;            // leapfrog fold (null: off): p += lf_kick * gin ; lf_q += lf_drift * p  (lf_q may be x itself)
+  float* lf_q;
+  float lf_kick, lf_drift;
   RqsConsts c;
 };
 
@@ -194,7 +197,7 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
     }
     __syncwarp();
     for (unsigned it = 0; it < my_tiles; ++it) {
-      if (it + 1 < my_tiles && lane == 0) {
+      if (it + 1 < my_tiles && lane == 0 && a.flag_in == nullptr) {
         const size_t nrow = (first + (size_t)(it + 1) * stride) * FB_ROWS;
         fb_prefetch_l2(a.x + nrow * 64, FB_ROWS * 256);
         fb_prefetch_l2(a.gout + nrow * 64, FB_ROWS * 256);
@@ -407,15 +410,21 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
       }
     };
     // x / dL/d(out) pairs are fetched one chunk ahead (across tiles too), so their latency hides behind an adjoint
+    // In a tile-flag chain x itself may be produced inside the chain (the forward launches of the same evaluation), so a
+    // tile's x is only touched once its flag has been seen: the cross-tile prefetches below are taken when a probe finds
+    // the next tile's flag already set (the steady state) and otherwise made up for after the blocking wait.  All loads
+    // of chain data go to L2 (ld.global.cg): an L1 line could predate the producing launch.
     float2 xn = make_float2(0.f, 0.f), gn = xn;
-    if (my_tiles) xn = __ldg(reinterpret_cast<const float2*>(a.x + ((size_t)first * FB_ROWS + row) * 64) + slice);
     // the 8 pairs whose conditioning columns this thread turns into the A1 operand, fetched before the previous tile's
     // tail (the waits on its last three GEMMs hide the latency)
     float4 a1n[4];
-    if (my_tiles) {
+    bool have_next = false;                    // xn / a1n of the coming tile are already in registers
+    if (my_tiles && a.flag_in == nullptr) {
+      xn = __ldcg(reinterpret_cast<const float2*>(a.x + ((size_t)first * FB_ROWS + row) * 64) + slice);
       const float4* x4 = reinterpret_cast<const float4*>(a.x + ((size_t)first * FB_ROWS + row) * 64 + slice * 16);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) a1n[j] = __ldg(x4 + j);
+      for (int j = 0; j < 4; ++j) a1n[j] = __ldcg(x4 + j);
+      have_next = true;
     }
     for (unsigned it = 0; it < my_tiles; ++it) {
       const size_t tile = first + (size_t)it * stride;
@@ -433,6 +442,13 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
         __syncwarp();
       }
       gn = __ldcg(gor + slice);
+      if (!have_next) {
+        xn = __ldcg(xr + slice);
+        const float4* x4 = reinterpret_cast<const float4*>(xr + slice * 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a1n[j] = __ldcg(x4 + j);
+      }
+      have_next = false;
       // ---- A1: conditioning columns of features 8 slice .. 8 slice + 7 of this row (fp16, K block 0, chunk `slice`)
       {
         float f[8];
@@ -470,10 +486,18 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
         const int f = c * FB_CF + slice;
         const float2 xc = xn, gc = gn;
         if (c + 1 < FB_NCHUNK) {
-          xn = __ldg(xr + f + FB_CF);
+          xn = __ldcg(xr + f + FB_CF);
           gn = __ldcg(gor + f + FB_CF);
         } else if (it + 1 < my_tiles) {
-          xn = __ldg(reinterpret_cast<const float2*>(a.x + ((tile + stride) * FB_ROWS + row) * 64) + slice);
+          // next tile: prefetch only if its flag is already up (non-blocking probe by lane 0)
+          int up = 1;
+          if (a.flag_in != nullptr) {
+            up = (lane == 0) ? fb_ld_acquire(a.flag_in + tile + stride) : 0;
+            __syncwarp();
+            up = __shfl_sync(0xffffffffu, up, 0);
+          }
+          have_next = up != 0;
+          if (have_next) xn = __ldcg(reinterpret_cast<const float2*>(a.x + ((tile + stride) * FB_ROWS + row) * 64) + slice);
         }
         FB_T(tr, 64 + slice * 32 + c * 3);
         mbar_wait(&bar_d3f[g & 1], (g >> 1) & 1);
@@ -535,10 +559,10 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
         if (lane == 0) mbar_arrive(bar_gready);
         FB_T(tr, 64 + slice * 32 + c * 3 + 2);
       }
-      if (it + 1 < my_tiles) {
+      if (have_next) {
         const float4* x4 = reinterpret_cast<const float4*>(a.x + ((tile + stride) * FB_ROWS + row) * 64 + slice * 16);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a1n[j] = __ldg(x4 + j);
+        for (int j = 0; j < 4; ++j) a1n[j] = __ldcg(x4 + j);
       }
       // ---- dZ2 = dH2 (1 - h2^2), in place over h2 (every chunk GEMM has completed: bar_dh2 follows them)
       mbar_wait(bar_dh2, it & 1);
@@ -570,11 +594,40 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) sT[lane * 32 + ((slice * 8 + j) ^ lane)] = __uint_as_float(v[j]);
         asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
-        float* gq = a.gin + (tile * FB_ROWS + q * 32) * 64 + 2 * lane + (a.cond_first ? 0 : 1);
+        if (a.lf_p == nullptr) {
+          float* gq = a.gin + (tile * FB_ROWS + q * 32) * 64 + 2 * lane + (a.cond_first ? 0 : 1);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = slice * 8 + j;
-          fb_red_add(gq + (size_t)r * 64, sT[r * 32 + (lane ^ r)]);
+          for (int j = 0; j < 8; ++j) {
+            const int r = slice * 8 + j;
+            fb_red_add(gq + (size_t)r * 64, sT[r * 32 + (lane ^ r)]);
+          }
+        } else {
+          // Leapfrog folded into the launch that completes the force (the layer nearest the data): the thread that owns
+          // (row, feature pair) finishes dL/dx of the pair -- 256 contiguous bytes per row and warp -- and advances the
+          // momentum and the position of the same pair (velocity Verlet, applications/src/systems.py:331-336).  The
+          // position may be this launch's own input: every read of this tile's x happened before this point.
+          const size_t pair0 = ((tile * FB_ROWS + q * 32) * 64) / 2 + lane;
+          float2* g2 = reinterpret_cast<float2*>(a.gin) + pair0;
+          float2* p2 = reinterpret_cast<float2*>(a.lf_p) + pair0;
+          float2* q2 = reinterpret_cast<float2*>(a.lf_q) + pair0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = slice * 8 + j;
+            float2 gv = __ldcg(g2 + (size_t)r * 32);
+            const float dxc = sT[r * 32 + (lane ^ r)];
+            if (a.cond_first) gv.x += dxc; else gv.y += dxc;
+            g2[(size_t)r * 32] = gv;
+            float2 pv = p2[(size_t)r * 32];
+            pv.x = fmaf(a.lf_kick, gv.x, pv.x);
+            pv.y = fmaf(a.lf_kick, gv.y, pv.y);
+            p2[(size_t)r * 32] = pv;
+            if (a.lf_drift != 0.f) {
+              float2 qv = q2[(size_t)r * 32];
+              qv.x = fmaf(a.lf_drift, pv.x, qv.x);
+              qv.y = fmaf(a.lf_drift, pv.y, qv.y);
+              q2[(size_t)r * 32] = qv;
+            }
+          }
         }
       }
       FB_T(tr && slice == 0, 43);
@@ -611,11 +664,31 @@ extern "C" int nfk_fused_bwd_trace_read(long long* host) {
 }
 #endif
 
+extern "C" int nfk_nsf_pairs_fused_bwd_leapfrog(const float* x, const float* grad_out, float grad_out_scale,
+                                                const float* grad_logdet, float grad_logdet_const, float* grad_x,
+                                                const void* w1_img, const void* w2_img, const void* w3_img,
+                                                const void* w3t_img, const void* w2t_img, const void* w1t_img,
+                                                const float* b1, const float* b2, const float* b3, int64_t N, int mask_col,
+                                                float B, int inverse, int32_t* tile_flags_in, int32_t* tile_flags_out,
+                                                float* momentum, float* position, float kick, float drift, void* stream);
+
 extern "C" int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, float grad_out_scale, const float* grad_logdet,
+                                       float grad_logdet_const, float* grad_x, const void* w1_img, const void* w2_img,
+                                       const void* w3_img, const void* w3t_img, const void* w2t_img, const void* w1t_img,
+                                       const float* b1, const float* b2, const float* b3, int64_t N, int mask_col, float B,
+                                       int inverse, int32_t* tile_flags_in, int32_t* tile_flags_out, void* stream) {
+  return nfk_nsf_pairs_fused_bwd_leapfrog(x, grad_out, grad_out_scale, grad_logdet, grad_logdet_const, grad_x, w1_img, w2_img,
+                                          w3_img, w3t_img, w2t_img, w1t_img, b1, b2, b3, N, mask_col, B, inverse,
+                                          tile_flags_in, tile_flags_out, nullptr, nullptr, 0.f, 0.f, stream);
+}
+
+extern "C" int nfk_nsf_pairs_fused_bwd_leapfrog(const float* x, const float* grad_out, float grad_out_scale, const float* grad_logdet,
                                        float grad_logdet_const, float* grad_x, const void* w1_img, const void* w2_img, const void* w3_img,
                                        const void* w3t_img, const void* w2t_img, const void* w1t_img, const float* b1,
                                        const float* b2, const float* b3, int64_t N, int mask_col, float B, int inverse,
-                                       int32_t* tile_flags_in, int32_t* tile_flags_out, void* stream) {
+                                       int32_t* tile_flags_in, int32_t* tile_flags_out, float* momentum, float* position,
+                                       float kick, float drift, void* stream) {
+  NFK_REQUIRE((momentum == nullptr) == (position == nullptr), "nsf_pairs_fused_bwd: momentum and position go together");
   NFK_REQUIRE(N >= 0 && N % FB_ROWS == 0, "nsf_pairs_fused_bwd: N must be a multiple of %d (got %lld)", FB_ROWS, (long long)N);
   NFK_REQUIRE(mask_col == 0 || mask_col == 1, "nsf_pairs_fused_bwd: mask column must be 0 or 1");
   NFK_REQUIRE(B > 0.f, "nsf_pairs_fused_bwd: tail bound must be positive");
@@ -647,6 +720,10 @@ extern "C" int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, fl
   a.cond_first = (mask_col == 0);
   a.flag_in = tile_flags_in;
   a.flag_out = tile_flags_out;
+  a.lf_p = momentum;
+  a.lf_q = position;
+  a.lf_kick = kick;
+  a.lf_drift = drift;
   a.c = make_rqs_consts(8, B);
   auto kern = inverse ? nsf_fused_bwd_kernel<true> : nsf_fused_bwd_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM);

@@ -141,6 +141,9 @@ class FlowSimulation:
         self.grad_evals = 0
         self.tensor_core_grad = True      # bf16-conditioner models: hand-written forward+backward path
         self.fused_grad = True            # ... through the one-launch-per-layer kernels when hidden width <= 128
+        self.fused_leapfrog = False       # ... with kick / drift folded into the last backward launch of every evaluation
+        #                                   (nfk_nsf_pairs_fused_bwd_leapfrog; measured 1 % slower than the two element-wise
+        #                                   launches it replaces, so off by default)
         self.use_graph = True             # replay whole trajectories as one CUDA graph on that path
         self._graphs = {}
 
@@ -197,7 +200,34 @@ class FlowSimulation:
         return -logp.detach(), force.contiguous()
 
     # ---- whole trajectory as one CUDA graph -------------------------------------------------
+    def _fused_leapfrog_ok(self, q):
+        from . import _fused
+        return (self.tensor_core_grad and self.fused_grad and self.fused_leapfrog and q.dim() == 2 and q.shape[1] == 64
+                and q.is_contiguous() and _lib.have("nfk_nsf_pairs_fused_bwd_leapfrog")
+                and _fused.tile_chain_ok(self.model, q.shape[0]) and _fused.flow_eligible(self.model))
+
+    def _trajectory_fused(self, q, p, path_len, dt):
+        """The whole trajectory as ONE chain of layer launches: the launch that completes the force of an evaluation
+        (backward of the layer nearest the data) also does the kick and the drift of its rows, and the next evaluation's
+        first forward launch takes a 128-row tile as soon as that tile's position has been advanced.  Only the end
+        point's potential is computed.  p receives dt/2 F(q_0), dt F(q_i) for the interior points and dt/2 F(q_L) --
+        the two half kicks around an interior point are one fused multiply-add here."""
+        from . import _fused
+        logp = None
+        for i in range(path_len + 1):
+            last = i == path_len
+            kick = 0.5 * dt if (i == 0 or last) else dt
+            drift = 0.0 if last else dt * self.inv_mass
+            logp, _ = _fused.flow_logp_and_grad(self.model, q, need_logp=last, leapfrog=(p, q, kick, drift),
+                                                hang_on_previous=(i > 0 and _fused.CHAIN_EVALS),
+                                                next_hangs_on_this=(not last and _fused.CHAIN_EVALS),
+                                                zero_flags=(i == 0))
+            self.grad_evals += 1
+        return -logp
+
     def _trajectory(self, q, p, path_len, dt):
+        if path_len >= 1 and self._fused_leapfrog_ok(q):
+            return self._trajectory_fused(q, p, path_len, dt)
         pot, force = self.potential_and_force(q, need_potential=(path_len == 0))
         for i in range(path_len):
             _ops.leapfrog_kick_drift(q, p, force, dt, self.inv_mass)
@@ -212,20 +242,20 @@ class FlowSimulation:
         from . import _wide
         if not _wide.flow_grad_eligible(self.model):
             return None
-        key = (path_len, dt, self.n_chains, self.fused_grad, _lib.param_epoch(),
+        key = (path_len, dt, self.n_chains, self.fused_grad, self.fused_leapfrog, _lib.param_epoch(),
                tuple((p._version, p.data_ptr()) for p in self.model.parameters()))
         entry = self._graphs.get(key)
         if entry is None:
             self._graphs.clear()
             q = self.position.clone()
             p = self.velocity.clone()
+            evals = self.grad_evals
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):                       # warm-up: weight images, kernel attributes
                 self._trajectory(q.clone(), p.clone(), 1, dt)
             torch.cuda.current_stream(self.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            evals = self.grad_evals
             with torch.cuda.graph(graph):
                 pot = self._trajectory(q, p, path_len, dt)
             self.grad_evals = evals
@@ -253,10 +283,6 @@ class FlowSimulation:
         # integrate on copies: HMC keeps references to the position it last accepted (hmc.py:36, :58),
         # so advancing self.position in place would turn every rejection into an acceptance
         q, p = self.position.clone(), self.velocity.clone()
-        pot, force = self.potential_and_force(q)
-        for _ in range(path_len):
-            _ops.leapfrog_kick_drift(q, p, force, dt, self.inv_mass)      # p += dt/2 F ; q += dt p / m
-            pot, force = self.potential_and_force(q)
-            _ops.leapfrog_kick(p, force, dt)                               # p += dt/2 F(q_new)
+        pot = self._trajectory(q, p, int(path_len), float(dt))
         self.position, self.velocity = q, p
         return q, pot

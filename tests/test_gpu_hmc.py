@@ -254,6 +254,63 @@ def test_tile_chained_launches_equal_launch_by_launch_dependency_bitwise():
         _fused.TILE_CHAIN = True
 
 
+def _trajectories(m, q0, p0, use_graph, fold, tile_chain, path_len, calls=2):
+    from normalizingflow_b200 import _fused
+    from normalizingflow_b200.hmc import FlowSimulation
+    _fused.TILE_CHAIN = tile_chain
+    try:
+        sim = FlowSimulation(m, n_chains=q0.shape[0], init_pos=q0)
+        sim.use_graph, sim.fused_leapfrog = use_graph, fold
+        sim.set_velocity(p0)
+        e0, out = sim.grad_evals, []
+        for _ in range(calls):
+            q, U = sim.integration_step(path_len=path_len, dt=0.01)
+            out.append((q.clone(), U.clone(), sim.velocity.clone()))
+        torch.cuda.synchronize()
+        assert sim.grad_evals - e0 == calls * (path_len + 1)
+        return out
+    finally:
+        _fused.TILE_CHAIN = True
+
+
+def test_graph_replayed_tile_chains_reproduce_launch_by_launch_trajectories_bitwise():
+    """Replayed as one CUDA graph the launches of an evaluation really overlap (in eager mode the host paces them): the
+    tile-flag chain -- including the first backward launch hanging on the last forward launch, whose output is the
+    backward's own x -- must give the launch-by-launch result bit for bit.  (Regression: the backward kernel used to
+    prefetch the next tile's x before having seen that tile's flag.)"""
+    m = _model(precision="bf16")
+    C = (2 * 148 + 9) * 128
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    q0 = torch.randn(C, 64, device="cuda", generator=gen) * 0.5
+    p0 = torch.randn(C, 64, device="cuda", generator=gen)
+    ref = _trajectories(m, q0, p0, use_graph=False, fold=False, tile_chain=False, path_len=3)
+    for use_graph in (False, True):
+        got = _trajectories(m, q0, p0, use_graph=use_graph, fold=False, tile_chain=True, path_len=3)
+        for a, b in zip(ref, got):
+            assert all(torch.equal(x, y) for x, y in zip(a, b)), use_graph
+    assert int(m._fused_tile_flags[1].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_leapfrog_folded_into_the_last_backward_launch_matches_separate_kick_and_drift(use_graph):
+    """Kick / drift inside the launch that completes the force against separate kick / drift launches: bit-identical
+    for one step (no interior point); over several steps the two half kicks around an interior point are one fused
+    multiply-add, and the dynamics amplify that rounding difference (d log|det| / dx jumps across knots)."""
+    m = _model(precision="bf16")
+    C = 5 * 128
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    q0 = torch.randn(C, 64, device="cuda", generator=gen) * 0.5
+    p0 = torch.randn(C, 64, device="cuda", generator=gen)
+    for path_len, tol in ((1, 0.0), (6, 2e-2)):
+        ref = _trajectories(m, q0, p0, use_graph=False, fold=False, tile_chain=True, path_len=path_len)
+        got = _trajectories(m, q0, p0, use_graph=use_graph, fold=True, tile_chain=True, path_len=path_len)
+        for a, b in zip(ref, got):
+            for x, y in zip(a, b):
+                assert torch.isfinite(y).all()
+                assert float((x - y).abs().max()) <= tol * (1.0 + float(x.abs().max())), (path_len, float((x - y).abs().max()))
+    assert int(m._fused_tile_flags[1].abs().sum()) == 0
+
+
 def test_single_chain_eager_rejection_restores_the_position():
     """n_chains = 1 on the eager integrator (fp32 conditioner): HMC keeps references to the position it
     last accepted (nf/hmc.py:36, :58), so the integrator must not advance that tensor in place -- a
