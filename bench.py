@@ -497,6 +497,22 @@ def hmc_block(a, sd, dev, world, rank):
                        "note": "the fused kernels keep the spline parameters and their gradients on chip: real traffic is "
                                "about 1.3 KB per chain and layer, and the evaluation is bound by the adjoint arithmetic "
                                "(issue slots / MUFU), not by HBM"}
+    # the replayed graph (launches really overlapping, tile by tile) must reproduce the launch-by-launch trajectory bit for bit
+    def small_traj(use_graph, chain):
+        _fused.TILE_CHAIN = chain
+        try:
+            s2 = FlowSimulation(model, n_chains=min(C, 8192), nparticles=SIZE, dim=DIM, init_pos=q0[:8192])
+            s2.use_graph = use_graph
+            s2.set_velocity(torch.ones_like(s2.position) * 0.3)
+            qa, ua = s2.integration_step(path_len=3, dt=dt)
+            qb, ub = s2.integration_step(path_len=3, dt=dt)
+            torch.cuda.synchronize()
+            return qa.clone(), ua.clone(), qb.clone(), ub.clone()
+        finally:
+            _fused.TILE_CHAIN = True
+    ref_t = small_traj(False, False)
+    got_t = small_traj(True, True)
+    out["graph_replay_with_tile_flags_equals_launch_by_launch_bitwise"] = bool(all(torch.equal(x_, y_) for x_, y_ in zip(ref_t, got_t)))
     if rank == 0:
         sub = q0[:2048]
         lp_f, g_f = _fused.flow_logp_and_grad(model, sub) if fused_path else _wide.flow_logp_and_grad(model, sub)
