@@ -498,7 +498,9 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
         if (lane == 0)
           while (f2_ld_acquire(a.flag_in + tile2) == 0) __nanosleep(64);
         __syncwarp();
-        fence_proxy_async();                                             // ... and the bulk copy below (async proxy) sees it
+        // ... and the bulk copy below (async proxy) sees what the flag publishes, also when the producer wrote it with
+        // ordinary stores (generic proxy): a proxy fence over GLOBAL memory, not just shared
+        asm volatile("fence.proxy.async;" ::: "memory");
       }
       if (lane == 0) mbar_expect_tx(&bar_x[s], 8 * F2_XROW_BYTES);       // arrive (1 of 16) + expect
       __syncwarp();
@@ -509,7 +511,7 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
     // thread's writes are fenced, then one release store of the flag (tile-flag chains only)
     auto publish = [&](size_t t_) {
       if (lane < 8) bulk_wait_all<0>();
-      fence_proxy_async();
+      asm volatile("fence.proxy.async;" ::: "memory");       // the rows went out through the async proxy
       __threadfence();
       asm volatile("bar.sync 5, 512;" ::: "memory");
       if (tid == 0) f2_st_release(a.flag_out + t_, 1);
