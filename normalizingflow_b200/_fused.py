@@ -366,9 +366,13 @@ def flow_logp_and_grad(model, x, need_logp=True, leapfrog=None, hang_on_previous
         h, logdet = run(f, h, False, logdet, f_in, fw[i] if (fw is not None and (i + 1 < L or join)) else None)
     logp = _ops.gauss_logprob(h, var, add=logdet, add_sign=1.0) if need_logp else None
     g, scale = h, -1.0 / var                                  # d log N(z; 0, var I) / dz = -z / var, applied by the first launch
+    keep = []                      # in a chain the launches overlap: no buffer of the evaluation is handed back to the
+    #                                allocator (and possibly re-issued at another offset) before the last launch is queued
     for i, (f, xin) in enumerate(zip(reversed(model.flows), reversed(inputs))):
         f_in = (bw[i - 1] if i > 0 else (fw[L - 1] if join else None)) if bw is not None else None
         f_out = (bw[i] if i + 1 < L else (link if next_hangs_on_this else None)) if bw is not None else None
+        keep.append(g)
         g = layer_backward(f, xin, g, None, 1.0, False, scale, f_in, f_out, leapfrog=leapfrog if i + 1 == L else None)
         scale = 1.0
+    del keep
     return logp, g

@@ -97,19 +97,24 @@ class HMC:
         sim = self.simulation
         pos = sim.get_position().clone()
         pot = sim.get_potential().clone()
-        positions, potentials, accepted, log_prob = [], [], 0.0, None
-        for _ in range(epochs):
-            positions.append(pos.clone())
-            potentials.append(pot.clone())
+        # recorded positions / potentials go straight into their result tensors, the acceptance count stays on the device:
+        # no host synchronisation inside the loop, so the next epoch's launches queue up behind the running trajectory
+        positions = torch.empty((epochs,) + tuple(pos.shape), dtype=pos.dtype, device=pos.device)
+        potentials = torch.empty((epochs,) + tuple(pot.shape), dtype=pot.dtype, device=pot.device)
+        accepted = torch.zeros((), dtype=torch.float32, device=pos.device)
+        log_prob = None
+        for e in range(epochs):
+            positions[e].copy_(pos)
+            potentials[e].copy_(pot)
             new_pos, new_pot, log_prob = self.run_sim()
             u = torch.rand(self.n_chains, device=pos.device, generator=getattr(sim, "generator", None))
             acc = u < torch.exp((pot - new_pot) * self.beta)
             pos = torch.where(acc[:, None], new_pos, pos)
             pot = torch.where(acc, new_pot, pot)
-            accepted += float(acc.float().mean())
+            accepted += acc.float().mean()
             sim.set_position(pos)
         self.position, self.potential = pos, pot
-        return torch.stack(positions), torch.stack(potentials), log_prob, accepted / epochs
+        return positions, potentials, log_prob, float(accepted) / epochs
 
 
 class FlowSimulation:
