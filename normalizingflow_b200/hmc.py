@@ -52,14 +52,25 @@ class HMC:
             v = self.v_dist.sample((1,))
             return v.flatten(), self.v_dist.log_prob(v)
         dev = self.simulation.device
-        std = torch.sqrt(self._inv_mass / self.init_beta).to(dev)
+        std = self._v_consts(dev)[0]
         v = torch.randn(self.n_chains, self.dim * self.nparticles, device=dev,
                         generator=getattr(self.simulation, "generator", None)) * std
         return v, self._log_prob_v(v)
 
+    def _v_consts(self, dev):
+        """(std, 1 / var, log-normaliser) of the velocity distribution on `dev`, uploaded once: a host -> device copy from
+        pageable memory inside the epoch loop blocks the host until the stream has drained, i.e. once per epoch."""
+        key = (str(dev), float(self.init_beta))
+        c = getattr(self, "_v_cache", None)
+        if c is None or c[0] != key:
+            var = (self._inv_mass / self.init_beta).to(torch.float32)
+            c = self._v_cache = (key, (torch.sqrt(var).to(dev), (1.0 / var).to(dev),
+                                       float(-0.5 * torch.log(2 * math.pi * var).sum())))
+        return c[1]
+
     def _log_prob_v(self, v):
-        var = (self._inv_mass / self.init_beta).to(v.device)
-        return (-0.5 * (v * v / var).sum(-1) - 0.5 * torch.log(2 * math.pi * var).sum())
+        _, inv_var, log_norm = self._v_consts(v.device)
+        return -0.5 * (v * v * inv_var).sum(-1) + log_norm
 
     def run_sim(self, v=None):
         if v is None:
