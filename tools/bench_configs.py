@@ -153,6 +153,8 @@ def cfg5(c_global, H, precision):
     fl = [NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=H, mask=[i % 2]) for i in range(8)]
     for f in fl:
         f.psi.precision = precision
+        if precision == "bf16":
+            f.arith = "fast"       # as bench.py: inside the 16-bit conditioner's class, bins still the exact search
     m = NormalizingFlowModel(GaussianPrior(64, device=dev), fl, device=dev).to(dev)
     C = my_rows(c_global)
     sim = FlowSimulation(m, n_chains=C, nparticles=32, dim=2, generator=torch.Generator(device=dev).manual_seed(5 + RANK))
