@@ -273,13 +273,14 @@ def _trajectories(m, q0, p0, use_graph, fold, tile_chain, path_len, calls=2):
         _fused.TILE_CHAIN = True
 
 
-def test_graph_replayed_tile_chains_reproduce_launch_by_launch_trajectories_bitwise():
+@pytest.mark.parametrize("n_tiles", [5, 2 * 148 + 9])
+def test_graph_replayed_tile_chains_reproduce_launch_by_launch_trajectories_bitwise(n_tiles):
     """Replayed as one CUDA graph the launches of an evaluation really overlap (in eager mode the host paces them): the
     tile-flag chain -- including the first backward launch hanging on the last forward launch, whose output is the
     backward's own x -- must give the launch-by-launch result bit for bit.  (Regression: the backward kernel used to
     prefetch the next tile's x before having seen that tile's flag.)"""
     m = _model(precision="bf16")
-    C = (2 * 148 + 9) * 128
+    C = n_tiles * 128              # 5 tiles: far fewer CTAs than SMs, i.e. many launches of the chain resident at once
     gen = torch.Generator(device="cuda").manual_seed(4)
     q0 = torch.randn(C, 64, device="cuda", generator=gen) * 0.5
     p0 = torch.randn(C, 64, device="cuda", generator=gen)

@@ -7,7 +7,7 @@ dev = torch.device("cuda")
 fl = [flows.NSF_CL(32, dim=2, K=8, B=3.0, hidden_dim=16, mask=[i % 2]) for i in range(8)]
 m = models.NormalizingFlowModel(models.GaussianPrior(64, device=dev), fl, device=dev).to(dev)
 for f in fl: f.psi.precision = "bf16"
-C = 5 * 128
+C = int(sys.argv[1]) if len(sys.argv) > 1 else 5 * 128
 gen = torch.Generator(device="cuda").manual_seed(4)
 q0 = torch.randn(C, 64, device="cuda", generator=gen) * 0.5
 p0 = torch.randn(C, 64, device="cuda", generator=gen)
