@@ -497,22 +497,27 @@ def hmc_block(a, sd, dev, world, rank):
                        "note": "the fused kernels keep the spline parameters and their gradients on chip: real traffic is "
                                "about 1.3 KB per chain and layer, and the evaluation is bound by the adjoint arithmetic "
                                "(issue slots / MUFU), not by HBM"}
-    # the replayed graph (launches really overlapping, tile by tile) must reproduce the launch-by-launch trajectory bit for bit
-    def small_traj(use_graph, chain):
-        _fused.TILE_CHAIN = chain
+    # the replayed graph (launches really overlapping, tile by tile) must reproduce the launch-by-launch trajectory bit for
+    # bit: (a) separate kick / drift launches, tile flags inside evaluations vs none; (b) the trajectory as ONE chain
+    # (leapfrog folded into the last backward launch, evaluations hanging on each other) vs the fold launch by launch
+    def small_traj(use_graph, chain, fold, chain_evals):
+        _fused.TILE_CHAIN, _fused.CHAIN_EVALS = ("always" if chain else False), chain_evals
         try:
-            s2 = FlowSimulation(model, n_chains=min(C, 8192), nparticles=SIZE, dim=DIM, init_pos=q0[:8192])
-            s2.use_graph = use_graph
+            s2 = FlowSimulation(model, n_chains=min(C, 32768), nparticles=SIZE, dim=DIM, init_pos=q0[:32768])
+            s2.use_graph, s2.fused_leapfrog = use_graph, fold
             s2.set_velocity(torch.ones_like(s2.position) * 0.3)
             qa, ua = s2.integration_step(path_len=3, dt=dt)
             qb, ub = s2.integration_step(path_len=3, dt=dt)
             torch.cuda.synchronize()
             return qa.clone(), ua.clone(), qb.clone(), ub.clone()
         finally:
-            _fused.TILE_CHAIN = True
-    ref_t = small_traj(False, False)
-    got_t = small_traj(True, True)
-    out["graph_replay_with_tile_flags_equals_launch_by_launch_bitwise"] = bool(all(torch.equal(x_, y_) for x_, y_ in zip(ref_t, got_t)))
+            _fused.TILE_CHAIN, _fused.CHAIN_EVALS = True, True
+    same = lambda a_, b_: bool(all(torch.equal(x_, y_) for x_, y_ in zip(a_, b_)))          # noqa: E731
+    out["graph_replay_with_tile_flags_equals_launch_by_launch_bitwise"] = same(small_traj(False, False, False, False),
+                                                                               small_traj(True, True, False, False))
+    out["trajectory_as_one_chain_equals_launch_by_launch_bitwise"] = same(small_traj(False, True, True, False),
+                                                                          small_traj(True, True, True, True))
+    out["leapfrog_folded_into_last_backward_launch"] = bool(sim.fused_leapfrog and sim._fused_leapfrog_ok(sim.position))
     if rank == 0:
         sub = q0[:2048]
         lp_f, g_f = _fused.flow_logp_and_grad(model, sub) if fused_path else _wide.flow_logp_and_grad(model, sub)

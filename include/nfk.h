@@ -254,15 +254,18 @@ int nfk_nsf_pairs_fused2(const float* x, float* out, float* logdet, const void* 
 /* The same launch as one link of a CHAIN of layer launches over the same rows on one stream (a whole flow, forward or
  * inverse): tile_flags_in / tile_flags_out [N / 128] int32 or NULL make the dependency between consecutive launches
  * per 128-row tile instead of per launch (rows are independent, nf/models.py:16-18).  With tile_flags_out the launch
- * sets flag t to 1 when rows [128 t, 128 t + 128) of out and logdet are complete; with tile_flags_in it does not wait
- * for the previous launch as a whole but takes tile t when flag t is set, and clears it.  The caller zeroes the flags
- * before the chain, passes each producer's tile_flags_out as the next launch's tile_flags_in, and NULL as the first
- * launch's tile_flags_in (that launch waits for the stream); weight images and biases must be complete before it. */
+ * stores tile_flag_epoch into flag t when rows [128 t, 128 t + 128) of out and logdet are complete; with
+ * tile_flags_in it does not wait for the previous launch as a whole but takes tile t when flag t >= tile_flag_epoch.
+ * Flags only grow: the caller zeroes them once, passes each producer's tile_flags_out as the next launch's
+ * tile_flags_in with the same epoch, raises the epoch (from 1) every time the same flag arrays are used again without
+ * an intervening stream-wide wait (consecutive evaluations of a trajectory), and passes NULL as tile_flags_in of the
+ * first launch (that launch waits for the stream); weight images and biases must be complete before it. */
 int nfk_nsf_pairs_fused2_chain(const float* x, float* out, float* logdet, const void* w1_img, const void* w2_img,
                                const void* w3_img, const float* b1, const float* b2, const float* b3, int64_t N,
                                int mask_col, float B, int inverse, int accumulate, int arith, int split,
                                float* dbg_params /*nullable*/, int8_t* dbg_bins /*nullable*/,
-                               int32_t* tile_flags_in /*nullable*/, int32_t* tile_flags_out /*nullable*/, void* stream);
+                               int32_t* tile_flags_in /*nullable*/, int32_t* tile_flags_out /*nullable*/,
+                               int tile_flag_epoch, void* stream);
 
 /* Gradient of one fused layer w.r.t. its input in ONE launch (csrc/nsf_fused_bwd.cu; hidden <= 128, size 32, dim 2,
  * K 8): recomputes the conditioner with the forward kernel's fp16 operands (same parameters, bit for bit), runs the
@@ -276,13 +279,12 @@ int nfk_nsf_pairs_fused2_chain(const float* x, float* out, float* logdet, const 
  * accumulator columns; transposed bf16 images: w3t_img [4][3][128 x 64] (pair of chunks p, K block: n = hidden
  * unit, k = parameter index within the pair, same order), w2t_img [2][128 x 64] (n = input unit, k = output unit),
  * w1t_img [2][32 x 64] (n = conditioning feature, k = hidden unit).
- * tile_flags_in / tile_flags_out [N / 128] int32 or NULL: per-tile dependency between consecutive launches of a chain
- * on one stream (rows are independent).  With tile_flags_out the launch sets flag t to 1 when rows [128 t, 128 t + 128)
- * of grad_x are complete; with tile_flags_in it does NOT wait for the previous launch as a whole (programmatic
- * dependent launch) but starts tile t when flag t is set, and clears the flag.  The caller zeroes the flags once
- * before the chain and must pass the producer's tile_flags_out as the consumer's tile_flags_in; the first launch of
- * a chain passes tile_flags_in = NULL (it waits for the stream), every other input of a flagged launch must be
- * complete before that first launch.
+ * tile_flags_in / tile_flags_out [N / 128] int32 or NULL, tile_flag_epoch >= 1: per-tile dependency between consecutive
+ * launches of a chain on one stream (rows are independent), as for nfk_nsf_pairs_fused2_chain: the launch stores the
+ * epoch into flag t when rows [128 t, 128 t + 128) of grad_x are complete; with tile_flags_in it does NOT wait for the
+ * previous launch as a whole (programmatic dependent launch) but starts tile t when flag t >= epoch.  A tile's x is
+ * only touched after its flag, so x may itself be produced inside the chain (the forward launches of the same
+ * evaluation).
  * Replaces autograd through NSF_CL.forward / inverse (nf/flows.py:227-253) for dL/dx, as the flow-preconditioned HMC
  * force evaluation needs it (nf/hmc.py:34-41, applications/src/systems.py:308-311). */
 int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, float grad_out_scale, const float* grad_logdet,
@@ -290,7 +292,7 @@ int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, float grad_ou
                             const void* w3_img, const void* w3t_img, const void* w2t_img,
                             const void* w1t_img, const float* b1, const float* b2, const float* b3,
                             int64_t N, int mask_col, float B, int inverse, int32_t* tile_flags_in /*nullable*/,
-                            int32_t* tile_flags_out /*nullable*/, void* stream);
+                            int32_t* tile_flags_out /*nullable*/, int tile_flag_epoch, void* stream);
 
 /* The same launch with the leapfrog update folded in (the launch that completes the force, i.e. the layer nearest the
  * data; reference applications/src/systems.py:331-336 drives kick / drift as separate tensor operations): after
@@ -298,15 +300,18 @@ int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, float grad_ou
  *   momentum += kick * F ;  position += drift * momentum   (drift = 0: kick only)
  * for the same row.  momentum, position [N, 64]; position may be x itself (a tile's reads of x are over by then).
  * With tile_flags_out the flag also covers momentum and position, so the first forward launch of the next
- * evaluation can hang on it (nfk_nsf_pairs_fused2_chain with that flag array as tile_flags_in). */
+ * evaluation can hang on it (nfk_nsf_pairs_fused2_chain with that flag array as tile_flags_in): that launch counts
+ * the next evaluation's epoch, which is what tile_flag_out_epoch is for. */
 int nfk_nsf_pairs_fused_bwd_leapfrog(const float* x, const float* grad_out, float grad_out_scale,
                                      const float* grad_logdet, float grad_logdet_const, float* grad_x,
                                      const void* w1_img, const void* w2_img, const void* w3_img,
                                      const void* w3t_img, const void* w2t_img, const void* w1t_img,
                                      const float* b1, const float* b2, const float* b3, int64_t N, int mask_col,
                                      float B, int inverse, int32_t* tile_flags_in /*nullable*/,
-                                     int32_t* tile_flags_out /*nullable*/, float* momentum /*nullable*/,
-                                     float* position /*nullable*/, float kick, float drift, void* stream);
+                                     int32_t* tile_flags_out /*nullable*/, int tile_flag_epoch,
+                                     int tile_flag_out_epoch /* stored into tile_flags_out; 0: tile_flag_epoch */,
+                                     float* momentum /*nullable*/, float* position /*nullable*/, float kick, float drift,
+                                     void* stream);
 
 /* ---- wide conditioner path (hidden width > 128; the class default is 800, nf/flows.py:216):
  * persistent warp-specialised tcgen05 GEMM  Y = act(A W^T + b)  over operands stored in HBM as

@@ -87,13 +87,14 @@ def packed_split(layer):
     return pk
 
 
-def _launch(layer, pk, x, out, logdet, n, inverse, accumulate, split, dbg_p=None, dbg_b=None, flags_in=None, flags_out=None):
+def _launch(layer, pk, x, out, logdet, n, inverse, accumulate, split, dbg_p=None, dbg_b=None, flags_in=None, flags_out=None,
+            epoch=1):
     dev = x.device
     if flags_in is not None or flags_out is not None:
         call("nfk_nsf_pairs_fused2_chain", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
              ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), n, layer._mask[0], float(layer.B), int(bool(inverse)),
              int(accumulate), _ops._arith(layer.arith), int(split), ptr(dbg_p), ptr(dbg_b), ptr(flags_in), ptr(flags_out),
-             stream_ptr(dev))
+             int(epoch), stream_ptr(dev))
     elif GENERATION == 2 or split:
         call("nfk_nsf_pairs_fused2", ptr(x), ptr(out), ptr(logdet), ptr(pk["w1"]), ptr(pk["w2"]), ptr(pk["w3"]),
              ptr(pk["b1"]), ptr(pk["b2"]), ptr(pk["b3"]), n, layer._mask[0], float(layer.B), int(bool(inverse)),
@@ -166,7 +167,7 @@ def run_debug(layer, x, inverse):
     return out[:n_real], logdet[:n_real], params[:n_real, :, :23].contiguous(), bins[:n_real]
 
 
-def run(layer, x, inverse, logdet=None, flags_in=None, flags_out=None):
+def run(layer, x, inverse, logdet=None, flags_in=None, flags_out=None, epoch=1):
     """(out, logdet) of one NSF_CL layer through the fused kernel (whole 128-row tiles; a partial last
     tile is padded).  flags_in / flags_out ([N / 128] int32, N a multiple of 128): per-tile dependency between the
     launches of a chain, see nfk_nsf_pairs_fused2_chain in include/nfk.h."""
@@ -183,7 +184,7 @@ def run(layer, x, inverse, logdet=None, flags_in=None, flags_out=None):
         with torch.cuda.device(dev):
             tm = _ops.KERNEL_TIMER
             ev = tm.start("nsf_pairs_fused3x" if _is_split(layer) else "nsf_pairs_fused", dev) if tm is not None else None
-            _launch(layer, pk, x, out, logdet, n_main, inverse, accumulate, _is_split(layer), None, None, flags_in, flags_out)
+            _launch(layer, pk, x, out, logdet, n_main, inverse, accumulate, _is_split(layer), None, None, flags_in, flags_out, epoch)
             if ev is not None:
                 tm.stop(ev, dev)
     if n_main < N:
@@ -210,7 +211,8 @@ def run(layer, x, inverse, logdet=None, flags_in=None, flags_out=None):
 TILE_CHAIN = True
 # ... and consecutive evaluations of a trajectory too (the first forward launch hangs on the previous evaluation's last
 # backward launch, which has advanced the position)
-CHAIN_EVALS = False         # (off: replayed as a CUDA graph such a trajectory does not reproduce the launch-by-launch result)
+CHAIN_EVALS = True
+_DEBUG_KEEP = None               # a list: every buffer of every evaluation stays allocated (no reuse across evaluations)
 _DEBUG_NO_FLAGS = False          # tools/ubench/dbg_traj.py: leapfrog fold with launch-by-launch dependencies
 
 
@@ -259,7 +261,7 @@ def packed_bwd(layer):
 
 
 def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=False, g_out_scale=1.0, flags_in=None,
-                   flags_out=None, keep_padding=False, leapfrog=None):
+                   flags_out=None, keep_padding=False, leapfrog=None, epoch=1, out_epoch=0):
     """dL/dx [N, 64] of one bwd_eligible layer from the layer input x, dL/d(out) = g_out_scale * g_out and dL/d(log_det)
     (a per-row tensor, or a constant for every row).  A partial last tile is zero-padded.  flags_in / flags_out
     ([N / 128] int32): per-tile dependency between the launches of a chain, see nfk_nsf_pairs_fused_bwd in include/nfk.h.
@@ -292,13 +294,13 @@ def layer_backward(layer, x, g_out, g_logdet=None, g_logdet_const=1.0, inverse=F
                  ptr(f32c(g_logdet)) if g_logdet is not None else ptr(None), float(g_logdet_const), ptr(g_in), ptr(pk["w1"]),
                  ptr(pk["w2"]), ptr(pb["w3"]), ptr(pb["w3t"]), ptr(pb["w2t"]), ptr(pb["w1t"]), ptr(pk["b1"]), ptr(pk["b2"]),
                  ptr(pb["b3"]), n_pad, layer._mask[0], float(layer.B), int(bool(inverse)), ptr(flags_in), ptr(flags_out),
-                 ptr(lp), ptr(lq), float(kick), float(drift), stream_ptr(dev))
+                 int(epoch), int(out_epoch), ptr(lp), ptr(lq), float(kick), float(drift), stream_ptr(dev))
         else:
             call("nfk_nsf_pairs_fused_bwd", ptr(x), ptr(g_out), float(g_out_scale),
                  ptr(f32c(g_logdet)) if g_logdet is not None else ptr(None), float(g_logdet_const), ptr(g_in), ptr(pk["w1"]),
                  ptr(pk["w2"]), ptr(pb["w3"]), ptr(pb["w3t"]), ptr(pb["w2t"]), ptr(pb["w1t"]), ptr(pk["b1"]), ptr(pk["b2"]),
                  ptr(pb["b3"]), n_pad, layer._mask[0], float(layer.B), int(bool(inverse)), ptr(flags_in), ptr(flags_out),
-                 stream_ptr(dev))
+                 int(epoch), stream_ptr(dev))
         if ev is not None:
             tm.stop(ev, dev)
     return g_in if keep_padding else g_in[:N]
@@ -312,9 +314,28 @@ def flow_eligible(model) -> bool:
             and all(isinstance(f, NSF_CL) and f.fused and bwd_eligible(f) for f in model.flows))
 
 
-def tile_chain_ok(model, n_rows) -> bool:
-    return (TILE_CHAIN and n_rows % ROWS == 0 and len(model.flows) > 1 and GENERATION == 2
-            and _lib.have("nfk_nsf_pairs_fused2_chain"))
+def tile_chain_ok(model, n_rows, dev=None) -> bool:
+    """Tile-flag chains pay when a launch has more tiles than the GPU has SMs (the chain turns the last, partial wave of
+    every launch into the first wave of the next); with a single partial wave the flag traffic is a net loss
+    (8,192 chains: 0.405 ms per evaluation without, 0.411 with)."""
+    if not (TILE_CHAIN and n_rows % ROWS == 0 and len(model.flows) > 1 and GENERATION == 2
+            and _lib.have("nfk_nsf_pairs_fused2_chain")):
+        return False
+    if TILE_CHAIN == "always":                      # tests: exercise the chains at any size
+        return True
+    if dev is None:
+        dev = next(model.parameters()).device
+    return n_rows // ROWS > _sm_count(dev)
+
+
+_SM_COUNT = {}
+
+
+def _sm_count(dev):
+    key = str(dev)
+    if key not in _SM_COUNT:
+        _SM_COUNT[key] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _SM_COUNT[key]
 
 
 def _tile_flags(model, dev, n_tiles, L):
@@ -328,15 +349,16 @@ def _tile_flags(model, dev, n_tiles, L):
 
 
 def flow_logp_and_grad(model, x, need_logp=True, leapfrog=None, hang_on_previous=False, next_hangs_on_this=False,
-                       zero_flags=True):
+                       zero_flags=True, epoch=1):
     """log p(x) [N] and d log p / dx [N, d] through a flow whose layers are all bwd_eligible, under an isotropic Gaussian
     prior: one forward launch per layer (keeping each layer's input), the log-prob reduction, one backward launch per
     layer; None when the model does not qualify.
     leapfrog = (momentum, position, kick, drift): the last backward launch also advances momentum and position
     (layer_backward).  hang_on_previous / next_hangs_on_this: consecutive evaluations of a trajectory form one tile-flag
     chain (the first forward launch of an evaluation takes tile t as soon as the previous evaluation's last backward
-    launch has advanced the position of tile t); zero_flags = False keeps the flags as the previous evaluation left
-    them (all consumed), so no fill kernel interrupts the chain."""
+    launch has advanced the position of tile t); such evaluations share the flag arrays without a fill kernel between
+    them (zero_flags = False) and therefore count epochs: flags only grow, evaluation number e of a trajectory waits
+    for and stores e + 1, so a launch that is resident early cannot take an earlier evaluation's flag for its own."""
     if not flow_eligible(model):
         return None
     var = model._prior_var()
@@ -346,7 +368,7 @@ def flow_logp_and_grad(model, x, need_logp=True, leapfrog=None, hang_on_previous
         packed(f)                  # not wait for the stream, so nothing but flagged tiles may be produced inside the chain
         packed_bwd(f)
     fw = bw = link = None
-    if tile_chain_ok(model, N) and not _DEBUG_NO_FLAGS:
+    if tile_chain_ok(model, N, h.device) and not _DEBUG_NO_FLAGS:
         # per-tile dependency between consecutive launches of the forward chain and of the backward chain (rows are
         # independent): a launch starts on the SMs the previous one has already left instead of waiting for its last wave
         flags = _tile_flags(model, h.device, N // ROWS, L)
@@ -363,7 +385,7 @@ def flow_logp_and_grad(model, x, need_logp=True, leapfrog=None, hang_on_previous
     for i, f in enumerate(model.flows):
         inputs.append(h)
         f_in = (fw[i - 1] if i > 0 else (link if hang_on_previous else None)) if fw is not None else None
-        h, logdet = run(f, h, False, logdet, f_in, fw[i] if (fw is not None and (i + 1 < L or join)) else None)
+        h, logdet = run(f, h, False, logdet, f_in, fw[i] if (fw is not None and (i + 1 < L or join)) else None, epoch)
     logp = _ops.gauss_logprob(h, var, add=logdet, add_sign=1.0) if need_logp else None
     g, scale = h, -1.0 / var                                  # d log N(z; 0, var I) / dz = -z / var, applied by the first launch
     keep = []                      # in a chain the launches overlap: no buffer of the evaluation is handed back to the
@@ -372,7 +394,10 @@ def flow_logp_and_grad(model, x, need_logp=True, leapfrog=None, hang_on_previous
         f_in = (bw[i - 1] if i > 0 else (fw[L - 1] if join else None)) if bw is not None else None
         f_out = (bw[i] if i + 1 < L else (link if next_hangs_on_this else None)) if bw is not None else None
         keep.append(g)
-        g = layer_backward(f, xin, g, None, 1.0, False, scale, f_in, f_out, leapfrog=leapfrog if i + 1 == L else None)
+        g = layer_backward(f, xin, g, None, 1.0, False, scale, f_in, f_out, leapfrog=leapfrog if i + 1 == L else None,
+                           epoch=epoch, out_epoch=(epoch + 1 if (i + 1 == L and next_hangs_on_this) else 0))
         scale = 1.0
+    if _DEBUG_KEEP is not None:
+        _DEBUG_KEEP.append((inputs, keep, logdet, h, g))
     del keep
     return logp, g

@@ -69,11 +69,11 @@ SIGNATURES = {
     "nfk_nsf_pairs_fused2": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int,
                                      c_int, c_int, _P, _P, _P]),
     "nfk_nsf_pairs_fused2_chain": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, c_int,
-                                           c_int, c_int, _P, _P, _P, _P, _P]),
+                                           c_int, c_int, _P, _P, _P, _P, c_int, _P]),
     "nfk_nsf_pairs_fused_bwd_leapfrog": (c_int, [_P, _P, c_float, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64,
-                                                 c_int, c_float, c_int, _P, _P, _P, _P, c_float, c_float, _P]),
+                                                 c_int, c_float, c_int, _P, _P, c_int, c_int, _P, _P, c_float, c_float, _P]),
     "nfk_nsf_pairs_fused_bwd": (c_int, [_P, _P, c_float, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int,
-                                        c_float, c_int, _P, _P, _P]),
+                                        c_float, c_int, _P, _P, c_int, _P]),
     "nfk_gemm_f32": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int64,
                              c_int, _P]),
     "nfk_gemm_ws_rows_per_tile": (c_int, []),

@@ -68,8 +68,9 @@ struct Fused2Args {
   int accumulate;
   float* dbg_params;
   signed char* dbg_bins;
-  int* flag_in;                  // [n_tiles] or null: tile t of x is complete when flag_in[t] != 0 (per-tile dependency on the producing launch)
-  int* flag_out;                 // [n_tiles] or null: set to 1 when tile t of out / logdet is complete
+  int* flag_in;                  // [n_tiles] or null: tile t of x is complete when flag_in[t] >= flag_epoch (per-tile dependency on the producing launch)
+  int* flag_out;                 // [n_tiles] or null: set to flag_epoch when tile t of out / logdet is complete
+  int flag_epoch;                // >= 1; the caller zeroes the flags before the first chain and raises the epoch from chain to chain
   RqsConsts c;
 };
 
@@ -496,7 +497,7 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
       const int s = it2 & 1;
       if (CHAIN && a.flag_in != nullptr) {                               // the producing launch has finished this tile
         if (lane == 0)
-          while (f2_ld_acquire(a.flag_in + tile2) == 0) __nanosleep(64);
+          while (f2_ld_acquire(a.flag_in + tile2) < a.flag_epoch) __nanosleep(64);
         __syncwarp();
         // ... and the bulk copy below (async proxy) sees what the flag publishes, also when the producer wrote it with
         // ordinary stores (generic proxy): a proxy fence over GLOBAL memory, not just shared
@@ -514,7 +515,7 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
       asm volatile("fence.proxy.async;" ::: "memory");       // the rows went out through the async proxy
       __threadfence();
       asm volatile("bar.sync 5, 512;" ::: "memory");
-      if (tid == 0) f2_st_release(a.flag_out + t_, 1);
+      if (tid == 0) f2_st_release(a.flag_out + t_, a.flag_epoch);
     };
     if (my_tiles) load_rows(0);
     if (my_tiles > 1) load_rows(1);
@@ -567,7 +568,6 @@ nsf_fused2_kernel(const __grid_constant__ Fused2Args a) {
         bulk_s2g(a.out + (tile * F2_ROWS + myrow) * 64, xs + myrow * F2_XLD, F2_XROW_BYTES);
         bulk_commit();
       }
-      if (CHAIN && a.flag_in != nullptr && tid == 0) a.flag_in[tile] = 0;      // consumed: back to 0 for the next chain of launches
       // refill this buffer with tile it + 2 as soon as the store has read it
       if (it + 2 < my_tiles) {
         if (lane < 8) bulk_wait_read<0>();
@@ -643,14 +643,14 @@ extern "C" int nfk_nsf_pairs_fused2(const float* x, float* out, float* logdet, c
                                     int mask_col, float B, int inverse, int accumulate, int arith, int split,
                                     float* dbg_params, int8_t* dbg_bins, void* stream) {
   return nfk_nsf_pairs_fused2_chain(x, out, logdet, w1_img, w2_img, w3_img, b1, b2, b3, N, mask_col, B, inverse, accumulate,
-                                    arith, split, dbg_params, dbg_bins, nullptr, nullptr, stream);
+                                    arith, split, dbg_params, dbg_bins, nullptr, nullptr, 1, stream);
 }
 
 extern "C" int nfk_nsf_pairs_fused2_chain(const float* x, float* out, float* logdet, const void* w1_img, const void* w2_img,
                                           const void* w3_img, const float* b1, const float* b2, const float* b3, int64_t N,
                                           int mask_col, float B, int inverse, int accumulate, int arith, int split,
                                           float* dbg_params, int8_t* dbg_bins, int32_t* tile_flags_in,
-                                          int32_t* tile_flags_out, void* stream) {
+                                          int32_t* tile_flags_out, int tile_flag_epoch, void* stream) {
   NFK_REQUIRE(N >= 0 && N % F2_ROWS == 0, "nsf_pairs_fused2: N must be a multiple of %d (got %lld)", F2_ROWS, (long long)N);
   NFK_REQUIRE(mask_col == 0 || mask_col == 1, "nsf_pairs_fused2: mask column must be 0 or 1");
   NFK_REQUIRE(arith >= NFK_ARITH_EXACT && arith <= NFK_ARITH_FAST, "nsf_pairs_fused2: bad arith %d", arith);
@@ -679,11 +679,13 @@ extern "C" int nfk_nsf_pairs_fused2_chain(const float* x, float* out, float* log
   a.dbg_bins = reinterpret_cast<signed char*>(dbg_bins);
   a.flag_in = tile_flags_in;
   a.flag_out = tile_flags_out;
+  a.flag_epoch = tile_flag_epoch;
   a.c = make_rqs_consts(8, B);
   cudaStream_t st = (cudaStream_t)stream;
   const bool inv = inverse != 0;
   if (tile_flags_in != nullptr || tile_flags_out != nullptr) {
     NFK_REQUIRE(!split && dbg_params == nullptr, "nsf_pairs_fused2_chain: tile flags go with the plain 16-bit kernel only (split = 0, no debug outputs)");
+    NFK_REQUIRE(tile_flag_epoch >= 1, "nsf_pairs_fused2_chain: the flag epoch starts at 1");
     return dispatch_fused2<false, false, true>(a, arith, inv, st);
   }
   if (dbg_params) return split ? dispatch_fused2<true, true>(a, arith, inv, st) : dispatch_fused2<false, true>(a, arith, inv, st);

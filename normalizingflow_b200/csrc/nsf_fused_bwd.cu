@@ -65,8 +65,11 @@ struct FusedBwdArgs {
   const float* b3;                // [32][24] in the order of w3_img's rows
   long long n_tiles;
   int cond_first;
-  int* flag_in;           // [n_tiles] or null: tile t may start when flag_in[t] != 0 (set by the launch that produces gout)
-  int* flag_out;          // [n_tiles] or null: set to 1 when tile t of gin (and of lf_p / lf_q) is complete
+  int* flag_in;           // [n_tiles] or null: tile t may start when flag_in[t] >= flag_epoch (set by the launch that produces gout)
+  int* flag_out;          // [n_tiles] or null: set to flag_epoch when tile t of gin (and of lf_p / lf_q) is complete
+  int flag_epoch;         // >= 1: flags only grow inside a sequence of chains, so a launch of a later chain that is already
+  //                         resident cannot mistake an earlier chain's flag for its own
+  int flag_out_epoch;     // what this launch stores: flag_epoch, or the NEXT evaluation's epoch when its first launch hangs on this one
   float* lf_p;            // leapfrog fold (null: off): p += lf_kick * gin ; lf_q += lf_drift * p  (lf_q may be x itself)
   float* lf_q;
   float lf_kick, lf_drift;
@@ -438,7 +441,7 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
       // ---- dL/d(out) of this tile is complete (per-tile dependency on the producing launch), first pair of it
       if (a.flag_in != nullptr) {
         if (lane == 0)
-          while (fb_ld_acquire(a.flag_in + tile) == 0) __nanosleep(64);
+          while (fb_ld_acquire(a.flag_in + tile) < a.flag_epoch) __nanosleep(64);
         __syncwarp();
       }
       gn = __ldcg(gor + slice);
@@ -492,7 +495,7 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
           // next tile: prefetch only if its flag is already up (non-blocking probe by lane 0)
           int up = 1;
           if (a.flag_in != nullptr) {
-            up = (lane == 0) ? fb_ld_acquire(a.flag_in + tile + stride) : 0;
+            up = (lane == 0) ? (fb_ld_acquire(a.flag_in + tile + stride) >= a.flag_epoch ? 1 : 0) : 0;
             __syncwarp();
             up = __shfl_sync(0xffffffffu, up, 0);
           }
@@ -631,15 +634,13 @@ nsf_fused_bwd_kernel(const __grid_constant__ FusedBwdArgs a) {
         }
       }
       FB_T(tr && slice == 0, 43);
-      if (a.flag_in != nullptr || a.flag_out != nullptr) {
+      if (a.flag_out != nullptr) {
         // every work thread's stores and reductions of this tile are ordered before the flag (fence, CTA barrier of the
-        // work warps, release store); the consumed input flag returns to 0 for the next chain of launches
+        // work warps, release store)
+        if (a.lf_p != nullptr) asm volatile("fence.proxy.async;" ::: "memory");   // the position may be read by the next launch's TMA
         __threadfence();
         asm volatile("bar.sync 5, 512;" ::: "memory");
-        if (tid == 0) {
-          if (a.flag_in != nullptr) a.flag_in[tile] = 0;
-          if (a.flag_out != nullptr) fb_st_release(a.flag_out + tile, 1);
-        }
+        if (tid == 0) fb_st_release(a.flag_out + tile, a.flag_out_epoch);
       }
     }
   }
@@ -670,24 +671,30 @@ extern "C" int nfk_nsf_pairs_fused_bwd_leapfrog(const float* x, const float* gra
                                                 const void* w3t_img, const void* w2t_img, const void* w1t_img,
                                                 const float* b1, const float* b2, const float* b3, int64_t N, int mask_col,
                                                 float B, int inverse, int32_t* tile_flags_in, int32_t* tile_flags_out,
-                                                float* momentum, float* position, float kick, float drift, void* stream);
+                                                int tile_flag_epoch, int tile_flag_out_epoch, float* momentum, float* position,
+                                                float kick, float drift, void* stream);
 
 extern "C" int nfk_nsf_pairs_fused_bwd(const float* x, const float* grad_out, float grad_out_scale, const float* grad_logdet,
                                        float grad_logdet_const, float* grad_x, const void* w1_img, const void* w2_img,
                                        const void* w3_img, const void* w3t_img, const void* w2t_img, const void* w1t_img,
                                        const float* b1, const float* b2, const float* b3, int64_t N, int mask_col, float B,
-                                       int inverse, int32_t* tile_flags_in, int32_t* tile_flags_out, void* stream) {
+                                       int inverse, int32_t* tile_flags_in, int32_t* tile_flags_out, int tile_flag_epoch,
+                                       void* stream) {
   return nfk_nsf_pairs_fused_bwd_leapfrog(x, grad_out, grad_out_scale, grad_logdet, grad_logdet_const, grad_x, w1_img, w2_img,
                                           w3_img, w3t_img, w2t_img, w1t_img, b1, b2, b3, N, mask_col, B, inverse,
-                                          tile_flags_in, tile_flags_out, nullptr, nullptr, 0.f, 0.f, stream);
+                                          tile_flags_in, tile_flags_out, tile_flag_epoch, tile_flag_epoch, nullptr, nullptr, 0.f,
+                                          0.f, stream);
 }
 
 extern "C" int nfk_nsf_pairs_fused_bwd_leapfrog(const float* x, const float* grad_out, float grad_out_scale, const float* grad_logdet,
                                        float grad_logdet_const, float* grad_x, const void* w1_img, const void* w2_img, const void* w3_img,
                                        const void* w3t_img, const void* w2t_img, const void* w1t_img, const float* b1,
                                        const float* b2, const float* b3, int64_t N, int mask_col, float B, int inverse,
-                                       int32_t* tile_flags_in, int32_t* tile_flags_out, float* momentum, float* position,
-                                       float kick, float drift, void* stream) {
+                                       int32_t* tile_flags_in, int32_t* tile_flags_out, int tile_flag_epoch,
+                                       int tile_flag_out_epoch, float* momentum, float* position, float kick, float drift,
+                                       void* stream) {
+  NFK_REQUIRE((tile_flags_in == nullptr && tile_flags_out == nullptr) || tile_flag_epoch >= 1,
+              "nsf_pairs_fused_bwd: the flag epoch starts at 1");
   NFK_REQUIRE((momentum == nullptr) == (position == nullptr), "nsf_pairs_fused_bwd: momentum and position go together");
   NFK_REQUIRE(N >= 0 && N % FB_ROWS == 0, "nsf_pairs_fused_bwd: N must be a multiple of %d (got %lld)", FB_ROWS, (long long)N);
   NFK_REQUIRE(mask_col == 0 || mask_col == 1, "nsf_pairs_fused_bwd: mask column must be 0 or 1");
@@ -720,6 +727,8 @@ extern "C" int nfk_nsf_pairs_fused_bwd_leapfrog(const float* x, const float* gra
   a.cond_first = (mask_col == 0);
   a.flag_in = tile_flags_in;
   a.flag_out = tile_flags_out;
+  a.flag_epoch = tile_flag_epoch;
+  a.flag_out_epoch = tile_flag_out_epoch >= 1 ? tile_flag_out_epoch : tile_flag_epoch;
   a.lf_p = momentum;
   a.lf_q = position;
   a.lf_kick = kick;

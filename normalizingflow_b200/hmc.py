@@ -157,9 +157,8 @@ class FlowSimulation:
         self.grad_evals = 0
         self.tensor_core_grad = True      # bf16-conditioner models: hand-written forward+backward path
         self.fused_grad = True            # ... through the one-launch-per-layer kernels when hidden width <= 128
-        self.fused_leapfrog = False       # ... with kick / drift folded into the last backward launch of every evaluation
-        #                                   (nfk_nsf_pairs_fused_bwd_leapfrog; measured 1 % slower than the two element-wise
-        #                                   launches it replaces, so off by default)
+        self.fused_leapfrog = True        # ... with kick / drift folded into the last backward launch of every evaluation and
+        #                                   the next evaluation's first launch hanging on it: one chain per trajectory
         self.use_graph = True             # replay whole trajectories as one CUDA graph on that path
         self._graphs = {}
 
@@ -237,7 +236,8 @@ class FlowSimulation:
             logp, _ = _fused.flow_logp_and_grad(self.model, q, need_logp=last, leapfrog=(p, q, kick, drift),
                                                 hang_on_previous=(i > 0 and _fused.CHAIN_EVALS),
                                                 next_hangs_on_this=(not last and _fused.CHAIN_EVALS),
-                                                zero_flags=(i == 0))
+                                                zero_flags=(i == 0 or not _fused.CHAIN_EVALS),
+                                                epoch=(i + 1 if _fused.CHAIN_EVALS else 1))
             self.grad_evals += 1
         return -logp
 

@@ -234,7 +234,7 @@ def test_tile_chained_launches_equal_launch_by_launch_dependency_bitwise():
     """65,536 x 64 rows would be the production shape; 3 x 148 + 5 tiles are enough to have CTAs with different
     tile counts.  With tile flags a launch starts tile t when the producing launch has finished tile t (rows are
     independent): forces and log-probs must not change by a bit, with and without the log-prob reduction in the
-    middle of the chain, and the flags must be back at zero afterwards."""
+    middle of the chain."""
     from normalizingflow_b200 import _fused
     m = _model(precision="bf16")
     N = (3 * 148 + 5) * 128
@@ -242,14 +242,13 @@ def test_tile_chained_launches_equal_launch_by_launch_dependency_bitwise():
     try:
         _fused.TILE_CHAIN = False
         lp0, g0 = _fused.flow_logp_and_grad(m, x)
-        _fused.TILE_CHAIN = True
+        _fused.TILE_CHAIN = "always"
         for _ in range(3):
             lp1, g1 = _fused.flow_logp_and_grad(m, x)
             lp2, g2 = _fused.flow_logp_and_grad(m, x, need_logp=False)
             assert lp2 is None
             assert torch.equal(lp0, lp1) and torch.equal(g0, g1) and torch.equal(g0, g2)
         torch.cuda.synchronize()
-        assert int(m._fused_tile_flags[1].abs().sum()) == 0
     finally:
         _fused.TILE_CHAIN = True
 
@@ -257,7 +256,7 @@ def test_tile_chained_launches_equal_launch_by_launch_dependency_bitwise():
 def _trajectories(m, q0, p0, use_graph, fold, tile_chain, path_len, calls=2):
     from normalizingflow_b200 import _fused
     from normalizingflow_b200.hmc import FlowSimulation
-    _fused.TILE_CHAIN = tile_chain
+    _fused.TILE_CHAIN = "always" if tile_chain else False      # "always": also below one wave of tiles
     try:
         sim = FlowSimulation(m, n_chains=q0.shape[0], init_pos=q0)
         sim.use_graph, sim.fused_leapfrog = use_graph, fold
@@ -289,27 +288,40 @@ def test_graph_replayed_tile_chains_reproduce_launch_by_launch_trajectories_bitw
         got = _trajectories(m, q0, p0, use_graph=use_graph, fold=False, tile_chain=True, path_len=3)
         for a, b in zip(ref, got):
             assert all(torch.equal(x, y) for x, y in zip(a, b)), use_graph
-    assert int(m._fused_tile_flags[1].abs().sum()) == 0
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_leapfrog_folded_into_the_last_backward_launch_matches_separate_kick_and_drift(use_graph):
-    """Kick / drift inside the launch that completes the force against separate kick / drift launches: bit-identical
-    for one step (no interior point); over several steps the two half kicks around an interior point are one fused
-    multiply-add, and the dynamics amplify that rounding difference (d log|det| / dx jumps across knots)."""
+@pytest.mark.parametrize("n_tiles", [5, 148 + 7])
+def test_leapfrog_folded_into_the_last_backward_launch_and_trajectory_as_one_chain(use_graph, n_tiles):
+    """Kick / drift inside the launch that completes the force, the next evaluation's first forward launch hanging on
+    it tile by tile (flags count evaluation epochs): (a) bit-identical to separate kick / drift launches for one step
+    (no interior point); (b) over several steps bit-identical to the fold WITHOUT chaining consecutive evaluations
+    (the two half kicks around an interior point are one fused multiply-add in both), also replayed as a graph with
+    far fewer tiles than SMs, where launches of several evaluations are resident at once; (c) close to the separate
+    launches over several steps (the dynamics amplify the rounding difference of (b))."""
+    from normalizingflow_b200 import _fused
     m = _model(precision="bf16")
-    C = 5 * 128
+    C = n_tiles * 128
     gen = torch.Generator(device="cuda").manual_seed(4)
     q0 = torch.randn(C, 64, device="cuda", generator=gen) * 0.5
     p0 = torch.randn(C, 64, device="cuda", generator=gen)
-    for path_len, tol in ((1, 0.0), (6, 2e-2)):
-        ref = _trajectories(m, q0, p0, use_graph=False, fold=False, tile_chain=True, path_len=path_len)
-        got = _trajectories(m, q0, p0, use_graph=use_graph, fold=True, tile_chain=True, path_len=path_len)
-        for a, b in zip(ref, got):
-            for x, y in zip(a, b):
-                assert torch.isfinite(y).all()
-                assert float((x - y).abs().max()) <= tol * (1.0 + float(x.abs().max())), (path_len, float((x - y).abs().max()))
-    assert int(m._fused_tile_flags[1].abs().sum()) == 0
+    sep1 = _trajectories(m, q0, p0, use_graph=False, fold=False, tile_chain=True, path_len=1)
+    sep6 = _trajectories(m, q0, p0, use_graph=False, fold=False, tile_chain=True, path_len=6)
+    try:
+        _fused.CHAIN_EVALS = False
+        fold6 = _trajectories(m, q0, p0, use_graph=False, fold=True, tile_chain=True, path_len=6)
+    finally:
+        _fused.CHAIN_EVALS = True
+    one1 = _trajectories(m, q0, p0, use_graph=use_graph, fold=True, tile_chain=True, path_len=1)
+    one6 = _trajectories(m, q0, p0, use_graph=use_graph, fold=True, tile_chain=True, path_len=6)
+    for a, b in zip(sep1, one1):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+    for a, b in zip(fold6, one6):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+    for a, b in zip(sep6, one6):
+        for x, y in zip(a, b):
+            assert torch.isfinite(y).all()
+            assert float((x - y).abs().max()) <= 2e-2 * (1.0 + float(x.abs().max())), float((x - y).abs().max())
 
 
 def test_single_chain_eager_rejection_restores_the_position():

@@ -22,23 +22,9 @@ def run(graph, fold, chain_evals, n=2, path_len=6):
         outs.append((q.clone(), U.clone(), sim.velocity.clone()))
     torch.cuda.synchronize()
     return outs
-ref = run(False, False, False)
-for pl in (1, 6):
-    r = run(True, False, False, path_len=pl)
-    rf = run(False, False, False, path_len=pl)
-    d = [max(float((a - b).abs().max()) for a, b in zip(x, y)) for x, y in zip(r, rf)]
-    print(f"graph=True fold=False (tile flags inside evaluations) path_len={pl}: max diff per call {d}", flush=True)
-_fused._DEBUG_NO_FLAGS = True
-for pl in (1, 6):
-    r = run(True, True, False, path_len=pl)
-    rf = run(False, False, False, path_len=pl)
-    d = [max(float((a - b).abs().max()) for a, b in zip(x, y)) for x, y in zip(r, rf)]
-    print(f"graph=True fold=True NO FLAGS path_len={pl}: max diff per call {d}", flush=True)
-_fused._DEBUG_NO_FLAGS = False
 for graph in (False, True):
-    for fold, ce in ((True, False), (True, True)):
-        for pl in (1, 6):
-            r = run(graph, fold, ce, path_len=pl)
-            rf = run(False, False, False, path_len=pl)
-            d = [max(float((a - b).abs().max()) for a, b in zip(x, y)) for x, y in zip(r, rf)]
-            print(f"graph={graph} fold={fold} chain_evals={ce} path_len={pl}: max diff per call {d}", flush=True)
+    for pl in (1, 6):
+        r = run(graph, True, True, path_len=pl)
+        rf = run(False, True, False, path_len=pl)
+        d = [max(float((a - b).abs().max()) for a, b in zip(x, y)) for x, y in zip(r, rf)]
+        print(f"C={C} graph={graph} fold=True chain_evals=True vs fold without chaining, path_len={pl}: max diff per call {d}", flush=True)
