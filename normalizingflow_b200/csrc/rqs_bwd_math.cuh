@@ -311,118 +311,15 @@ __device__ __forceinline__ void rqs_element_bwd(const P& p, float x, float gy, f
     if (i < K - 1) gp[2 * K + i] = (i == k - 1 ? gD0 : 0.f) + (i == k ? gD1 : 0.f);
 }
 
-// K = 8, fast-math variant organised for a SMALL LIVE SET (the one-launch layer backward, nsf_fused_bwd.cu, runs it
-// at 96 registers per thread): the searched side goes first (its knots give the bin and are dropped at once), the
-// other side never materialises its knots (the two the bin needs are picked out of the running sum), and every
-// gradient group is written as soon as it is complete.  Same arithmetic as rqs_element_bwd<8, true> except the
-// shift of the second softmax, which is 2B / sum (= 2B max_j a_j, the argmax term being exp(0) / sum) instead of a
-// running maximum.  INV is the transform direction (searched side: heights when inverting, utils.py:89-96).
-__device__ __forceinline__ void side_softmaxes8(const float* raw, float* a, float* b, const RqsConsts& c) {
-  float m = raw[0];
-#pragma unroll
-  for (int j = 1; j < 8; ++j) m = fmaxf(m, raw[j]);
-  const float ml = m * LOG2E;
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    a[j] = ex2_approx(fmaf(raw[j], LOG2E, -ml));
-    s += a[j];
-  }
-  const float rs = rcp_approx(s);
-  const float m2 = c.g0 * rs;                      // 2B log2(e) max_j a_j
-  float s2 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    a[j] *= rs;
-    b[j] = ex2_approx(fmaf(c.g0, a[j], -m2));
-    s2 += b[j];
-  }
-  const float rs2 = rcp_approx(s2);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) b[j] *= rs2;
-}
-
-template <bool INV, class P>
-__device__ __forceinline__ void rqs_element_bwd8_lean(const P& p, float x, float gy, float gl, const RqsConsts& c,
-                                                      float& gx_out, float* gp) {
-  constexpr int K = 8;
-  if (!((x >= c.negB) && (x <= c.B))) {            // identity tails (utils.py:42-43)
-    gx_out = gy;
-#pragma unroll
-    for (int i = 0; i < 3 * K - 1; ++i) gp[i] = 0.f;
-    return;
-  }
-  constexpr int SOFF = INV ? K : 0, OOFF = INV ? 0 : K;      // searched / other side: offsets into raw and gp
-  float as[K], bs[K], ao[K], bo[K];
-  int k = 0;
-  float s0, s1, o0, o1;
-  {
-    float raw[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) raw[i] = p(SOFF + i);
-    side_softmaxes8(raw, as, bs, c);
-    float kn[K + 1];
-    float run = 0.f;
-    kn[0] = c.negB;
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      run += c.min_bin + c.one_m * bs[j];
-      kn[j + 1] = c.twoB * run + c.negB;
-    }
-    kn[K] = c.B;
-#pragma unroll
-    for (int i = 1; i < K; ++i) k += (x >= kn[i]) ? 1 : 0;
-    k += (x >= c.Bnudge) ? 1 : 0;
-    k = min(k, K - 1);
-    s0 = kn[0];
-    s1 = kn[1];
-#pragma unroll
-    for (int i = 1; i < K; ++i)
-      if (k == i) {
-        s0 = kn[i];
-        s1 = kn[i + 1];
-      }
-  }
-  {
-    float raw[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) raw[i] = p(OOFF + i);
-    side_softmaxes8(raw, ao, bo, c);
-    float run = 0.f;
-    o0 = c.negB;
-    o1 = c.B;
-#pragma unroll
-    for (int j = 0; j < K - 1; ++j) {               // interior knots 1..7
-      run += c.min_bin + c.one_m * bo[j];
-      const float kn = c.twoB * run + c.negB;
-      if (k == j + 1) o0 = kn;
-      if (k == j) o1 = kn;
-    }
-  }
-  const int i0 = max(k - 1, 0), i1 = min(k, K - 2);
-  const float dr0 = p.dyn(2 * K, i0), dr1 = p.dyn(2 * K, i1);
-  const float D20 = (k == 0) ? c.edge_c : Bm<true>::softplus(dr0);
-  const float D21 = (k == K - 1) ? c.edge_c : Bm<true>::softplus(dr1);
-  const float d0 = c.min_d + Bm<true>::softplus(D20), d1 = c.min_d + Bm<true>::softplus(D21);
-  float gxv, gc0, gc1, ge0, ge1, gd0, gd1;
-  rq_segment_bwd<true>(INV, x, INV ? o0 : s0, INV ? o1 : s1, INV ? s0 : o0, INV ? s1 : o1, d0, d1, gy, gl, gxv, gc0,
-                       gc1, ge0, ge1, gd0, gd1);
-  gx_out = gxv;
-  side_backward<K>(as, bs, k, INV ? ge0 : gc0, INV ? ge1 : gc1, gp + SOFF, c);
-  side_backward<K>(ao, bo, k, INV ? gc0 : ge0, INV ? gc1 : ge1, gp + OOFF, c);
-  const float gD0 = (k > 0) ? gd0 * Bm<true>::sigmoid(D20) * Bm<true>::sigmoid(dr0) : 0.f;
-  const float gD1 = (k < K - 1) ? gd1 * Bm<true>::sigmoid(D21) * Bm<true>::sigmoid(dr1) : 0.f;
-#pragma unroll
-  for (int i = 0; i < K - 1; ++i) gp[2 * K + i] = (i == k - 1 ? gD0 : 0.f) + (i == k ? gD1 : 0.f);
-}
-
-// ---- the same adjoint with the two sides PACKED (width side in the low, height side in the high half of fp32x2
-// registers: FFMA2 / FADD2 / FMUL2 do both softmax chains, forward and backward, in one instruction stream).  The raw
+// ---- K = 8, fast-math adjoint with the two sides PACKED (width side in the low, height side in the high half of fp32x2
+// registers: FFMA2 / FADD2 / FMUL2 do both softmax chains, forward and backward, in one instruction stream), organised
+// for a small live set (the one-launch layer backward, nsf_fused_bwd.cu, runs it at 96 registers per thread).  The raw
 // parameters arrive interleaved: v[2j] = width logit j, v[2j+1] = height logit j, v[16+i] = derivative logit i (the
 // one-launch layer backward permutes the rows of its W3 image accordingly), `b` the bias in the same order.
-// Differences from rqs_element_bwd8_lean, all inside the fast-math class: knots come from the prefix sums of the
-// normalised bins (knot_j = q0 cum_j + kstep j - B), and the dot product of the second softmax's backward is taken
-// from the two selected knots (sum_{i<k} b_i and b_k) instead of a sum over the bins.
+// Differences from rqs_element_bwd<8, true>, all inside the fast-math class: the shift of the second softmax is
+// 2B / sum (= 2B max_j a_j, the argmax term being exp(0) / sum) instead of a running maximum, knots come from the
+// prefix sums of the normalised bins (knot_j = q0 cum_j + kstep j - B), and the dot product of the second softmax's
+// backward is taken from the two selected knots (sum_{i<k} b_i and b_k) instead of a sum over the bins.
 struct PairRegParams {
   const uint32_t* v;
   const float* b;
