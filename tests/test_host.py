@@ -326,3 +326,14 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+
+
+def test_backward_kernel_parameter_row_order_interleaves_width_and_height_logits():
+    """csrc/nsf_fused_bwd.cu reads a feature's width / height logit pair from adjacent accumulator columns (packed
+    fp32x2 arithmetic): the host permutes the 24 padded parameter rows of W3 / b3 accordingly."""
+    from normalizingflow_b200 import _fused
+    order = _fused._BWD_ROW_ORDER
+    assert sorted(order) == list(range(24))
+    assert [order[2 * j] for j in range(8)] == list(range(8))               # width logits (nf/utils.py:27-33: W first)
+    assert [order[2 * j + 1] for j in range(8)] == list(range(8, 16))       # height logits
+    assert order[16:] == list(range(16, 24))                                # derivative logits + the padding row
