@@ -11,7 +11,11 @@
 //               bf16 A operand G in shared memory (8 features = 192 columns = 3 K blocks per pair of chunks)
 //   per pair    dH2 += G W3_pair        (B operand: W3 transposed, streamed through the ring; accumulates in TMEM)
 //   then        dZ2 = dH2 (1 - h2^2) -> GEMM with W2^T -> dH1 ;  dZ1 = dH1 (1 - h1^2) -> GEMM with W1^T -> dXc
-//               dL/dx[:, cond] += dXc                                                    (red.global.add)
+//               dL/dx[:, cond] += dXc      (red.global.add after a 32 x 32 transpose per lane quadrant through the idle G
+//               buffer; or, with the leapfrog fold, the thread that completes a pair also advances momentum / position)
+//
+// Chains: with tile flags (flag_in / flag_out / flag_epoch) consecutive launches depend on each other per 128-row tile
+// instead of per launch -- see include/nfk.h and the comment at griddepcontrol below.
 //
 // The forward GEMMs use exactly the fp16 operands and MMA order of nsf_fused2_kernel (the rows of W3 permuted so
 // that a feature's width and height logits arrive interleaved), so the recomputed parameters are the forward
