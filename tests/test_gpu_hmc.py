@@ -253,6 +253,27 @@ def test_tile_chained_launches_equal_launch_by_launch_dependency_bitwise():
         _fused.TILE_CHAIN = True
 
 
+def test_force_at_the_full_chain_count_is_row_independent_and_chain_invariant():
+    """BASELINE config 5's size (65,536 chains): a permuted batch gives the permuted log-probs and forces bit for bit
+    (every row sees the same arithmetic wherever it sits: tile, CTA, wave), with tile-flag chains and without."""
+    from normalizingflow_b200 import _fused
+    m = _model(precision="bf16")
+    C = 65536
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x = 0.8 * torch.randn(C, 64, device="cuda", generator=gen)
+    perm = torch.randperm(C, device="cuda", generator=gen)
+    lp, g = _fused.flow_logp_and_grad(m, x)
+    lp_p, g_p = _fused.flow_logp_and_grad(m, x[perm].contiguous())
+    assert torch.equal(lp[perm], lp_p) and torch.equal(g[perm], g_p)
+    try:
+        _fused.TILE_CHAIN = False
+        lp_n, g_n = _fused.flow_logp_and_grad(m, x)
+    finally:
+        _fused.TILE_CHAIN = True
+    assert torch.equal(lp, lp_n) and torch.equal(g, g_n)
+    assert torch.isfinite(g).all() and torch.isfinite(lp).all()
+
+
 def _trajectories(m, q0, p0, use_graph, fold, tile_chain, path_len, calls=2):
     from normalizingflow_b200 import _fused
     from normalizingflow_b200.hmc import FlowSimulation

@@ -337,3 +337,30 @@ def test_backward_kernel_parameter_row_order_interleaves_width_and_height_logits
     assert [order[2 * j] for j in range(8)] == list(range(8))               # width logits (nf/utils.py:27-33: W first)
     assert [order[2 * j + 1] for j in range(8)] == list(range(8, 16))       # height logits
     assert order[16:] == list(range(16, 24))                                # derivative logits + the padding row
+
+
+def test_flow_eligibility_for_the_one_launch_gradient_path_is_decided_on_the_host():
+    """_fused.flow_eligible: every layer an NSF_CL(32, dim 2, K 8, hidden <= 128) with a 16-bit conditioner on the fused
+    path, under an isotropic zero-mean Gaussian prior -- no kernel is launched to find out."""
+    import torch
+    from normalizingflow_b200 import _fused, flows, models
+    if not _fused._lib.have("nfk_nsf_pairs_fused_bwd"):
+        return
+
+    def make(H, prec, K=8):
+        fl = [flows.NSF_CL(32, dim=2, K=K, B=3.0, hidden_dim=H, mask=[i % 2]) for i in range(2)]
+        for f in fl:
+            f.psi.precision = prec
+        return models.NormalizingFlowModel(models.GaussianPrior(64), fl)
+    assert _fused.flow_eligible(make(128, "bf16")) and _fused.flow_eligible(make(16, "bf16"))
+    assert not _fused.flow_eligible(make(200, "bf16"))          # wide conditioner: the multi-launch path
+    assert not _fused.flow_eligible(make(128, "fp32"))          # parity mode: autograd through the fp32 kernels
+    assert not _fused.flow_eligible(make(128, "bf16", K=4))
+    m = make(128, "bf16")
+    m.flows[1].fused = False
+    assert not _fused.flow_eligible(m)
+    mvn = torch.distributions.MultivariateNormal(torch.zeros(64), 0.25 * torch.eye(64))
+    m2 = models.NormalizingFlowModel(mvn, list(make(64, "bf16").flows))
+    assert _fused.flow_eligible(m2)                             # what the reference builds (applications/src/setup.py:25-30)
+    m3 = models.NormalizingFlowModel(torch.distributions.MultivariateNormal(torch.ones(64), torch.eye(64)), list(make(64, "bf16").flows))
+    assert not _fused.flow_eligible(m3)
